@@ -1,0 +1,267 @@
+#!/usr/bin/env python
+"""bench.py — megapixels/s of the raw->sRGB hot path (BASELINE.json metric) on N B200s.
+
+  python bench.py --gpus N --steps K --warmup W            our arm (CUDA, through the C ABI)
+  python bench.py --impl reference --steps K --warmup W    the reference's CPU path (oracle port) on host cores
+
+Workload (config.workload): BASELINE config 2 — 6000x4000 RGGB Bayer frames, full pipe to 8-bit sRGB
+(gofloat -> demosaic -> to_lab -> basecurve -> from_lab -> gamma -> pack).  A step is one pass of the hot path
+over a batch of FRAMES_PER_STEP frames that rotate through NSETS distinct input/output buffer sets
+(NSETS * 120 MB > the 126 MB L2, so no frame is served from cache).  At N > 1 every rank runs the same batch on
+its own GPU (frames are independent: no data-path collective, scaling "weak"); value = total MP/s.
+
+One JSON line on stdout (rank 0).  See DESIGN.md "Measurement" for the roofline arithmetic.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+W, H = 6000, 4000
+MP = W * H / 1e6
+CFA = "RGGB"
+NSETS = 8
+FRAMES_PER_STEP = 32
+ALGO_BYTES_PER_PX = 5  # 2 B in (u16 CFA sample) + 3 B out (u8 sRGB) — SURVEY.md §8d
+METRIC = "megapixels/sec raw->sRGB full pipe"
+
+
+def workload_params():
+    import common
+    return common.raw_params(cfa=CFA)
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self._stop_evt = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            self.ok = False
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20,
+                 "hw_power_brake_slowdown": 0x80, "applications_clocks_setting": 0x2, "sync_boost": 0x10}
+        while not self._stop_evt.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
+                    else nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            time.sleep(0.002)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=2)
+        med = float(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def pinned_array(ip, nbytes, dtype, shape):
+    p = C.c_void_p()
+    rc = ip.lib().ipb_host_alloc(nbytes, C.byref(p))
+    if rc != 0:
+        raise RuntimeError("ipb_host_alloc failed")
+    buf = (C.c_uint8 * nbytes).from_address(p.value)
+    return np.frombuffer(buf, dtype=dtype).reshape(shape), p
+
+
+def cpu_reference_leg(steps, warmup, frames_note=True):
+    """Times the oracle's op-by-op CPU pipeline (same pass structure as the reference) on all host cores."""
+    import common
+    import oracle
+    oracle.build()
+    L = oracle.lib()
+    L.orc_set_threads(0)
+    cores = L.orc_get_threads()
+    data = common.synth_cfa(W, H)
+    p = oracle.make_pipeline(data, "raw", workload_params())
+    for _ in range(warmup):
+        oracle.pipeline_output_8bit(p)
+    times = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        oracle.pipeline_output_8bit(p)
+        times.append(time.perf_counter() - t0)
+    per = float(np.mean(times))
+    return {"value": MP / per, "unit": "MP/s", "cores": int(cores), "kind": "port",
+            "sample": f"{steps} x one 6000x4000 RGGB frame, output_8bit, OpenMP row-parallel C port of the reference "
+                      f"CPU path (Rust toolchain absent)", "ms_per_frame": per * 1e3}
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    steps, warmup = max(1, min(args.steps, 12)), max(1, min(args.warmup, 2))
+    cb = cpu_reference_leg(steps, warmup)
+    line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "MP/s", "n_gpus": args.gpus,
+            "steps": steps, "warmup": warmup, "ms_per_step": cb["ms_per_frame"], "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "C2: 6000x4000 RGGB Bayer -> 8-bit sRGB, one frame per step on host cores",
+                       "frames_per_step": 1},
+            "cpu_baseline": cb,
+            "e2e": {"value": cb["value"], "unit": "MP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--frames-per-step", type=int, default=FRAMES_PER_STEP)
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import common
+    import imagepipe_b200 as ip
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    stream = torch.cuda.Stream()
+    ctx = ip.Context(local_rank, stream.cuda_stream)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    K, Wm, F = args.steps, max(3, args.warmup), args.frames_per_step
+    params = workload_params()
+    # NSETS distinct synthetic frames, generated on the device, and NSETS output buffers
+    frames = [ip.synth_cfa_u16(common.SEED + rank * 1000 + i, W, 0, H, ctx=ctx) for i in range(NSETS)]
+    outs = [ip.DeviceArray(W * H * 3, ctx) for _ in range(NSETS)]
+    pipes = []
+    for i in range(NSETS):
+        src = ip.ImageSource.Raw(frames[i], width=W, height=H, cpp=1)
+        p = ip.Pipeline.new_from_source(src, ctx=ctx)
+        common.fill_ipb_ops(p.ops, params)
+        pipes.append(p)
+
+    def step():
+        for j in range(F):
+            pipes[j % NSETS].output_8bit(dst=outs[j % NSETS])
+
+    for _ in range(Wm):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = ctx.launch_count
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(K + 1)]
+    with torch.cuda.stream(stream):
+        ev[0].record(stream)
+        for k in range(K):
+            step()
+            ev[k + 1].record(stream)
+    barrier()
+    clocks = sampler.stop()
+    launches = ctx.launch_count - launches0
+    total_ms = ev[0].elapsed_time(ev[K])
+    step_ms = [ev[k].elapsed_time(ev[k + 1]) for k in range(K)]
+    t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms_max = float(t.item())
+    value = world * K * F * MP / (total_ms_max / 1e3)
+
+    # ---- e2e: the same metric through Pipeline.output_8bit with HOST buffers (pinned), copies inside the timed region
+    e2e_frames, e2e_steps = 4, max(3, K // 10)
+    host_in, hp_in = pinned_array(ip, W * H * 2, np.uint16, (H, W))
+    host_out, hp_out = pinned_array(ip, W * H * 3, np.uint8, (H, W, 3))
+    host_in[:] = frames[0].to_numpy()
+    pe = ip.Pipeline.new_from_source(ip.ImageSource.Raw(host_in), ctx=ctx)
+    common.fill_ipb_ops(pe.ops, params)
+    for _ in range(2):
+        pe.output_8bit(dst=host_out)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        for _ in range(e2e_frames):
+            pe.output_8bit(dst=host_out)  # H2D + kernel + D2H, synchronous at return
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    te = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = world * e2e_steps * e2e_frames * MP / float(te.item())
+    # result check on the last e2e frame: the device-resident path produced the same bytes
+    same = bool(np.array_equal(host_out, outs[0].to_numpy(np.uint8, (H, W, 3))))
+
+    if rank == 0:
+        peak, peak_kind = measured_peak()
+        kernel_ms = float(np.mean(step_ms)) / F  # one fused launch per frame, nothing else in the step
+        achieved = ALGO_BYTES_PER_PX * W * H / (kernel_ms / 1e3) / 1e9
+        line = {
+            "metric": METRIC, "value": value, "unit": "MP/s", "n_gpus": world, "steps": K, "warmup": Wm,
+            "ms_per_step": total_ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "C2: 6000x4000 RGGB Bayer -> 8-bit sRGB, fused demosaic->gamma kernel",
+                       "frames_per_step": F, "buffer_sets": NSETS,
+                       "l2": f"inputs larger than L2: {NSETS} rotating sets x 120 MB",
+                       "parallelism": f"frames round-robin, {world} replica(s), no collective"},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "kernel": "k_fused_full<u8>", "kernel_ms": kernel_ms, "peak_kind": peak_kind,
+                         "algorithmic_bytes_per_launch": ALGO_BYTES_PER_PX * W * H},
+            "e2e": {"value": e2e_value, "unit": "MP/s", "h2d_bytes_per_step": e2e_frames * W * H * 2,
+                    "d2h_bytes_per_step": e2e_frames * W * H * 3, "steps": e2e_steps, "frames_per_step": e2e_frames,
+                    "matches_device_path": same},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+        }
+        if not args.no_cpu_baseline and world == 1:
+            line["cpu_baseline"] = cpu_reference_leg(3, 1)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

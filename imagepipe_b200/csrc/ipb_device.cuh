@@ -1,0 +1,224 @@
+// ipb_device.cuh — per-pixel device arithmetic of the raw->sRGB hot path.
+//
+// Exactness discipline (DESIGN.md "Numerics"): this translation unit set is compiled with
+// -fmad=false, so `a*b + c` is two IEEE roundings exactly like the reference (Rust never contracts
+// to FMA).  fmaf() is used only inside div_rc(), a 3-instruction division by a constant that is
+// proven bit-identical to IEEE division by exhaustion (tools/verify_constdiv.c).  All constants are
+// f32-evaluated the way the reference evaluates them (color_conversions.rs:121-122,181-182).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace ipb {
+
+constexpr int kLutEntries = 8192;     // float2 {table[i], table[i+1]-table[i]}, i = 0..8191
+constexpr float kLutMax = 8191.0f;    // TransformLookup::max, color_conversions.rs:89
+constexpr int kMaxSplinePts = 34;     // IPB_MAX_CURVE_POINTS + 2 auto-added end points
+
+// SplineFunc coefficients (curves.rs:59-64), built on the host by the same f32 code path.
+struct SplineDev {
+  int n;     // number of points (0 => basecurve is a pass-through, curves.rs:34-36)
+  int nseg;  // c3s.len()
+  float x[kMaxSplinePts], y[kMaxSplinePts], c1[kMaxSplinePts], c2[kMaxSplinePts], c3[kMaxSplinePts];
+};
+
+// Everything the colour chain needs, derived on the host from OpToLab/OpBaseCurve/settings.
+struct ColorParams {
+  float mul[4];    // normalize_wbs(wb_coeffs) or 1s for monochrome — colorspaces.rs:97-101
+  float cm[12];    // cmatrix [[f32;4];3] — colorspaces.rs:90-95
+  float rgbm[9];   // XYZ_D65_33 = inverse(SRGB_D65_33) in f32 — color_conversions.rs:8
+  int use_e;       // 0: the 4th (E) channel is identically 0 and the matrix is finite -> skip its term
+  int linear;      // settings.linear: skip gamma (gamma.rs:17-18)
+  SplineDev sp;
+};
+
+// ---------------------------------------------------------------- exact helpers
+
+// x / d for a constant d with rc = RN(1/d): bit-identical to IEEE division (tools/verify_constdiv.c).
+__device__ __forceinline__ float div_rc(float x, float d, float rc) {
+  float q = x * rc;
+  float r = fmaf(-q, d, x);
+  return fmaf(r, rc, q);
+}
+#define IPB_DIVC(x, d) ::ipb::div_rc((x), (d), 1.0f / (d))
+
+// glibc 2.39 cbrtf (sysdeps/ieee754/flt-32/s_cbrtf.c) restated for finite x > 0; checked bit-identical to
+// the host libm over [2^-7, 64).  Only used by the out-of-table fallback of the Lab transfer
+// function (color_conversions.rs:103-104,123), i.e. for XYZ ratios above 1.0.
+static __device__ __noinline__ float cbrt_glibc(float x) {
+  const double factor[5] = {1.0 / 1.5874010519681994748, 1.0 / 1.2599210498948731648, 1.0,
+                            1.2599210498948731648, 1.5874010519681994748};
+  if (!(x < __int_as_float(0x7f800000))) return x + x;  // inf / NaN
+  int bits = __float_as_int(x);
+  int ex = (bits >> 23) & 0xff;
+  if (ex == 0) return cbrtf(x);  // subnormal: never reached by the hot path (x > 1)
+  int xe = ex - 126;
+  float xm = __int_as_float((bits & 0x007fffff) | 0x3f000000);  // frexpf: [0.5, 1)
+  float u = (float)(0.492659620528969547 + (0.697570460207922770 - 0.191502161678719066 * (double)xm) * (double)xm);
+  float t2 = u * u * u;
+  float ym = (float)((double)u * ((double)t2 + 2.0 * (double)xm) / (2.0 * (double)t2 + (double)xm) * factor[2 + xe % 3]);
+  return scalbnf(ym, xe / 3);
+}
+
+// ---------------------------------------------------------------- TransformLookup (color_conversions.rs:80-115)
+
+// Table access policies: global memory (unfused per-op kernels) or shared memory (fused kernels).
+struct LutGlobal {
+  const float2 *t;
+  __device__ __forceinline__ float2 at(int key) const { return __ldg(t + key); }
+};
+struct LutShared {
+  uint32_t base;  // shared-window byte address of entry 0
+  __device__ __forceinline__ float2 at(int key) const {
+    float2 v;
+    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(base + ((uint32_t)key << 3)));
+    return v;
+  }
+};
+
+// lookup() table branch for val in [0,1] (or -0.0): pos = val*max; key = trunc(pos); a = pos - trunc(pos);
+// v1 + a*(v2 - v1).  floor == trunc for pos >= 0; FADD.RM with 2^23 yields floor(pos) in the low mantissa bits.
+template <class Lut>
+__device__ __forceinline__ float lut_lerp(const Lut &lut, float val) {
+  float pos = val * kLutMax;
+  float tf = __fadd_rd(pos, 8388608.0f);
+  float base = tf - 8388608.0f;
+  float a = pos - base;
+  int key = __float_as_int(tf) & 0x3fff;
+  float2 e = lut.at(key);
+  return e.x + a * e.y;
+}
+
+// XYZ_LAB_TRANSFORM.lookup — color_conversions.rs:120-124 with the analytic fallback outside [0,1]
+template <class Lut>
+__device__ __forceinline__ float lab_f(const Lut &lut, float v) {
+  if (v < 0.0f || v > 1.0f) {
+    const float e = 216.0f / 24389.0f;
+    const float k = 24389.0f / 27.0f;
+    if (v > e) return cbrt_glibc(v);
+    return IPB_DIVC(k * v + 16.0f, 116.0f);
+  }
+  return lut_lerp(lut, v);
+}
+
+// ---------------------------------------------------------------- colour chain
+
+// camera_to_lab + xyz_to_lab — color_conversions.rs:42-55,156-169
+template <class Lut>
+__device__ __forceinline__ void camera_to_lab(const ColorParams &P, const Lut &lab, float r, float g, float b,
+                                              float e, float &ol, float &oa, float &ob) {
+  r = fminf(r * P.mul[0], 1.0f);
+  g = fminf(g * P.mul[1], 1.0f);
+  b = fminf(b * P.mul[2], 1.0f);
+  float x = r * P.cm[0] + g * P.cm[1] + b * P.cm[2];
+  float y = r * P.cm[4] + g * P.cm[5] + b * P.cm[6];
+  float z = r * P.cm[8] + g * P.cm[9] + b * P.cm[10];
+  if (P.use_e) {
+    e = fminf(e * P.mul[3], 1.0f);
+    x = x + e * P.cm[3];
+    y = y + e * P.cm[7];
+    z = z + e * P.cm[11];
+  }
+  float xr = IPB_DIVC(x, 0.95047f);
+  float yr = y;  // y / 1.0
+  float zr = IPB_DIVC(z, 1.08883f);
+  float fx = lab_f(lab, xr);
+  float fy = lab_f(lab, yr);
+  float fz = lab_f(lab, zr);
+  float l = 116.0f * fy - 16.0f;
+  float a = 500.0f * (fx - fy);
+  float bb = 200.0f * (fy - fz);
+  ol = IPB_DIVC(l, 100.0f);
+  oa = IPB_DIVC(a + 127.0f, 255.0f);
+  ob = IPB_DIVC(bb + 127.0f, 255.0f);
+}
+
+// SplineFunc::interpolate — curves.rs:126-157.  The binary search over points[0..nseg) ends at the last
+// knot strictly below val, or returns y exactly on a knot; the cubic evaluated at diff == 0 gives the
+// same y, so the segment is "last knot <= val".  NaN falls through every comparison of the reference's
+// search and returns y[(nseg-1)/2].
+__device__ __forceinline__ float spline_eval(const SplineDev &s, float val) {
+  const int last = s.n - 1;
+  float xi = s.x[0], yi = s.y[0], c1 = s.c1[0], c2 = s.c2[0], c3 = s.c3[0];
+  for (int j = 1; j < s.nseg; j++) {
+    bool ge = val >= s.x[j];
+    xi = ge ? s.x[j] : xi;
+    yi = ge ? s.y[j] : yi;
+    c1 = ge ? s.c1[j] : c1;
+    c2 = ge ? s.c2[j] : c2;
+    c3 = ge ? s.c3[j] : c3;
+  }
+  float diff = val - xi;
+  float res = yi + c1 * diff + c2 * diff * diff + c3 * diff * diff * diff;
+  res = (val <= s.x[0]) ? s.y[0] : res;
+  res = (val >= s.x[last]) ? s.y[last] : res;
+  res = (val != val) ? s.y[(s.nseg - 1) / 2] : res;
+  return res;
+}
+
+// lab_to_xyz + lab_to_rgb — color_conversions.rs:58-65,172-191
+__device__ __forceinline__ void lab_to_rgb(const ColorParams &P, float l, float a, float b, float &r, float &g,
+                                           float &bl) {
+  const float e = 216.0f / 24389.0f;
+  const float k = 24389.0f / 27.0f;
+  float cl = l * 100.0f;
+  float ca = (a * 255.0f) - 127.0f;
+  float cb = (b * 255.0f) - 127.0f;
+  float fy = IPB_DIVC(cl + 16.0f, 116.0f);
+  float fx = IPB_DIVC(ca, 500.0f) + fy;
+  float fz = fy - IPB_DIVC(cb, 200.0f);
+  float fx3 = fx * fx * fx;
+  float xr = fx3 > e ? fx3 : IPB_DIVC(116.0f * fx - 16.0f, k);
+  float yr = cl > k * e ? fy * fy * fy : IPB_DIVC(cl, k);
+  float fz3 = fz * fz * fz;
+  float zr = fz3 > e ? fz3 : IPB_DIVC(116.0f * fz - 16.0f, k);
+  float x = xr * 0.95047f;
+  float y = yr;  // * 1.0
+  float z = zr * 1.08883f;
+  r = x * P.rgbm[0] + y * P.rgbm[1] + z * P.rgbm[2];
+  g = x * P.rgbm[3] + y * P.rgbm[4] + z * P.rgbm[5];
+  bl = x * P.rgbm[6] + y * P.rgbm[7] + z * P.rgbm[8];
+}
+
+// OpGamma per element — gamma.rs:21: apply_srgb_gamma(x.max(0.0).min(1.0)); the clamp keeps it on the table
+template <class Lut>
+__device__ __forceinline__ float gamma_elem(const Lut &gam, float v) {
+  return lut_lerp(gam, fminf(fmaxf(v, 0.0f), 1.0f));
+}
+
+// demosaiced RGBE -> final RGB (to_lab, basecurve, from_lab, gamma): the whole chain for one pixel
+template <class Lut>
+__device__ __forceinline__ void color_chain(const ColorParams &P, const Lut &lab, const Lut &gam, float r, float g,
+                                            float b, float e, float &or_, float &og, float &ob) {
+  float l, a, bb;
+  camera_to_lab(P, lab, r, g, b, e, l, a, bb);
+  if (P.sp.n > 0) l = spline_eval(P.sp, l);
+  lab_to_rgb(P, l, a, bb, or_, og, ob);
+  if (!P.linear) {
+    or_ = gamma_elem(gam, or_);
+    og = gamma_elem(gam, og);
+    ob = gamma_elem(gam, ob);
+  }
+}
+
+// output8bit — color_conversions.rs:323-325: (v*256).max(0).min(255) as u8.  FADD.RZ with 2^23 leaves
+// trunc() in the low mantissa byte (the clamp keeps the value in [0,255]).
+__device__ __forceinline__ uint32_t output8bit(float v) {
+  float t = fminf(fmaxf(v * 256.0f, 0.0f), 255.0f);
+  return __float_as_uint(__fadd_rz(t, 8388608.0f)) & 0xffu;
+}
+// output16bit — color_conversions.rs:328-330: (v*65535).round().max(0).min(65535) as u16
+__device__ __forceinline__ uint32_t output16bit(float v) {
+  float t = fminf(fmaxf(roundf(v * 65535.0f), 0.0f), 65535.0f);
+  return (uint32_t)t;
+}
+
+// gofloat level mapping — gofloat.rs:127: ((v as f32 - black) / range).min(1.0).  With exact != 0 the host
+// has verified (all 65536 inputs) that the 3-instruction division is bit-identical for this black/range.
+__device__ __forceinline__ float golevel(float v, float black, float range, float rc, int exact_rc) {
+  float num = v - black;
+  float q = exact_rc ? div_rc(num, range, rc) : __fdiv_rn(num, range);
+  return fminf(q, 1.0f);
+}
+
+}  // namespace ipb

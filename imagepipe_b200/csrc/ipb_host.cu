@@ -1,0 +1,1421 @@
+// ipb_host.cu — host side of libipb200.so: the C ABI of include/ipb200.h.
+//
+// What lives here is the host logic the reference keeps around its pixel loops, restated for a device-resident
+// OpBuffer: contexts and streams, ref-counted buffers (Arc<OpBuffer>), parameter preparation (white-balance
+// normalisation, matrices, look-up tables, spline coefficients, CFA tables), the size negotiation of
+// Pipeline::run, op-by-op execution, and the decision to run the fused raw->sRGB kernels.  No pixel is ever
+// computed on the host: every entry point that produces pixels launches a CUDA kernel or fails.
+// Host float arithmetic is compiled -ffp-contract=off; all of it is f32 like the reference's.
+#include "../../include/ipb200.h"
+
+#include <atomic>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "ipb_internal.h"
+
+using namespace ipb;
+
+// ------------------------------------------------------------------------------------------------ objects
+
+struct ipb_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  int sm_count = 0;
+  float2 *lut_lab = nullptr, *lut_gamma = nullptr, *lut_rev = nullptr;  // device {v, dv} tables
+  std::string err;
+  unsigned long long launches = 0;
+};
+
+struct ipb_buffer {
+  std::atomic<int> refcnt{1};
+  ipb_ctx *ctx = nullptr;
+  size_t width = 0, height = 0, colors = 0;
+  int monochrome = 0;
+  float *dptr = nullptr;
+  bool owned = true;
+};
+
+struct ipb_pipeline {
+  ipb_ctx *ctx = nullptr;
+  ipb_source image{};
+  ipb_ops ops{};
+  ipb_settings settings{};
+  int fused = 1;
+  // row-stripe source (multi-GPU / chunked transfers)
+  bool has_stripe = false;
+  ipb_stripe stripe{};
+  ipb_source stripe_rows{};
+  // device staging for host-resident sources and host destinations (grown on demand, reused across runs)
+  void *stage_in = nullptr;
+  size_t stage_in_bytes = 0;
+  void *stage_out = nullptr;
+  size_t stage_out_bytes = 0;
+};
+
+namespace {
+
+thread_local std::string g_create_err;
+
+int fail(ipb_ctx *ctx, int code, const char *fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  if (ctx) ctx->err = buf; else g_create_err = buf;
+  return code;
+}
+
+#define IPB_CUDA(ctx, call)                                                                        \
+  do {                                                                                             \
+    cudaError_t e_ = (call);                                                                       \
+    if (e_ != cudaSuccess) return fail((ctx), IPB_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e_)); \
+  } while (0)
+#define IPB_LAUNCH(ctx, call)                                                                      \
+  do {                                                                                             \
+    cudaError_t e_ = (call);                                                                       \
+    if (e_ != cudaSuccess) return fail((ctx), IPB_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e_)); \
+    (ctx)->launches++;                                                                             \
+  } while (0)
+#define IPB_TRY(call)            \
+  do {                           \
+    int rc_ = (call);            \
+    if (rc_ != IPB_OK) return rc_; \
+  } while (0)
+
+// ------------------------------------------------------------------------------------------------ constants
+
+// color_conversions.rs:1-39 — matrices, evaluated in f32 exactly as the reference evaluates them at start-up
+struct HostTables {
+  float srgb_d65_33[3][3];
+  float xyz_d65_33[3][3];
+  float srgb_d65_43[3][4];
+  float xyz_d65_34[4][3];
+  float lab[kLutEntries + 1], rev[kLutEntries + 1], fwd[kLutEntries + 1];  // 8193 entries each
+};
+
+float lab_f_host(float v) {  // color_conversions.rs:120-124
+  float e = 216.0f / 24389.0f;
+  float k = 24389.0f / 27.0f;
+  if (v > e) return cbrtf(v);
+  return (k * v + 16.0f) / 116.0f;
+}
+float srgb_rev_host(float v) {  // :126-132
+  if (v < 0.04045f) return v / 12.92f;
+  return powf((v + 0.055f) / 1.055f, 2.4f);
+}
+float srgb_fwd_host(float v) {  // :134-140
+  if (v < 0.0031308f) return v * 12.92f;
+  return 1.055f * powf(v, 1.0f / 2.4f) - 0.055f;
+}
+
+const HostTables &tables() {
+  static HostTables T;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    const float s[3][3] = {{0.4124564f, 0.3575761f, 0.1804375f},
+                           {0.2126729f, 0.7151522f, 0.0721750f},
+                           {0.0193339f, 0.1191920f, 0.9503041f}};
+    memcpy(T.srgb_d65_33, s, sizeof(s));
+    const float(*m)[3] = T.srgb_d65_33;
+    float(*o)[3] = T.xyz_d65_33;
+    // color_conversions.rs:20-39 inverse()
+    float invdet = 1.0f / (m[0][0] * (m[1][1] * m[2][2] - m[2][1] * m[1][2]) -
+                           m[0][1] * (m[1][0] * m[2][2] - m[1][2] * m[2][0]) +
+                           m[0][2] * (m[1][0] * m[2][1] - m[1][1] * m[2][0]));
+    o[0][0] = (m[1][1] * m[2][2] - m[2][1] * m[1][2]) * invdet;
+    o[0][1] = -(m[0][1] * m[2][2] - m[0][2] * m[2][1]) * invdet;
+    o[0][2] = (m[0][1] * m[1][2] - m[0][2] * m[1][1]) * invdet;
+    o[1][0] = -(m[1][0] * m[2][2] - m[1][2] * m[2][0]) * invdet;
+    o[1][1] = (m[0][0] * m[2][2] - m[0][2] * m[2][0]) * invdet;
+    o[1][2] = -(m[0][0] * m[1][2] - m[1][0] * m[0][2]) * invdet;
+    o[2][0] = (m[1][0] * m[2][1] - m[2][0] * m[1][1]) * invdet;
+    o[2][1] = -(m[0][0] * m[2][1] - m[2][0] * m[0][1]) * invdet;
+    o[2][2] = (m[0][0] * m[1][1] - m[1][0] * m[0][1]) * invdet;
+    for (int i = 0; i < 3; i++) {
+      for (int j = 0; j < 3; j++) { T.srgb_d65_43[i][j] = m[i][j]; T.xyz_d65_34[i][j] = o[i][j]; }
+      T.srgb_d65_43[i][3] = 0.0f;
+      T.xyz_d65_34[3][i] = 0.0f;
+    }
+    // TransformLookup::new(13, f) — color_conversions.rs:87-94
+    const float maxv = (float)(kLutEntries - 1);
+    for (int i = 0; i <= kLutEntries; i++) {
+      float v = (float)i / maxv;
+      T.lab[i] = lab_f_host(v);
+      T.rev[i] = srgb_rev_host(v);
+      T.fwd[i] = srgb_fwd_host(v);
+    }
+  });
+  return T;
+}
+
+// rawloader::CFA::new (crate absent; call sites demosaic.rs:32-33,80,86, scaling.rs:110): pattern string of
+// length 4 / 36 / 16 / 144 -> 2x2 / 6x6 / 2 wide x 8 high / 12x12, R G B E -> 0 1 2 3 (M -> 1, Y -> 3)
+int parse_cfa(const char *pat, CfaDev *out) {
+  size_t len = strnlen(pat, 147);
+  int w, h;
+  switch (len) {
+    case 0: w = 0; h = 0; break;
+    case 4: w = 2; h = 2; break;
+    case 36: w = 6; h = 6; break;
+    case 16: w = 2; h = 8; break;
+    case 144: w = 12; h = 12; break;
+    default: return IPB_ERR_BAD_CFA;
+  }
+  memset(out, 0, sizeof(*out));
+  out->width = w;
+  out->height = h;
+  if (w == 0) return IPB_OK;
+  uint8_t base[144];
+  for (size_t i = 0; i < len; i++) {
+    switch (pat[i]) {
+      case 'R': base[i] = 0; break;
+      case 'G': base[i] = 1; break;
+      case 'B': base[i] = 2; break;
+      case 'E': base[i] = 3; break;
+      case 'M': base[i] = 1; break;
+      case 'Y': base[i] = 3; break;
+      default: return IPB_ERR_BAD_CFA;
+    }
+  }
+  for (int r = 0; r < 48; r++)
+    for (int c = 0; c < 48; c++) out->pat[r * 48 + c] = base[(r % h) * w + (c % w)];
+  return IPB_OK;
+}
+
+// colorspaces.rs:12-27
+void normalize_wbs(const float vals[4], float out[4]) {
+  float unity = vals[1];
+  for (int i = 0; i < 4; i++) out[i] = !std::isnormal(vals[i]) ? 1.0f : vals[i] / unity;
+}
+
+// SplineFunc::new — curves.rs:68-124.  Returns false where the reference would panic (fewer than two points).
+bool build_spline(const ipb_basecurve *op, SplineDev *s) {
+  memset(s, 0, sizeof(*s));
+  if (op->npoints == 0 && fabsf(op->exposure) < 0.001f) return true;  // pass-through, n == 0 (curves.rs:34-36)
+  const size_t n = op->npoints;
+  float px[IPB_MAX_CURVE_POINTS], py[IPB_MAX_CURVE_POINTS];
+  const float ex = exp2f(op->exposure);
+  for (size_t i = 0; i < n; i++) { px[i] = op->points[i][0]; py[i] = op->points[i][1] * ex; }  // curves.rs:38-41
+  int np = 0;
+  if (n == 0 || (px[0] > 0.0f && py[0] > 0.0f)) { s->x[np] = 0.0f; s->y[np] = 0.0f; np++; }
+  for (size_t i = 0; i < n; i++) { s->x[np] = px[i]; s->y[np] = py[i]; np++; }
+  if (n == 0 || (px[n - 1] < 1.0f && py[n - 1] < 1.0f)) { s->x[np] = 1.0f; s->y[np] = 1.0f; np++; }
+  if (np < 2) return false;
+  float dxs[kMaxSplinePts], slopes[kMaxSplinePts];
+  const int nd = np - 1;
+  for (int i = 0; i < nd; i++) {
+    float dx = s->x[i + 1] - s->x[i];
+    float dy = s->y[i + 1] - s->y[i];
+    dxs[i] = dx;
+    slopes[i] = dy / dx;
+  }
+  int nc1 = 0;
+  s->c1[nc1++] = slopes[0];
+  for (int i = 0; i + 1 < nd; i++) {
+    float m = slopes[i], next = slopes[i + 1];
+    if (m * next <= 0.0f) {
+      s->c1[nc1++] = 0.0f;
+    } else {
+      float dx = dxs[i], dxnext = dxs[i + 1];
+      float common = dx + dxnext;
+      s->c1[nc1++] = 3.0f * common / ((common + dxnext) / m + (common + dx) / next);
+    }
+  }
+  s->c1[nc1++] = slopes[nd - 1];
+  for (int i = 0; i + 1 < nc1; i++) {
+    float c1 = s->c1[i], slope = slopes[i];
+    float invdx = 1.0f / dxs[i];
+    float common = c1 + s->c1[i + 1] - slope - slope;
+    s->c2[i] = (slope - c1 - common) * invdx;
+    s->c3[i] = common * invdx * invdx;
+  }
+  s->n = np;
+  s->nseg = nc1 - 1;
+  return true;
+}
+
+// OpToLab::run parameter preparation — colorspaces.rs:89-101
+void fill_tolab(ColorParams *P, const ipb_tolab *op, int monochrome) {
+  const HostTables &T = tables();
+  if (monochrome) {
+    memcpy(P->cm, T.srgb_d65_43, sizeof(P->cm));
+    P->mul[0] = P->mul[1] = P->mul[2] = P->mul[3] = 1.0f;
+  } else {
+    memcpy(P->cm, op->cam_to_xyz_normalized, sizeof(P->cm));
+    normalize_wbs(op->wb_coeffs, P->mul);
+  }
+  memcpy(P->rgbm, T.xyz_d65_33, sizeof(P->rgbm));
+  P->use_e = 1;
+}
+
+// scaling.rs:8-23
+void scaling_total(size_t width, size_t height, size_t maxwidth, size_t maxheight, float *scale, size_t *ow,
+                   size_t *oh) {
+  if (maxwidth == 0 && maxheight == 0) { *scale = 1.0f; *ow = width; *oh = height; return; }
+  float xscale = maxwidth == 0 ? 1.0f : (float)width / (float)maxwidth;
+  float yscale = maxheight == 0 ? 1.0f : (float)height / (float)maxheight;
+  auto f2u = [](float f) -> size_t { return f > 0.0f ? (size_t)f : 0; };
+  if (yscale <= 1.0f && xscale <= 1.0f) { *scale = 1.0f; *ow = width; *oh = height; }
+  else if (yscale > xscale) { *scale = yscale; *ow = f2u((float)width / yscale); *oh = maxheight; }
+  else { *scale = xscale; *ow = maxwidth; *oh = f2u((float)height / xscale); }
+}
+
+// gofloat.rs:74-82
+void size_image(const ipb_gofloat *op, size_t ow, size_t oh, size_t o[4]) {
+  auto umin = [](size_t a, size_t b) { return a < b ? a : b; };
+  o[0] = umin(op->crop_left, ow - 10);
+  o[1] = umin(op->crop_top, oh - 10);
+  o[2] = ow - umin(op->crop_left + op->crop_right, ow - 10);
+  o[3] = oh - umin(op->crop_top + op->crop_bottom, oh - 10);
+}
+
+// ---- rotatecrop.rs:89-163
+const float kRcEps = 1.0f / 1000000.0f;
+const float kFracPi2 = 1.57079632679489661923132169163975144f;
+bool rc_noop(const ipb_rotatecrop *op) {
+  return fabsf(op->rotation) < kRcEps && fabsf(op->crop_top) < kRcEps && fabsf(op->crop_right) < kRcEps &&
+         fabsf(op->crop_bottom) < kRcEps && fabsf(op->crop_left) < kRcEps;
+}
+long f2isize(float f) {
+  if (f != f) return 0;
+  if (f >= 9223372036854775808.0f) return 0x7fffffffffffffffL;
+  if (f <= -9223372036854775808.0f) return (long)0x8000000000000000UL;
+  return (long)f;
+}
+size_t f2usize(float f) {
+  if (!(f > 0.0f)) return 0;
+  if (f >= 18446744073709551616.0f) return (size_t)-1;
+  return (size_t)f;
+}
+void rc_rotate_point_reverse(const ipb_rotatecrop *op, float x, float y, float width, float height, float swidth,
+                             float sheight, long out[2]) {
+  if (op->rotation < kRcEps) { out[0] = f2isize(x); out[1] = f2isize(y); return; }
+  float angle = kFracPi2 * (op->rotation > 1.0f ? 1.0f : op->rotation);
+  float sn = sinf(angle), cs = cosf(angle);
+  float tx = x - (width / 2.0f), ty = y - (height / 2.0f);
+  float nx = tx * cs + ty * sn + (swidth / 2.0f);
+  float ny = -tx * sn + ty * cs + (sheight / 2.0f);
+  out[0] = f2isize(nx);
+  out[1] = f2isize(ny);
+}
+void rc_calc_size(const ipb_rotatecrop *op, size_t owidth, size_t oheight, bool reverse, size_t *ow, size_t *oh) {
+  if (rc_noop(op)) { *ow = owidth; *oh = oheight; return; }
+  float width = (float)owidth, height = (float)oheight;
+  if (!(reverse || op->rotation < kRcEps)) {
+    float angle = kFracPi2 * (op->rotation > 1.0f ? 1.0f : op->rotation);
+    float sn = sinf(angle), cs = cosf(angle);
+    float w2 = width * cs + height * sn, h2 = width * sn + height * cs;
+    width = w2;
+    height = h2;
+  }
+  float nwidth, nheight;
+  {
+    float ratio = 1.0f - op->crop_left - op->crop_right;
+    nwidth = reverse ? roundf(width / ratio) : roundf(width * ratio);
+    if (ratio < kRcEps || nwidth < 1.0f) { *ow = owidth; *oh = oheight; return; }
+  }
+  {
+    float ratio = 1.0f - op->crop_top - op->crop_bottom;
+    nheight = reverse ? roundf(height / ratio) : roundf(height * ratio);
+    if (ratio < kRcEps || nheight < 1.0f) { *ow = owidth; *oh = oheight; return; }
+  }
+  if (!(!reverse || op->rotation < kRcEps)) {
+    float angle = kFracPi2 * (op->rotation > 1.0f ? 1.0f : op->rotation);
+    float sn = sinf(angle), cs = cosf(angle);
+    float w2 = roundf(nheight / (sn + (cs / op->input_ratio)));
+    float h2 = roundf(w2 / op->input_ratio);
+    nwidth = w2;
+    nheight = h2;
+  }
+  *ow = f2usize(nwidth);
+  *oh = f2usize(nheight);
+}
+
+// rawloader Orientation::to_flips for the four base rotations, XOR the user flips (transform.rs:56-66);
+// the table is pinned by the eight golden bitmaps of transform.rs:167-278
+void orientation_flips(const ipb_transform *op, int f[3]) {
+  switch (op->rotation) {
+    case IPB_ROT_90: f[0] = 1; f[1] = 0; f[2] = 1; break;
+    case IPB_ROT_180: f[0] = 0; f[1] = 1; f[2] = 1; break;
+    case IPB_ROT_270: f[0] = 1; f[1] = 1; f[2] = 0; break;
+    default: f[0] = 0; f[1] = 0; f[2] = 0; break;
+  }
+  f[1] ^= (op->fliph != 0);
+  f[2] ^= (op->flipv != 0);
+}
+
+// Is the 3-instruction reciprocal division of the device bit-identical to (v - black) / range for every
+// possible u16 sample?  (gofloat.rs:127)
+bool golevel_rc_exact(float black, float range, float rc) {
+  if (!std::isfinite(rc) || !std::isnormal(range)) return false;
+  for (int v = 0; v < 65536; v++) {
+    float num = (float)v - black;
+    float q = num * rc;
+    float r = fmaf(-q, range, num);
+    float q2 = fmaf(r, rc, q);
+    float ref = num / range;
+    if (memcmp(&q2, &ref, 4) != 0) return false;
+  }
+  return true;
+}
+
+int upload_lut(ipb_ctx *ctx, const float *t, float2 **out) {
+  std::vector<float2> host(kLutEntries);
+  for (int i = 0; i < kLutEntries; i++) host[i] = make_float2(t[i], t[i + 1] - t[i]);
+  IPB_CUDA(ctx, cudaMalloc((void **)out, kLutEntries * sizeof(float2)));
+  IPB_CUDA(ctx, cudaMemcpy(*out, host.data(), kLutEntries * sizeof(float2), cudaMemcpyHostToDevice));
+  return IPB_OK;
+}
+
+int new_buffer(ipb_ctx *ctx, size_t w, size_t h, size_t colors, int mono, bool zero, ipb_buffer **out) {
+  ipb_buffer *b = new (std::nothrow) ipb_buffer();
+  if (!b) return fail(ctx, IPB_ERR_NOMEM, "out of host memory");
+  b->ctx = ctx; b->width = w; b->height = h; b->colors = colors; b->monochrome = mono;
+  size_t bytes = w * h * colors * sizeof(float);
+  cudaError_t e = cudaMallocAsync((void **)&b->dptr, bytes ? bytes : 4, ctx->stream);
+  if (e == cudaSuccess && zero && bytes) e = cudaMemsetAsync(b->dptr, 0, bytes, ctx->stream);
+  if (e != cudaSuccess) {
+    delete b;
+    return fail(ctx, e == cudaErrorMemoryAllocation ? IPB_ERR_NOMEM : IPB_ERR_CUDA, "buffer alloc %zux%zux%zu: %s", w, h,
+                colors, cudaGetErrorString(e));
+  }
+  *out = b;
+  return IPB_OK;
+}
+
+int enter(ipb_ctx *ctx) {
+  if (!ctx) return fail(nullptr, IPB_ERR_INVALID, "null context");
+  IPB_CUDA(ctx, cudaSetDevice(ctx->device));
+  return IPB_OK;
+}
+
+size_t src_elem_size(int kind) {
+  switch (kind) {
+    case IPB_SRC_RAW_U16: return 2;
+    case IPB_SRC_RAW_F32: return 4;
+    case IPB_SRC_RGB8: return 1;
+    default: return 2;
+  }
+}
+size_t src_cpp(const ipb_source *s) { return (s->kind == IPB_SRC_RGB8 || s->kind == IPB_SRC_RGB16) ? 3 : s->cpp; }
+
+// device view of a source: the pointer itself when on_device, otherwise a stream-ordered temporary copy
+struct DevSrc {
+  const void *ptr = nullptr;
+  void *tmp = nullptr;
+};
+int device_source(ipb_ctx *ctx, const ipb_source *img, DevSrc *d) {
+  if (!img->data) return fail(ctx, IPB_ERR_INVALID, "source has no data");
+  if (img->on_device) { d->ptr = img->data; return IPB_OK; }
+  size_t bytes = img->width * img->height * src_cpp(img) * src_elem_size(img->kind);
+  IPB_CUDA(ctx, cudaMallocAsync(&d->tmp, bytes ? bytes : 4, ctx->stream));
+  IPB_CUDA(ctx, cudaMemcpyAsync(d->tmp, img->data, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  d->ptr = d->tmp;
+  return IPB_OK;
+}
+void release_source(ipb_ctx *ctx, DevSrc *d) {
+  if (d->tmp) cudaFreeAsync(d->tmp, ctx->stream);
+  d->tmp = nullptr;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------ context
+
+extern "C" {
+
+int ipb_version(void) { return IPB_VERSION; }
+
+int ipb_ctx_create(int device, void *stream, ipb_ctx **out) {
+  if (!out) return fail(nullptr, IPB_ERR_INVALID, "null out pointer");
+  *out = nullptr;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail(nullptr, IPB_ERR_CUDA, "no usable CUDA device (%s); imagepipe-b200 has no CPU fallback",
+                e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+  if (device < 0 || device >= ndev) return fail(nullptr, IPB_ERR_INVALID, "device %d out of range (%d present)", device, ndev);
+  ipb_ctx *ctx = new (std::nothrow) ipb_ctx();
+  if (!ctx) return fail(nullptr, IPB_ERR_NOMEM, "out of host memory");
+  ctx->device = device;
+  auto bail = [&](int rc) { g_create_err = ctx->err; ipb_ctx_destroy(ctx); return rc; };
+  if ((e = cudaSetDevice(device)) != cudaSuccess) { ctx->err = cudaGetErrorString(e); return bail(IPB_ERR_CUDA); }
+  if (stream) {
+    ctx->stream = (cudaStream_t)stream;
+  } else {
+    if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) {
+      ctx->err = cudaGetErrorString(e);
+      return bail(IPB_ERR_CUDA);
+    }
+    ctx->own_stream = true;
+  }
+  cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
+  if (ctx->sm_count <= 0) ctx->sm_count = 148;
+  // keep freed blocks in the stream-ordered pool instead of returning them to the driver at every sync
+  cudaMemPool_t pool;
+  if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+    unsigned long long thr = ~0ull;
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+  }
+  const HostTables &T = tables();
+  int rc;
+  if ((rc = upload_lut(ctx, T.lab, &ctx->lut_lab)) != IPB_OK) return bail(rc);
+  if ((rc = upload_lut(ctx, T.fwd, &ctx->lut_gamma)) != IPB_OK) return bail(rc);
+  if ((rc = upload_lut(ctx, T.rev, &ctx->lut_rev)) != IPB_OK) return bail(rc);
+  *out = ctx;
+  return IPB_OK;
+}
+
+void ipb_ctx_destroy(ipb_ctx *ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  if (ctx->lut_lab) cudaFree(ctx->lut_lab);
+  if (ctx->lut_gamma) cudaFree(ctx->lut_gamma);
+  if (ctx->lut_rev) cudaFree(ctx->lut_rev);
+  if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+int ipb_ctx_set_stream(ipb_ctx *ctx, void *stream) {
+  IPB_TRY(enter(ctx));
+  if (ctx->own_stream) {
+    cudaStreamSynchronize(ctx->stream);
+    cudaStreamDestroy(ctx->stream);
+    ctx->own_stream = false;
+  }
+  if (stream) {
+    ctx->stream = (cudaStream_t)stream;
+  } else {
+    IPB_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    ctx->own_stream = true;
+  }
+  return IPB_OK;
+}
+
+int ipb_ctx_synchronize(ipb_ctx *ctx) {
+  IPB_TRY(enter(ctx));
+  IPB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return IPB_OK;
+}
+
+const char *ipb_last_error(const ipb_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_err.c_str(); }
+unsigned long long ipb_ctx_launch_count(const ipb_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int ipb_host_alloc(size_t bytes, void **out) {
+  if (!out) return IPB_ERR_INVALID;
+  cudaError_t e = cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocDefault);
+  if (e != cudaSuccess) return fail(nullptr, IPB_ERR_CUDA, "cudaHostAlloc(%zu): %s", bytes, cudaGetErrorString(e));
+  return IPB_OK;
+}
+void ipb_host_free(void *p) {
+  if (p) cudaFreeHost(p);
+}
+
+int ipb_device_alloc(ipb_ctx *ctx, size_t bytes, void **out) {
+  IPB_TRY(enter(ctx));
+  if (!out) return fail(ctx, IPB_ERR_INVALID, "null out pointer");
+  cudaError_t e = cudaMallocAsync(out, bytes ? bytes : 4, ctx->stream);
+  if (e != cudaSuccess)
+    return fail(ctx, e == cudaErrorMemoryAllocation ? IPB_ERR_NOMEM : IPB_ERR_CUDA, "device alloc %zu: %s", bytes, cudaGetErrorString(e));
+  return IPB_OK;
+}
+int ipb_device_free(ipb_ctx *ctx, void *dptr) {
+  IPB_TRY(enter(ctx));
+  if (dptr) IPB_CUDA(ctx, cudaFreeAsync(dptr, ctx->stream));
+  return IPB_OK;
+}
+int ipb_device_upload(ipb_ctx *ctx, void *dptr, const void *host, size_t bytes) {
+  IPB_TRY(enter(ctx));
+  if (bytes && (!dptr || !host)) return fail(ctx, IPB_ERR_INVALID, "null pointer");
+  if (bytes) IPB_CUDA(ctx, cudaMemcpyAsync(dptr, host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  IPB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return IPB_OK;
+}
+int ipb_device_download(ipb_ctx *ctx, void *host, const void *dptr, size_t bytes) {
+  IPB_TRY(enter(ctx));
+  if (bytes && (!dptr || !host)) return fail(ctx, IPB_ERR_INVALID, "null pointer");
+  if (bytes) IPB_CUDA(ctx, cudaMemcpyAsync(host, dptr, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  IPB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return IPB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ OpBuffer
+
+int ipb_buffer_new(ipb_ctx *ctx, size_t width, size_t height, size_t colors, int monochrome, ipb_buffer **out) {
+  IPB_TRY(enter(ctx));
+  if (!out) return fail(ctx, IPB_ERR_INVALID, "null out pointer");
+  return new_buffer(ctx, width, height, colors, monochrome, true, out);
+}
+
+int ipb_buffer_upload(ipb_ctx *ctx, size_t width, size_t height, size_t colors, int monochrome, const float *host,
+                      ipb_buffer **out) {
+  IPB_TRY(enter(ctx));
+  if (!out || (!host && width * height * colors)) return fail(ctx, IPB_ERR_INVALID, "null pointer");
+  ipb_buffer *b;
+  IPB_TRY(new_buffer(ctx, width, height, colors, monochrome, false, &b));
+  size_t bytes = width * height * colors * sizeof(float);
+  if (bytes) {
+    cudaError_t e = cudaMemcpyAsync(b->dptr, host, bytes, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);  // the host array may be pageable and short-lived
+    if (e != cudaSuccess) { ipb_buffer_release(b); return fail(ctx, IPB_ERR_CUDA, "upload: %s", cudaGetErrorString(e)); }
+  }
+  *out = b;
+  return IPB_OK;
+}
+
+int ipb_buffer_wrap(ipb_ctx *ctx, size_t width, size_t height, size_t colors, int monochrome, void *dptr,
+                    ipb_buffer **out) {
+  IPB_TRY(enter(ctx));
+  if (!out || !dptr) return fail(ctx, IPB_ERR_INVALID, "null pointer");
+  ipb_buffer *b = new (std::nothrow) ipb_buffer();
+  if (!b) return fail(ctx, IPB_ERR_NOMEM, "out of host memory");
+  b->ctx = ctx; b->width = width; b->height = height; b->colors = colors; b->monochrome = monochrome;
+  b->dptr = (float *)dptr;
+  b->owned = false;
+  *out = b;
+  return IPB_OK;
+}
+
+int ipb_buffer_download(ipb_ctx *ctx, const ipb_buffer *buf, float *host) {
+  IPB_TRY(enter(ctx));
+  if (!buf || !host) return fail(ctx, IPB_ERR_INVALID, "null pointer");
+  size_t bytes = buf->width * buf->height * buf->colors * sizeof(float);
+  if (bytes) IPB_CUDA(ctx, cudaMemcpyAsync(host, buf->dptr, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  IPB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return IPB_OK;
+}
+
+void ipb_buffer_retain(ipb_buffer *buf) {
+  if (buf) buf->refcnt.fetch_add(1, std::memory_order_relaxed);
+}
+void ipb_buffer_release(ipb_buffer *buf) {
+  if (!buf) return;
+  if (buf->refcnt.fetch_sub(1, std::memory_order_acq_rel) == 1) {
+    if (buf->owned && buf->dptr) {
+      cudaSetDevice(buf->ctx->device);
+      cudaFreeAsync(buf->dptr, buf->ctx->stream);
+    }
+    delete buf;
+  }
+}
+size_t ipb_buffer_width(const ipb_buffer *buf) { return buf ? buf->width : 0; }
+size_t ipb_buffer_height(const ipb_buffer *buf) { return buf ? buf->height : 0; }
+size_t ipb_buffer_colors(const ipb_buffer *buf) { return buf ? buf->colors : 0; }
+int ipb_buffer_monochrome(const ipb_buffer *buf) { return buf ? buf->monochrome : 0; }
+void *ipb_buffer_device_ptr(const ipb_buffer *buf) { return buf ? buf->dptr : nullptr; }
+
+// ------------------------------------------------------------------------------------------------ ImageOp::run
+
+int ipb_gofloat_run(ipb_ctx *ctx, const ipb_gofloat *op, const ipb_source *image, ipb_buffer **out) {
+  IPB_TRY(enter(ctx));
+  if (!op || !image || !out) return fail(ctx, IPB_ERR_INVALID, "null pointer");
+  if (image->width < 10 || image->height < 10)
+    return fail(ctx, IPB_ERR_INVALID, "gofloat: source smaller than 10x10 (size_image underflows, gofloat.rs:77-80)");
+  size_t xywh[4];
+  size_image(op, image->width, image->height, xywh);
+  const size_t x = xywh[0], y = xywh[1], width = xywh[2], height = xywh[3];
+  DevSrc src;
+  IPB_TRY(device_source(ctx, image, &src));
+  ipb_buffer *b = nullptr;
+  int rc = IPB_OK;
+  if (image->kind == IPB_SRC_RAW_U16 || image->kind == IPB_SRC_RAW_F32) {
+    float mins[4], ranges[4];
+    for (int i = 0; i < 4; i++) { mins[i] = op->blacklevels[i]; ranges[i] = op->whitelevels[i] - mins[i]; }  // gofloat.rs:86-89
+    int mode;
+    size_t colors;
+    int mono = 0;
+    if (image->cpp == 1 && !op->is_cfa) { mode = 0; colors = 4; mono = 1; }
+    else if (image->cpp == 3) { mode = 1; colors = 4; }
+    else { mode = 2; colors = image->cpp; }
+    rc = new_buffer(ctx, width, height, colors, mono, mode == 2, &b);
+    if (rc == IPB_OK) {
+      cudaError_t e = launch_gofloat_raw(ctx->stream, image->kind == IPB_SRC_RAW_F32, src.ptr,
+                                         image->width * image->height * image->cpp, image->width, x, y, width, height,
+                                         image->cpp, mode, mins, ranges, b->dptr);
+      if (e != cudaSuccess) rc = fail(ctx, IPB_ERR_CUDA, "gofloat kernel: %s", cudaGetErrorString(e));
+      else ctx->launches++;
+    }
+  } else if (image->kind == IPB_SRC_RGB8 || image->kind == IPB_SRC_RGB16) {
+    rc = new_buffer(ctx, width, height, 4, 0, false, &b);
+    if (rc == IPB_OK) {
+      cudaError_t e = launch_gofloat_other(ctx->stream, image->kind == IPB_SRC_RGB16, src.ptr, image->width, x, y, width,
+                                           height, ctx->lut_rev, b->dptr);
+      if (e != cudaSuccess) rc = fail(ctx, IPB_ERR_CUDA, "gofloat kernel: %s", cudaGetErrorString(e));
+      else ctx->launches++;
+    }
+  } else {
+    rc = fail(ctx, IPB_ERR_INVALID, "unknown source kind %d", image->kind);
+  }
+  release_source(ctx, &src);
+  if (rc != IPB_OK) { if (b) ipb_buffer_release(b); return rc; }
+  *out = b;
+  return IPB_OK;
+}
+
+static int scale_opbuf(ipb_ctx *ctx, const CfaDev *cfa, ipb_buffer *in, size_t nw, size_t nh, size_t out_colors,
+                       ipb_buffer **out) {
+  if (nw == 0 || nh == 0) return fail(ctx, IPB_ERR_INVALID, "scale to an empty image");
+  ipb_buffer *b;
+  IPB_TRY(new_buffer(ctx, nw, nh, out_colors, in->monochrome, false, &b));
+  XformGeom g;
+  g.tl[0] = 0; g.tl[1] = 0;
+  g.tr[0] = (long)in->width - 1; g.tr[1] = 0;
+  g.bl[0] = 0; g.bl[1] = (long)in->height - 1;
+  g.width = in->width; g.height = in->height; g.nwidth = nw; g.nheight = nh; g.components = out_colors;
+  cudaError_t e = launch_transform_f32(ctx->stream, g, cfa, in->dptr, b->dptr);
+  if (e != cudaSuccess) { ipb_buffer_release(b); return fail(ctx, IPB_ERR_CUDA, "scale kernel: %s", cudaGetErrorString(e)); }
+  ctx->launches++;
+  *out = b;
+  return IPB_OK;
+}
+
+static float cfa_minscale(const CfaDev &cfa) {  // demosaic.rs:33-39
+  switch (cfa.width) {
+    case 2: return 2.0f;
+    case 6: return 3.0f;
+    case 8: return 2.0f;
+    case 12: return 12.0f;
+    default: return 2.0f;
+  }
+}
+
+int ipb_demosaic_run(ipb_ctx *ctx, const ipb_demosaic *op, const ipb_settings *settings, ipb_buffer *in,
+                     ipb_buffer **out) {
+  IPB_TRY(enter(ctx));
+  if (!op || !settings || !in || !out) return fail(ctx, IPB_ERR_INVALID, "null pointer");
+  const size_t nwidth = settings->demosaic_width, nheight = settings->demosaic_height;
+  float scale;
+  size_t sw, sh;
+  scaling_total(in->width, in->height, nwidth, nheight, &scale, &sw, &sh);
+  CfaDev cfa;
+  if (parse_cfa(op->cfa, &cfa) != IPB_OK) return fail(ctx, IPB_ERR_BAD_CFA, "demosaic: bad CFA pattern \"%s\"", op->cfa);
+  const float minscale = cfa_minscale(cfa);
+  if (scale <= 1.0f && in->colors == 4) {  // demosaic.rs:41-43
+    ipb_buffer_retain(in);
+    *out = in;
+    return IPB_OK;
+  }
+  if (in->colors == 4) return scale_opbuf(ctx, nullptr, in, nwidth, nheight, 4, out);  // :44-46
+  if (cfa.width == 0) return fail(ctx, IPB_ERR_BAD_CFA, "demosaic: %zu-channel buffer without a CFA pattern", in->colors);
+  if (in->colors != 1) return fail(ctx, IPB_ERR_BAD_COLORS, "demosaic: expected 1 channel, got %zu", in->colors);
+  if (scale >= minscale) return scale_opbuf(ctx, &cfa, in, nwidth, nheight, 4, out);  // :47-50 scaled_demosaic
+  ipb_buffer *full;                                                                   // :51-60
+  IPB_TRY(new_buffer(ctx, in->width, in->height, 4, in->monochrome, false, &full));
+  cudaError_t e = launch_demosaic_full(ctx->stream, cfa, in->dptr, in->width, in->height, full->dptr);
+  if (e != cudaSuccess) { ipb_buffer_release(full); return fail(ctx, IPB_ERR_CUDA, "demosaic kernel: %s", cudaGetErrorString(e)); }
+  ctx->launches++;
+  if (scale > 1.0f) {
+    int rc = scale_opbuf(ctx, nullptr, full, nwidth, nheight, 4, out);
+    ipb_buffer_release(full);
+    return rc;
+  }
+  *out = full;
+  return IPB_OK;
+}
+
+int ipb_rotatecrop_run(ipb_ctx *ctx, const ipb_rotatecrop *op, ipb_buffer *in, ipb_buffer **out) {
+  IPB_TRY(enter(ctx));
+  if (!op || !in || !out) return fail(ctx, IPB_ERR_INVALID, "null pointer");
+  auto passthrough = [&]() { ipb_buffer_retain(in); *out = in; return (int)IPB_OK; };
+  if (rc_noop(op)) return passthrough();
+  if (in->colors > 4) return fail(ctx, IPB_ERR_BAD_COLORS, "rotatecrop: %zu channels", in->colors);
+  const float swidth = (float)in->width, sheight = (float)in->height;
+  size_t nwidth, nheight;
+  rc_calc_size(op, in->width, in->height, false, &nwidth, &nheight);
+  const float fnwidth = (float)nwidth, fnheight = (float)nheight;
+  float x = floorf(swidth * op->crop_left);
+  if (x < 0.0f || x > swidth) return passthrough();  // rotatecrop.rs:49-52 (logs and returns the input)
+  float y = floorf(sheight * op->crop_top);
+  if (y < 0.0f || y > sheight) return passthrough();
+  XformGeom g;
+  rc_rotate_point_reverse(op, x, y, fnwidth, fnheight, swidth, sheight, g.tl);
+  rc_rotate_point_reverse(op, x + fnwidth - 1.0f, y, fnwidth, fnheight, swidth, sheight, g.tr);
+  rc_rotate_point_reverse(op, x, y + fnheight - 1.0f, fnwidth, fnheight, swidth, sheight, g.bl);
+  g.width = in->width; g.height = in->height; g.nwidth = nwidth; g.nheight = nheight; g.components = in->colors;
+  ipb_buffer *b;
+  IPB_TRY(new_buffer(ctx, nwidth, nheight, in->colors, in->monochrome, false, &b));
+  cudaError_t e = launch_transform_f32(ctx->stream, g, nullptr, in->dptr, b->dptr);
+  if (e != cudaSuccess) { ipb_buffer_release(b); return fail(ctx, IPB_ERR_CUDA, "rotatecrop kernel: %s", cudaGetErrorString(e)); }
+  ctx->launches++;
+  *out = b;
+  return IPB_OK;
+}
+
+int ipb_tolab_run(ipb_ctx *ctx, const ipb_tolab *op, ipb_buffer *in, ipb_buffer **out) {
+  IPB_TRY(enter(ctx));
+  if (!op || !in || !out) return fail(ctx, IPB_ERR_INVALID, "null pointer");
+  if (in->colors != 4) return fail(ctx, IPB_ERR_BAD_COLORS, "to_lab: expected 4 channels, got %zu", in->colors);
+  ColorParams P;
+  memset(&P, 0, sizeof(P));
+  fill_tolab(&P, op, in->monochrome);
+  ipb_buffer *b;
+  IPB_TRY(new_buffer(ctx, in->width, in->height, 3, in->monochrome, false, &b));
+  cudaError_t e = launch_tolab(ctx->stream, P, ctx->lut_lab, in->dptr, in->width * in->height, b->dptr);
+  if (e != cudaSuccess) { ipb_buffer_release(b); return fail(ctx, IPB_ERR_CUDA, "to_lab kernel: %s", cudaGetErrorString(e)); }
+  ctx->launches++;
+  *out = b;
+  return IPB_OK;
+}
+
+int ipb_basecurve_run(ipb_ctx *ctx, const ipb_basecurve *op, ipb_buffer *in, ipb_buffer **out) {
+  IPB_TRY(enter(ctx));
+  if (!op || !in || !out) return fail(ctx, IPB_ERR_INVALID, "null pointer");
+  if (op->npoints > IPB_MAX_CURVE_POINTS) return fail(ctx, IPB_ERR_UNSUPPORTED, "basecurve: more than %d points", IPB_MAX_CURVE_POINTS);
+  SplineDev sp;
+  if (!build_spline(op, &sp)) return fail(ctx, IPB_ERR_INVALID, "basecurve: degenerate curve (the reference panics)");
+  if (sp.n == 0) {  // curves.rs:34-36
+    ipb_buffer_retain(in);
+    *out = in;
+    return IPB_OK;
+  }
+  if (in->colors != 3) return fail(ctx, IPB_ERR_BAD_COLORS, "basecurve: expected 3 channels, got %zu", in->colors);
+  ipb_buffer *b;
+  IPB_TRY(new_buffer(ctx, in->width, in->height, 3, in->monochrome, false, &b));
+  cudaError_t e = launch_basecurve(ctx->stream, sp, in->dptr, in->width * in->height, b->dptr);
+  if (e != cudaSuccess) { ipb_buffer_release(b); return fail(ctx, IPB_ERR_CUDA, "basecurve kernel: %s", cudaGetErrorString(e)); }
+  ctx->launches++;
+  *out = b;
+  return IPB_OK;
+}
+
+int ipb_fromlab_run(ipb_ctx *ctx, ipb_buffer *in, ipb_buffer **out) {
+  IPB_TRY(enter(ctx));
+  if (!in || !out) return fail(ctx, IPB_ERR_INVALID, "null pointer");
+  if (in->colors != 3) return fail(ctx, IPB_ERR_BAD_COLORS, "from_lab: expected 3 channels, got %zu", in->colors);
+  ColorParams P;
+  memset(&P, 0, sizeof(P));
+  memcpy(P.rgbm, tables().xyz_d65_33, sizeof(P.rgbm));
+  ipb_buffer *b;
+  IPB_TRY(new_buffer(ctx, in->width, in->height, 3, in->monochrome, false, &b));
+  cudaError_t e = launch_fromlab(ctx->stream, P, in->dptr, in->width * in->height, b->dptr);
+  if (e != cudaSuccess) { ipb_buffer_release(b); return fail(ctx, IPB_ERR_CUDA, "from_lab kernel: %s", cudaGetErrorString(e)); }
+  ctx->launches++;
+  *out = b;
+  return IPB_OK;
+}
+
+int ipb_gamma_run(ipb_ctx *ctx, const ipb_settings *settings, ipb_buffer *in, ipb_buffer **out) {
+  IPB_TRY(enter(ctx));
+  if (!settings || !in || !out) return fail(ctx, IPB_ERR_INVALID, "null pointer");
+  if (settings->linear) {  // gamma.rs:17-18
+    ipb_buffer_retain(in);
+    *out = in;
+    return IPB_OK;
+  }
+  ipb_buffer *b;
+  IPB_TRY(new_buffer(ctx, in->width, in->height, in->colors, in->monochrome, false, &b));
+  cudaError_t e = launch_gamma(ctx->stream, ctx->lut_gamma, in->dptr, in->width * in->height * in->colors, b->dptr);
+  if (e != cudaSuccess) { ipb_buffer_release(b); return fail(ctx, IPB_ERR_CUDA, "gamma kernel: %s", cudaGetErrorString(e)); }
+  ctx->launches++;
+  *out = b;
+  return IPB_OK;
+}
+
+int ipb_transform_run(ipb_ctx *ctx, const ipb_transform *op, ipb_buffer *in, ipb_buffer **out) {
+  IPB_TRY(enter(ctx));
+  if (!op || !in || !out) return fail(ctx, IPB_ERR_INVALID, "null pointer");
+  int f[3];
+  orientation_flips(op, f);
+  if (!f[0] && !f[1] && !f[2]) {  // transform.rs:68-69
+    ipb_buffer_retain(in);
+    *out = in;
+    return IPB_OK;
+  }
+  if (in->colors != 3) return fail(ctx, IPB_ERR_BAD_COLORS, "transform: expected 3 channels, got %zu", in->colors);
+  ipb_buffer *b;
+  if (f[0]) IPB_TRY(new_buffer(ctx, in->height, in->width, 3, in->monochrome, false, &b));
+  else IPB_TRY(new_buffer(ctx, in->width, in->height, 3, in->monochrome, false, &b));
+  cudaError_t e = launch_rotate(ctx->stream, in->dptr, in->width, in->height, f[0], f[1], f[2], b->dptr);
+  if (e != cudaSuccess) { ipb_buffer_release(b); return fail(ctx, IPB_ERR_CUDA, "rotate kernel: %s", cudaGetErrorString(e)); }
+  ctx->launches++;
+  *out = b;
+  return IPB_OK;
+}
+
+// ---- host-only size negotiation
+
+void ipb_gofloat_transform_forward(const ipb_gofloat *op, size_t w, size_t h, size_t *ow, size_t *oh) {
+  size_t o[4];
+  size_image(op, w, h, o);
+  *ow = o[2];
+  *oh = o[3];
+}
+void ipb_rotatecrop_transform_forward(ipb_rotatecrop *op, size_t w, size_t h, size_t *ow, size_t *oh) {
+  if (op->has_output_size) { *ow = op->output_width; *oh = op->output_height; return; }  // rotatecrop.rs:67-69
+  op->input_ratio = (float)w / (float)h;
+  rc_calc_size(op, w, h, false, ow, oh);
+}
+void ipb_rotatecrop_transform_reverse(ipb_rotatecrop *op, size_t w, size_t h, size_t *ow, size_t *oh) {
+  op->has_output_size = 1;
+  op->output_width = w;
+  op->output_height = h;
+  rc_calc_size(op, w, h, true, ow, oh);
+}
+void ipb_rotatecrop_reset(ipb_rotatecrop *op) {
+  op->input_ratio = 1.0f;
+  op->has_output_size = 0;
+}
+void ipb_transform_transform_forward(const ipb_transform *op, size_t w, size_t h, size_t *ow, size_t *oh) {
+  if (op->rotation == IPB_ROT_90 || op->rotation == IPB_ROT_270) { *ow = h; *oh = w; }
+  else { *ow = w; *oh = h; }
+}
+void ipb_scaling_size(size_t w, size_t h, size_t maxw, size_t maxh, size_t *ow, size_t *oh) {
+  float s;
+  scaling_total(w, h, maxw, maxh, &s, ow, oh);
+}
+float ipb_calculate_scale(size_t w, size_t h, size_t maxw, size_t maxh) {
+  float s;
+  size_t a, b;
+  scaling_total(w, h, maxw, maxh, &s, &a, &b);
+  return s;
+}
+
+int ipb_spline_eval(ipb_ctx *ctx, const ipb_basecurve *op, const float *in, float *out, size_t n) {
+  IPB_TRY(enter(ctx));
+  if (!op || !in || !out) return fail(ctx, IPB_ERR_INVALID, "null pointer");
+  if (op->npoints > IPB_MAX_CURVE_POINTS) return fail(ctx, IPB_ERR_UNSUPPORTED, "too many curve points");
+  ipb_basecurve raw = *op;
+  raw.exposure = 0.0f;  // SplineFunc::new(&points) — no exposure scaling (curves.rs:53-55)
+  SplineDev sp;
+  memset(&sp, 0, sizeof(sp));
+  if (raw.npoints == 0) {  // SplineFunc::new(&[]) is the identity line through (0,0) and (1,1)
+    ipb_basecurve tmp = raw;
+    tmp.exposure = 1.0f;  // defeat the pass-through shortcut of build_spline; y's are not scaled with no points
+    if (!build_spline(&tmp, &sp)) return fail(ctx, IPB_ERR_INVALID, "degenerate curve");
+  } else if (!build_spline(&raw, &sp)) {
+    return fail(ctx, IPB_ERR_INVALID, "degenerate curve (the reference panics)");
+  }
+  float *d;
+  IPB_CUDA(ctx, cudaMallocAsync((void **)&d, 2 * (n ? n : 1) * sizeof(float), ctx->stream));
+  IPB_CUDA(ctx, cudaMemcpyAsync(d, in, n * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+  IPB_LAUNCH(ctx, launch_spline_eval(ctx->stream, sp, d, n, d + n));
+  IPB_CUDA(ctx, cudaMemcpyAsync(out, d + n, n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+  IPB_CUDA(ctx, cudaFreeAsync(d, ctx->stream));
+  IPB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return IPB_OK;
+}
+
+// ---- pack
+
+extern "C++" {
+template <typename T>
+static int pack_impl(ipb_ctx *ctx, const ipb_buffer *in, T *dst, int dst_on_device) {
+  IPB_TRY(enter(ctx));
+  if (!in || !dst) return fail(ctx, IPB_ERR_INVALID, "null pointer");
+  if (in->colors != 3) return fail(ctx, IPB_ERR_BAD_COLORS, "pack: expected 3 channels, got %zu", in->colors);
+  const size_t n = in->width * in->height * 3;
+  T *d = dst;
+  if (!dst_on_device) IPB_CUDA(ctx, cudaMallocAsync((void **)&d, (n ? n : 1) * sizeof(T), ctx->stream));
+  cudaError_t e = sizeof(T) == 1 ? launch_pack8(ctx->stream, in->dptr, n, (uint8_t *)d)
+                                 : launch_pack16(ctx->stream, in->dptr, n, (uint16_t *)d);
+  if (e != cudaSuccess) return fail(ctx, IPB_ERR_CUDA, "pack kernel: %s", cudaGetErrorString(e));
+  ctx->launches++;
+  if (!dst_on_device) {
+    IPB_CUDA(ctx, cudaMemcpyAsync(dst, d, n * sizeof(T), cudaMemcpyDeviceToHost, ctx->stream));
+    IPB_CUDA(ctx, cudaFreeAsync(d, ctx->stream));
+    IPB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+  return IPB_OK;
+}
+}  // extern "C++"
+int ipb_pack_8bit(ipb_ctx *ctx, const ipb_buffer *in, uint8_t *dst, int dst_on_device) {
+  return pack_impl<uint8_t>(ctx, in, dst, dst_on_device);
+}
+int ipb_pack_16bit(ipb_ctx *ctx, const ipb_buffer *in, uint16_t *dst, int dst_on_device) {
+  return pack_impl<uint16_t>(ctx, in, dst, dst_on_device);
+}
+
+extern "C++" {
+template <typename T>
+static int scale_srgb_impl(ipb_ctx *ctx, const T *src, size_t w, size_t h, size_t nw, size_t nh, T *dst, int on_device) {
+  IPB_TRY(enter(ctx));
+  if (!src || !dst) return fail(ctx, IPB_ERR_INVALID, "null pointer");
+  if (w == 0 || h == 0 || nw == 0 || nh == 0) return fail(ctx, IPB_ERR_INVALID, "empty image");
+  const size_t nin = w * h * 3, nout = nw * nh * 3;
+  const T *s = src;
+  T *d = dst;
+  T *tmp = nullptr;
+  if (!on_device) {
+    IPB_CUDA(ctx, cudaMallocAsync((void **)&tmp, (nin + nout) * sizeof(T), ctx->stream));
+    IPB_CUDA(ctx, cudaMemcpyAsync(tmp, src, nin * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+    s = tmp;
+    d = tmp + nin;
+  }
+  XformGeom g;
+  g.tl[0] = 0; g.tl[1] = 0; g.tr[0] = (long)w - 1; g.tr[1] = 0; g.bl[0] = 0; g.bl[1] = (long)h - 1;
+  g.width = w; g.height = h; g.nwidth = nw; g.nheight = nh; g.components = 3;
+  cudaError_t e = sizeof(T) == 1 ? launch_transform_u8(ctx->stream, g, (const uint8_t *)s, (uint8_t *)d)
+                                 : launch_transform_u16(ctx->stream, g, (const uint16_t *)s, (uint16_t *)d);
+  if (e != cudaSuccess) return fail(ctx, IPB_ERR_CUDA, "scale_down_srgb kernel: %s", cudaGetErrorString(e));
+  ctx->launches++;
+  if (!on_device) {
+    IPB_CUDA(ctx, cudaMemcpyAsync(dst, d, nout * sizeof(T), cudaMemcpyDeviceToHost, ctx->stream));
+    IPB_CUDA(ctx, cudaFreeAsync(tmp, ctx->stream));
+    IPB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+  return IPB_OK;
+}
+}  // extern "C++"
+int ipb_scale_down_srgb(ipb_ctx *ctx, const uint8_t *src, size_t w, size_t h, size_t nw, size_t nh, uint8_t *dst,
+                        int on_device) {
+  return scale_srgb_impl<uint8_t>(ctx, src, w, h, nw, nh, dst, on_device);
+}
+int ipb_scale_down_srgb16(ipb_ctx *ctx, const uint16_t *src, size_t w, size_t h, size_t nw, size_t nh, uint16_t *dst,
+                          int on_device) {
+  return scale_srgb_impl<uint16_t>(ctx, src, w, h, nw, nh, dst, on_device);
+}
+
+// ------------------------------------------------------------------------------------------------ Pipeline
+
+void ipb_ops_default(ipb_ops *ops, const ipb_source *image) {
+  const HostTables &T = tables();
+  memset(ops, 0, sizeof(*ops));
+  ops->rotatecrop.input_ratio = 1.0f;  // rotatecrop.rs:27-36
+  const bool raw = image->kind == IPB_SRC_RAW_U16 || image->kind == IPB_SRC_RAW_F32;
+  if (raw) {
+    ops->gofloat.is_cfa = 1;  // filled from metadata by the caller (gofloat.rs:20-31)
+    ops->basecurve.npoints = 1;  // curves.rs:14-20
+    ops->basecurve.points[0][0] = 0.50f;
+    ops->basecurve.points[0][1] = 0.60f;
+    for (int i = 0; i < 4; i++) ops->tolab.wb_coeffs[i] = 1.0f;
+  } else {
+    memcpy(ops->tolab.cam_to_xyz, T.srgb_d65_43, sizeof(T.srgb_d65_43));  // colorspaces.rs:48-55
+    memcpy(ops->tolab.cam_to_xyz_normalized, T.srgb_d65_43, sizeof(T.srgb_d65_43));
+    memcpy(ops->tolab.xyz_to_cam, T.xyz_d65_34, sizeof(T.xyz_d65_34));
+    ops->tolab.wb_coeffs[0] = 1.0f; ops->tolab.wb_coeffs[1] = 1.0f; ops->tolab.wb_coeffs[2] = 1.0f;
+    ops->tolab.wb_coeffs[3] = 0.0f;
+  }
+}
+
+int ipb_pipeline_create(ipb_ctx *ctx, const ipb_source *image, const ipb_ops *ops, ipb_pipeline **out) {
+  IPB_TRY(enter(ctx));
+  if (!image || !out) return fail(ctx, IPB_ERR_INVALID, "null pointer");
+  ipb_pipeline *p = new (std::nothrow) ipb_pipeline();
+  if (!p) return fail(ctx, IPB_ERR_NOMEM, "out of host memory");
+  p->ctx = ctx;
+  p->image = *image;
+  if (ops) p->ops = *ops; else ipb_ops_default(&p->ops, image);
+  memset(&p->settings, 0, sizeof(p->settings));
+  p->settings.use_fastpath = 1;  // pipeline.rs:121-130
+  *out = p;
+  return IPB_OK;
+}
+
+void ipb_pipeline_destroy(ipb_pipeline *p) {
+  if (!p) return;
+  cudaSetDevice(p->ctx->device);
+  cudaStreamSynchronize(p->ctx->stream);
+  if (p->stage_in) cudaFree(p->stage_in);
+  if (p->stage_out) cudaFree(p->stage_out);
+  delete p;
+}
+
+ipb_ops *ipb_pipeline_ops(ipb_pipeline *p) { return p ? &p->ops : nullptr; }
+ipb_settings *ipb_pipeline_settings(ipb_pipeline *p) { return p ? &p->settings : nullptr; }
+int ipb_pipeline_set_source(ipb_pipeline *p, const ipb_source *image) {
+  if (!p || !image) return IPB_ERR_INVALID;
+  p->image = *image;
+  p->has_stripe = false;
+  return IPB_OK;
+}
+int ipb_pipeline_set_fused(ipb_pipeline *p, int fused) {
+  if (!p) return IPB_ERR_INVALID;
+  p->fused = fused != 0;
+  return IPB_OK;
+}
+
+// pipeline.rs:313-338: reset, forward size walk, clamp to maxwidth/maxheight, reverse walk
+static void negotiate(ipb_pipeline *p, size_t *fw, size_t *fh) {
+  ipb_rotatecrop_reset(&p->ops.rotatecrop);
+  size_t width = p->image.width, height = p->image.height, w, h;
+  ipb_gofloat_transform_forward(&p->ops.gofloat, width, height, &w, &h); width = w; height = h;
+  ipb_rotatecrop_transform_forward(&p->ops.rotatecrop, width, height, &w, &h); width = w; height = h;
+  ipb_transform_transform_forward(&p->ops.transform, width, height, &w, &h); width = w; height = h;
+  ipb_scaling_size(width, height, p->settings.maxwidth, p->settings.maxheight, &w, &h); width = w; height = h;
+  if (fw) *fw = width;
+  if (fh) *fh = height;
+  ipb_transform_transform_forward(&p->ops.transform, width, height, &w, &h); width = w; height = h;  // transform.rs:82-84
+  ipb_rotatecrop_transform_reverse(&p->ops.rotatecrop, width, height, &w, &h); width = w; height = h;
+  p->settings.demosaic_width = width;
+  p->settings.demosaic_height = height;
+}
+
+int ipb_pipeline_output_size(ipb_pipeline *p, size_t *width, size_t *height) {
+  if (!p) return IPB_ERR_INVALID;
+  if (p->image.width < 10 || p->image.height < 10) return fail(p->ctx, IPB_ERR_INVALID, "source smaller than 10x10");
+  negotiate(p, width, height);
+  return IPB_OK;
+}
+
+// What the fused kernels can take over: a u16 CFA source through gofloat's CFA branch, a pass-through
+// rotatecrop, and either demosaic branch that starts from the 1-channel buffer without an intermediate
+// full-size image (demosaic.rs:47-50 scaled, :51-60 with scale <= 1 full).
+enum FusedMode { kNotFused = 0, kFusedFull = 1, kFusedScaled = 2 };
+struct FusedPlan {
+  FusedMode mode = kNotFused;
+  CfaDev cfa;
+  size_t crop_x = 0, crop_y = 0, width = 0, height = 0;  // cropped frame
+  size_t out_width = 0, out_height = 0;                  // demosaic output == fused output
+};
+
+static int plan_fused(ipb_pipeline *p, FusedPlan *plan) {
+  plan->mode = kNotFused;
+  if (!p->fused) return IPB_OK;
+  const ipb_source &img = p->image;
+  if (img.kind != IPB_SRC_RAW_U16 || img.cpp != 1 || !p->ops.gofloat.is_cfa) return IPB_OK;
+  if (!rc_noop(&p->ops.rotatecrop)) return IPB_OK;
+  if (parse_cfa(p->ops.demosaic.cfa, &plan->cfa) != IPB_OK || plan->cfa.width == 0) return IPB_OK;
+  if (p->ops.basecurve.npoints > IPB_MAX_CURVE_POINTS) return IPB_OK;
+  if (img.width >= (1u << 30) || img.height >= (1u << 30)) return IPB_OK;
+  size_t xywh[4];
+  size_image(&p->ops.gofloat, img.width, img.height, xywh);
+  plan->crop_x = xywh[0]; plan->crop_y = xywh[1]; plan->width = xywh[2]; plan->height = xywh[3];
+  float scale;
+  size_t sw, sh;
+  scaling_total(plan->width, plan->height, p->settings.demosaic_width, p->settings.demosaic_height, &scale, &sw, &sh);
+  if (scale >= cfa_minscale(plan->cfa)) {
+    plan->mode = kFusedScaled;
+    plan->out_width = p->settings.demosaic_width;
+    plan->out_height = p->settings.demosaic_height;
+    if (plan->out_width < 2 || plan->out_height < 2) plan->mode = kNotFused;
+  } else if (scale <= 1.0f) {
+    plan->mode = kFusedFull;
+    plan->out_width = plan->width;
+    plan->out_height = plan->height;
+  }
+  return IPB_OK;
+}
+
+static int fill_color_params(ipb_pipeline *p, const FusedPlan &plan, ColorParams *P) {
+  memset(P, 0, sizeof(*P));
+  fill_tolab(P, &p->ops.tolab, 0);
+  // the E channel is identically zero when the pattern has no colour 3 and its matrix column is finite
+  bool has_e = false;
+  for (int i = 0; i < 48 * 48; i++) has_e |= plan.cfa.pat[i] == 3;
+  P->use_e = (has_e || !std::isfinite(P->cm[3]) || !std::isfinite(P->cm[7]) || !std::isfinite(P->cm[11]) ||
+              !std::isfinite(P->mul[3])) ? 1 : 0;
+  P->linear = p->settings.linear ? 1 : 0;
+  if (!build_spline(&p->ops.basecurve, &P->sp)) return fail(p->ctx, IPB_ERR_INVALID, "basecurve: degenerate curve");
+  return IPB_OK;
+}
+
+// source rows (un-cropped sensor coordinates) needed for output rows [r0, r1) of the fused path
+static void fused_src_rows(const ipb_pipeline *p, const FusedPlan &plan, size_t r0, size_t r1, size_t *s0, size_t *s1) {
+  size_t a, b;
+  if (plan.mode == kFusedFull) {
+    a = r0 > 0 ? r0 - 1 : 0;
+    b = r1 + 1 < plan.height ? r1 + 1 : plan.height;
+  } else {
+    // scaling.rs:72,79-80,86-87 with topleft (0,0): from_y = floor(skip_y_y * row), to_y = floor(skip_y_y * (row+1))
+    const float skip_y = ((float)((long)plan.height - 1) - 0.0f) / (float)(plan.out_height - 1);
+    auto clampy = [&](float f) { size_t v = f2usize(floorf(f)); return v < plan.height - 1 ? v : plan.height - 1; };
+    a = clampy(0.0f + skip_y * (float)r0);
+    b = clampy(0.0f + skip_y * (float)r1) + 1;  // to_y of the last row r1-1 uses (row+1) == r1
+  }
+  *s0 = a + plan.crop_y;
+  *s1 = b + plan.crop_y;
+  (void)p;
+}
+
+static int ensure_stage(ipb_ctx *ctx, void **buf, size_t *have, size_t need) {
+  if (*have >= need) return IPB_OK;
+  if (*buf) {
+    IPB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    IPB_CUDA(ctx, cudaFree(*buf));
+    *buf = nullptr;
+    *have = 0;
+  }
+  IPB_CUDA(ctx, cudaMalloc(buf, need));
+  *have = need;
+  return IPB_OK;
+}
+
+// Launch the fused kernel for output rows [r0, r1) into `out` (device, row r0 first).
+static int run_fused(ipb_pipeline *p, const FusedPlan &plan, int out_kind, size_t r0, size_t r1, void *out) {
+  ipb_ctx *ctx = p->ctx;
+  ColorParams P;
+  IPB_TRY(fill_color_params(p, plan, &P));
+  // which source rows do we have?
+  const ipb_source &src = p->has_stripe ? p->stripe_rows : p->image;
+  const size_t have0 = p->has_stripe ? p->stripe.src_row0 : 0;
+  const size_t have1 = have0 + src.height;
+  size_t need0, need1;
+  fused_src_rows(p, plan, r0, r1, &need0, &need1);
+  if (need0 < have0 || need1 > have1)
+    return fail(ctx, IPB_ERR_INVALID, "stripe holds source rows [%zu,%zu) but output rows [%zu,%zu) need [%zu,%zu)", have0,
+                have1, r0, r1, need0, need1);
+  const uint16_t *raw = (const uint16_t *)src.data;
+  if (!src.on_device) {
+    // copy just the rows this launch needs
+    const size_t bytes = (need1 - need0) * src.width * sizeof(uint16_t);
+    IPB_TRY(ensure_stage(ctx, &p->stage_in, &p->stage_in_bytes, bytes));
+    IPB_CUDA(ctx, cudaMemcpyAsync(p->stage_in, raw + (need0 - have0) * src.width, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    raw = (const uint16_t *)p->stage_in;
+  } else {
+    raw += (need0 - have0) * src.width;
+  }
+  FusedArgs a;
+  memset(&a, 0, sizeof(a));
+  a.raw = raw;
+  a.raw_pitch = src.width;
+  a.src_row0 = need0;
+  a.src_rows = need1 - need0;
+  a.crop_x = plan.crop_x; a.crop_y = plan.crop_y;
+  a.width = plan.width; a.height = plan.height;
+  a.out_row0 = r0; a.out_row1 = r1;
+  a.out_width = plan.out_width; a.out_height = plan.out_height;
+  a.out = out;
+  a.out_kind = out_kind;
+  a.black = p->ops.gofloat.blacklevels[0];
+  a.range = p->ops.gofloat.whitelevels[0] - a.black;  // gofloat.rs:86-89
+  a.range_rc = 1.0f / a.range;
+  a.exact_rc = golevel_rc_exact(a.black, a.range, a.range_rc) ? 1 : 0;
+  a.lut_lab = ctx->lut_lab;
+  a.lut_gamma = ctx->lut_gamma;
+  cudaError_t e = plan.mode == kFusedFull ? launch_fused_full(ctx->stream, a, plan.cfa, P, ctx->sm_count)
+                                          : launch_fused_scaled(ctx->stream, a, plan.cfa, P, ctx->sm_count);
+  if (e != cudaSuccess) return fail(ctx, IPB_ERR_CUDA, "fused kernel: %s %s", cudaGetErrorString(e), fused_last_error());
+  ctx->launches++;
+  return IPB_OK;
+}
+
+// op-by-op Pipeline::run (pipeline.rs:364-372 with cache == None), starting from the source
+static int run_unfused(ipb_pipeline *p, ipb_buffer **out) {
+  ipb_ctx *ctx = p->ctx;
+  ipb_buffer *cur = nullptr, *next = nullptr;
+  IPB_TRY(ipb_gofloat_run(ctx, &p->ops.gofloat, &p->image, &cur));
+#define STEP(call)                                  \
+  do {                                              \
+    int rc_ = (call);                               \
+    ipb_buffer_release(cur);                        \
+    if (rc_ != IPB_OK) return rc_;                  \
+    cur = next;                                     \
+  } while (0)
+  STEP(ipb_demosaic_run(ctx, &p->ops.demosaic, &p->settings, cur, &next));
+  STEP(ipb_rotatecrop_run(ctx, &p->ops.rotatecrop, cur, &next));
+  STEP(ipb_tolab_run(ctx, &p->ops.tolab, cur, &next));
+  STEP(ipb_basecurve_run(ctx, &p->ops.basecurve, cur, &next));
+  STEP(ipb_fromlab_run(ctx, cur, &next));
+  STEP(ipb_gamma_run(ctx, &p->settings, cur, &next));
+  STEP(ipb_transform_run(ctx, &p->ops.transform, cur, &next));
+#undef STEP
+  *out = cur;
+  return IPB_OK;
+}
+
+int ipb_pipeline_run(ipb_pipeline *p, ipb_buffer **out) {
+  if (!p || !out) return IPB_ERR_INVALID;
+  ipb_ctx *ctx = p->ctx;
+  IPB_TRY(enter(ctx));
+  if (p->image.width < 10 || p->image.height < 10) return fail(ctx, IPB_ERR_INVALID, "source smaller than 10x10");
+  if (p->has_stripe) return fail(ctx, IPB_ERR_UNSUPPORTED, "pipeline_run on a stripe source: use output_8bit_stripe");
+  negotiate(p, nullptr, nullptr);
+  FusedPlan plan;
+  IPB_TRY(plan_fused(p, &plan));
+  if (plan.mode == kNotFused) return run_unfused(p, out);
+  ipb_buffer *b;
+  IPB_TRY(new_buffer(ctx, plan.out_width, plan.out_height, 3, 0, false, &b));
+  int rc = run_fused(p, plan, kOutF32, 0, plan.out_height, b->dptr);
+  if (rc != IPB_OK) { ipb_buffer_release(b); return rc; }
+  ipb_buffer *t;
+  rc = ipb_transform_run(ctx, &p->ops.transform, b, &t);
+  ipb_buffer_release(b);
+  if (rc != IPB_OK) return rc;
+  *out = t;
+  return IPB_OK;
+}
+
+static bool ops_are_default_other(const ipb_pipeline *p) {  // Pipeline::default_ops (pipeline.rs:286-288)
+  ipb_ops d;
+  ipb_ops_default(&d, &p->image);
+  const ipb_ops &a = p->ops;
+  if (memcmp(&a.gofloat, &d.gofloat, sizeof(a.gofloat))) return false;
+  if (strncmp(a.demosaic.cfa, d.demosaic.cfa, sizeof(a.demosaic.cfa))) return false;
+  if (a.rotatecrop.crop_top != 0 || a.rotatecrop.crop_right != 0 || a.rotatecrop.crop_bottom != 0 ||
+      a.rotatecrop.crop_left != 0 || a.rotatecrop.rotation != 0) return false;
+  if (memcmp(&a.tolab, &d.tolab, sizeof(a.tolab))) return false;
+  if (a.basecurve.exposure != 0 || a.basecurve.npoints != 0) return false;
+  if (a.transform.rotation != 0 || a.transform.fliph || a.transform.flipv) return false;
+  return true;
+}
+
+extern "C++" {
+template <typename T>
+static int output_impl(ipb_pipeline *p, T *dst, size_t cap, int dst_on_device, size_t *width, size_t *height) {
+  if (!p || !dst) return IPB_ERR_INVALID;
+  ipb_ctx *ctx = p->ctx;
+  IPB_TRY(enter(ctx));
+  if (p->image.width < 10 || p->image.height < 10) return fail(ctx, IPB_ERR_INVALID, "source smaller than 10x10");
+  if (p->has_stripe) return fail(ctx, IPB_ERR_UNSUPPORTED, "stripe source: use output_8bit_stripe");
+  const bool other = p->image.kind == IPB_SRC_RGB8 || p->image.kind == IPB_SRC_RGB16;
+  const bool want8 = sizeof(T) == 1;
+
+  if (other && p->settings.use_fastpath && ops_are_default_other(p)) {  // pipeline.rs:381-402 / :428-449
+    const size_t w = p->image.width, h = p->image.height, n = w * h * 3;
+    size_t nw, nh;
+    ipb_scaling_size(w, h, p->settings.maxwidth, p->settings.maxheight, &nw, &nh);
+    if (nw * nh * 3 > cap) return fail(ctx, IPB_ERR_INVALID, "destination too small: %zu < %zu", cap, nw * nh * 3);
+    const bool same_depth = (p->image.kind == IPB_SRC_RGB8) == want8;
+    const bool scale = nw != w || nh != h;
+    DevSrc src;
+    IPB_TRY(device_source(ctx, &p->image, &src));
+    T *conv = nullptr;  // source raster at the output bit depth, on the device
+    const T *raster = (const T *)src.ptr;
+    if (!same_depth) {
+      IPB_CUDA(ctx, cudaMallocAsync((void **)&conv, (n ? n : 1) * sizeof(T), ctx->stream));
+      if (want8) IPB_LAUNCH(ctx, launch_rgb16_to_8(ctx->stream, (const uint16_t *)src.ptr, n, (uint8_t *)conv));
+      else IPB_LAUNCH(ctx, launch_rgb8_to_16(ctx->stream, (const uint8_t *)src.ptr, n, (uint16_t *)conv));
+      raster = conv;
+    }
+    T *d = dst;
+    if (!dst_on_device) IPB_CUDA(ctx, cudaMallocAsync((void **)&d, nw * nh * 3 * sizeof(T), ctx->stream));
+    if (scale) {
+      XformGeom g;
+      g.tl[0] = 0; g.tl[1] = 0; g.tr[0] = (long)w - 1; g.tr[1] = 0; g.bl[0] = 0; g.bl[1] = (long)h - 1;
+      g.width = w; g.height = h; g.nwidth = nw; g.nheight = nh; g.components = 3;
+      if (want8) IPB_LAUNCH(ctx, launch_transform_u8(ctx->stream, g, (const uint8_t *)raster, (uint8_t *)d));
+      else IPB_LAUNCH(ctx, launch_transform_u16(ctx->stream, g, (const uint16_t *)raster, (uint16_t *)d));
+    } else {
+      IPB_CUDA(ctx, cudaMemcpyAsync(d, raster, n * sizeof(T), cudaMemcpyDeviceToDevice, ctx->stream));
+    }
+    if (!dst_on_device) {
+      IPB_CUDA(ctx, cudaMemcpyAsync(dst, d, nw * nh * 3 * sizeof(T), cudaMemcpyDeviceToHost, ctx->stream));
+      IPB_CUDA(ctx, cudaFreeAsync(d, ctx->stream));
+    }
+    if (conv) IPB_CUDA(ctx, cudaFreeAsync(conv, ctx->stream));
+    release_source(ctx, &src);
+    if (!dst_on_device) IPB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (width) *width = nw;
+    if (height) *height = nh;
+    return IPB_OK;
+  }
+
+  p->settings.linear = want8 ? 0 : 1;  // pipeline.rs:405 / :452
+  size_t fw, fh;
+  negotiate(p, &fw, &fh);
+  FusedPlan plan;
+  IPB_TRY(plan_fused(p, &plan));
+  int flips[3];
+  orientation_flips(&p->ops.transform, flips);
+  const bool normal = !flips[0] && !flips[1] && !flips[2];
+  if (plan.mode != kNotFused && normal) {
+    const size_t n = plan.out_width * plan.out_height * 3;
+    if (n > cap) return fail(ctx, IPB_ERR_INVALID, "destination too small: %zu < %zu", cap, n);
+    T *d = dst;
+    if (!dst_on_device) {
+      IPB_TRY(ensure_stage(ctx, &p->stage_out, &p->stage_out_bytes, n * sizeof(T)));
+      d = (T *)p->stage_out;
+    }
+    IPB_TRY(run_fused(p, plan, want8 ? kOutU8 : kOutU16, 0, plan.out_height, d));
+    if (!dst_on_device) {
+      IPB_CUDA(ctx, cudaMemcpyAsync(dst, d, n * sizeof(T), cudaMemcpyDeviceToHost, ctx->stream));
+      IPB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    if (width) *width = plan.out_width;
+    if (height) *height = plan.out_height;
+    return IPB_OK;
+  }
+  ipb_buffer *b;
+  IPB_TRY(ipb_pipeline_run(p, &b));
+  const size_t n = b->width * b->height * 3;
+  int rc = IPB_OK;
+  if (n > cap) rc = fail(ctx, IPB_ERR_INVALID, "destination too small: %zu < %zu", cap, n);
+  else rc = pack_impl<T>(ctx, b, dst, dst_on_device);
+  if (width) *width = b->width;
+  if (height) *height = b->height;
+  ipb_buffer_release(b);
+  return rc;
+}
+
+}  // extern "C++"
+int ipb_pipeline_output_8bit(ipb_pipeline *p, uint8_t *dst, size_t dst_capacity, int dst_on_device, size_t *width,
+                             size_t *height) {
+  return output_impl<uint8_t>(p, dst, dst_capacity, dst_on_device, width, height);
+}
+int ipb_pipeline_output_16bit(ipb_pipeline *p, uint16_t *dst, size_t dst_capacity, int dst_on_device, size_t *width,
+                              size_t *height) {
+  return output_impl<uint16_t>(p, dst, dst_capacity, dst_on_device, width, height);
+}
+
+// ---- row stripes
+
+static int stripe_plan(ipb_pipeline *p, FusedPlan *plan) {
+  ipb_ctx *ctx = p->ctx;
+  if (p->image.width < 10 || p->image.height < 10) return fail(ctx, IPB_ERR_INVALID, "source smaller than 10x10");
+  p->settings.linear = 0;
+  negotiate(p, nullptr, nullptr);
+  IPB_TRY(plan_fused(p, plan));
+  int flips[3];
+  orientation_flips(&p->ops.transform, flips);
+  if (plan->mode == kNotFused || flips[0] || flips[1] || flips[2])
+    return fail(ctx, IPB_ERR_UNSUPPORTED, "row stripes need the fused CFA path with a Normal orientation");
+  return IPB_OK;
+}
+
+int ipb_pipeline_stripe_rows(ipb_pipeline *p, size_t out_row0, size_t out_row1, size_t *src_row0, size_t *src_row1) {
+  if (!p || !src_row0 || !src_row1) return IPB_ERR_INVALID;
+  FusedPlan plan;
+  IPB_TRY(stripe_plan(p, &plan));
+  if (out_row0 >= out_row1 || out_row1 > plan.out_height)
+    return fail(p->ctx, IPB_ERR_INVALID, "output rows [%zu,%zu) outside the %zu-row result", out_row0, out_row1, plan.out_height);
+  fused_src_rows(p, plan, out_row0, out_row1, src_row0, src_row1);
+  return IPB_OK;
+}
+
+int ipb_pipeline_set_stripe_source(ipb_pipeline *p, const ipb_source *rows, const ipb_stripe *stripe) {
+  if (!p || !rows || !stripe) return IPB_ERR_INVALID;
+  if (rows->kind != IPB_SRC_RAW_U16 || rows->cpp != 1 || rows->width != p->image.width)
+    return fail(p->ctx, IPB_ERR_INVALID, "stripe rows must be u16 CFA rows of the pipeline's sensor width");
+  if (stripe->full_height != p->image.height || stripe->src_row0 + rows->height > p->image.height)
+    return fail(p->ctx, IPB_ERR_INVALID, "stripe does not fit the %zu-row frame", p->image.height);
+  p->stripe_rows = *rows;
+  p->stripe = *stripe;
+  p->has_stripe = true;
+  return IPB_OK;
+}
+
+int ipb_pipeline_output_8bit_stripe(ipb_pipeline *p, uint8_t *dst, size_t dst_capacity, int dst_on_device,
+                                    size_t *width, size_t *rows) {
+  if (!p || !dst) return IPB_ERR_INVALID;
+  ipb_ctx *ctx = p->ctx;
+  IPB_TRY(enter(ctx));
+  if (!p->has_stripe) return fail(ctx, IPB_ERR_INVALID, "no stripe source set");
+  FusedPlan plan;
+  IPB_TRY(stripe_plan(p, &plan));
+  const size_t r0 = p->stripe.out_row0, r1 = p->stripe.out_row1;
+  if (r0 >= r1 || r1 > plan.out_height) return fail(ctx, IPB_ERR_INVALID, "stripe output rows [%zu,%zu) outside the %zu-row result", r0, r1, plan.out_height);
+  const size_t n = (r1 - r0) * plan.out_width * 3;
+  if (n > dst_capacity) return fail(ctx, IPB_ERR_INVALID, "destination too small: %zu < %zu", dst_capacity, n);
+  uint8_t *d = dst;
+  if (!dst_on_device) {
+    IPB_TRY(ensure_stage(ctx, &p->stage_out, &p->stage_out_bytes, n));
+    d = (uint8_t *)p->stage_out;
+  }
+  IPB_TRY(run_fused(p, plan, kOutU8, r0, r1, d));
+  if (!dst_on_device) {
+    IPB_CUDA(ctx, cudaMemcpyAsync(dst, d, n, cudaMemcpyDeviceToHost, ctx->stream));
+    IPB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+  if (width) *width = plan.out_width;
+  if (rows) *rows = r1 - r0;
+  return IPB_OK;
+}
+
+int ipb_synth_cfa_u16(ipb_ctx *ctx, uint64_t seed, size_t width, size_t row0, size_t rows, uint16_t *dptr) {
+  IPB_TRY(enter(ctx));
+  if (!dptr) return fail(ctx, IPB_ERR_INVALID, "null pointer");
+  IPB_LAUNCH(ctx, launch_synth(ctx->stream, seed, width, row0, rows, dptr));
+  return IPB_OK;
+}
+
+}  // extern "C"

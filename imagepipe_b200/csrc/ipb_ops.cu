@@ -1,0 +1,462 @@
+// ipb_ops.cu — one CUDA kernel per ImageOp of the reference (the "unfused" path): each op reads one
+// device OpBuffer and writes a new one, exactly like the reference's per-op passes.  These kernels are
+// the per-op entry points of the C ABI (ipb_*_run) and the building blocks for chains the fused kernels
+// do not cover.  They are HBM-bound elementwise / stencil passes: one thread per pixel (or element),
+// consecutive threads on consecutive addresses, grid sized to cover the buffer.
+#include "ipb_internal.h"
+
+namespace ipb {
+
+static inline unsigned grid_for(size_t n, unsigned block) {
+  size_t g = (n + block - 1) / block;
+  return (unsigned)(g ? g : 1);
+}
+
+// ------------------------------------------------------------------ K1 gofloat (gofloat.rs:84-201)
+
+template <typename T>
+__global__ void k_gofloat_raw(const T *__restrict__ src, size_t total, size_t owidth, size_t x, size_t y,
+                              size_t width, size_t height, size_t cpp, int mode, float m0, float m1, float m2,
+                              float r0, float r1, float r2, float *__restrict__ out) {
+  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (mode == 2) {  // CFA / plain: cpp channels, level index 0 only (gofloat.rs:122-130)
+    size_t linelen = width * cpp;
+    if (idx >= linelen * height) return;
+    size_t row = idx / linelen, c = idx - row * linelen;
+    size_t off = owidth * (row + y) + x + c;
+    if (off < total) out[idx] = fminf(__fdiv_rn((float)src[off] - m0, r0), 1.0f);
+    return;
+  }
+  if (idx >= width * height) return;
+  size_t row = idx / width, col = idx - row * width;
+  float4 o;
+  if (mode == 0) {  // monochrome -> RGB (gofloat.rs:97-109)
+    float v = fminf(__fdiv_rn((float)src[owidth * (row + y) + x + col] - m0, r0), 1.0f);
+    o = make_float4(v, v, v, 0.0f);
+  } else {  // 3 cpp -> four channel (gofloat.rs:110-121)
+    const T *p = src + (owidth * (row + y) + x + col) * 3;
+    o.x = fminf(__fdiv_rn((float)p[0] - m0, r0), 1.0f);
+    o.y = fminf(__fdiv_rn((float)p[1] - m1, r1), 1.0f);
+    o.z = fminf(__fdiv_rn((float)p[2] - m2, r2), 1.0f);
+    o.w = 0.0f;
+  }
+  reinterpret_cast<float4 *>(out)[idx] = o;
+}
+
+cudaError_t launch_gofloat_raw(cudaStream_t s, int is_f32, const void *src, size_t total, size_t owidth, size_t x,
+                               size_t y, size_t width, size_t height, size_t cpp, int mode, const float mins[4],
+                               const float ranges[4], float *out) {
+  size_t n = mode == 2 ? width * cpp * height : width * height;
+  if (n == 0) return cudaSuccess;
+  if (is_f32)
+    k_gofloat_raw<float><<<grid_for(n, 256), 256, 0, s>>>((const float *)src, total, owidth, x, y, width, height, cpp,
+                                                          mode, mins[0], mins[1], mins[2], ranges[0], ranges[1],
+                                                          ranges[2], out);
+  else
+    k_gofloat_raw<uint16_t><<<grid_for(n, 256), 256, 0, s>>>((const uint16_t *)src, total, owidth, x, y, width,
+                                                             height, cpp, mode, mins[0], mins[1], mins[2], ranges[0],
+                                                             ranges[1], ranges[2], out);
+  return cudaGetLastError();
+}
+
+// run_other (gofloat.rs:171-201): RGB8 through input8bit + expand_srgb_gamma, RGB16 through input16bit
+template <typename T>
+__global__ void k_gofloat_other(const T *__restrict__ src, size_t owidth, size_t x, size_t y, size_t width,
+                                size_t height, const float2 *__restrict__ lut_rev, float *__restrict__ out) {
+  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= width * height) return;
+  size_t row = idx / width, col = idx - row * width;
+  const T *p = src + (owidth * (row + y) + x + col) * 3;
+  float4 o;
+  if (sizeof(T) == 1) {
+    LutGlobal lut{lut_rev};
+    o.x = lut_lerp(lut, IPB_DIVC((float)p[0], 255.0f));
+    o.y = lut_lerp(lut, IPB_DIVC((float)p[1], 255.0f));
+    o.z = lut_lerp(lut, IPB_DIVC((float)p[2], 255.0f));
+  } else {
+    o.x = IPB_DIVC((float)p[0], 65535.0f);
+    o.y = IPB_DIVC((float)p[1], 65535.0f);
+    o.z = IPB_DIVC((float)p[2], 65535.0f);
+  }
+  o.w = 0.0f;
+  reinterpret_cast<float4 *>(out)[idx] = o;
+}
+
+cudaError_t launch_gofloat_other(cudaStream_t s, int is16, const void *src, size_t owidth, size_t x, size_t y,
+                                 size_t width, size_t height, const float2 *lut_rev, float *out) {
+  size_t n = width * height;
+  if (n == 0) return cudaSuccess;
+  if (is16)
+    k_gofloat_other<uint16_t><<<grid_for(n, 256), 256, 0, s>>>((const uint16_t *)src, owidth, x, y, width, height,
+                                                               lut_rev, out);
+  else
+    k_gofloat_other<uint8_t><<<grid_for(n, 256), 256, 0, s>>>((const uint8_t *)src, owidth, x, y, width, height,
+                                                              lut_rev, out);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------ K2 demosaic::full (demosaic.rs:67-119)
+
+__global__ void k_demosaic_full(const __grid_constant__ CfaDev cfa, const float *__restrict__ in, int w, int h,
+                                float *__restrict__ out) {
+  __shared__ uint8_t pat[48 * 48];
+  for (int i = threadIdx.x; i < 48 * 48; i += blockDim.x) pat[i] = cfa.pat[i];
+  __syncthreads();
+  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (size_t)w * h) return;
+  int row = (int)(idx / w), col = (int)(idx - (size_t)row * w);
+  int pr = row % 48, pc = col % 48;
+  int pixcolor = pat[pr * 48 + pc];
+  float sums[4] = {0.f, 0.f, 0.f, 0.f}, counts[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int dy = -1; dy <= 1; dy++) {
+#pragma unroll
+    for (int dx = -1; dx <= 1; dx++) {
+      int r = row + dy, c = col + dx;
+      int oc = pat[((pr + 48 + dy) % 48) * 48 + (pc + 48 + dx) % 48];
+      // taps of the centre's own colour (other than the centre itself) go to the discarded bin 4 (:87)
+      bool keep = (oc != pixcolor) || (dx == 0 && dy == 0);
+      if (keep && r >= 0 && r < h && c >= 0 && c < w) {
+        float v = in[(size_t)r * w + c];
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+          if (oc == k) { sums[k] += v; counts[k] += 1.0f; }
+      }
+    }
+  }
+  float4 o;
+  o.x = counts[0] > 0.f ? __fdiv_rn(sums[0], counts[0]) : 0.f;
+  o.y = counts[1] > 0.f ? __fdiv_rn(sums[1], counts[1]) : 0.f;
+  o.z = counts[2] > 0.f ? __fdiv_rn(sums[2], counts[2]) : 0.f;
+  o.w = counts[3] > 0.f ? __fdiv_rn(sums[3], counts[3]) : 0.f;
+  reinterpret_cast<float4 *>(out)[idx] = o;
+}
+
+cudaError_t launch_demosaic_full(cudaStream_t s, const CfaDev &cfa, const float *in, size_t w, size_t h, float *out) {
+  size_t n = w * h;
+  if (n == 0) return cudaSuccess;
+  k_demosaic_full<<<grid_for(n, 256), 256, 0, s>>>(cfa, in, (int)w, (int)h, out);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------ K3 transform_buffer<T> (scaling.rs:51-130)
+
+struct XformDev {
+  float tl0, tl1, skip_x_x, skip_x_y, skip_y_x, skip_y_y;
+  size_t width, height, nwidth, nheight;
+  int components;
+};
+
+template <typename T> __device__ __forceinline__ float as_f32(T v) { return (float)v; }
+template <typename T> __device__ __forceinline__ T from_f32(float v);
+template <> __device__ __forceinline__ float from_f32<float>(float v) { return v; }
+// Rust `as u8` / `as u16`: saturating, NaN -> 0 (cvt.rzi.u32.f32 has the same semantics)
+template <> __device__ __forceinline__ uint8_t from_f32<uint8_t>(float v) { return (uint8_t)min(__float2uint_rz(v), 255u); }
+template <> __device__ __forceinline__ uint16_t from_f32<uint16_t>(float v) { return (uint16_t)min(__float2uint_rz(v), 65535u); }
+
+__device__ __forceinline__ size_t f2usize(float f) { return (size_t)__float2ull_rz(f); }  // saturating, NaN -> 0
+
+template <typename T, bool CFA>
+__global__ void k_transform_buffer(const XformDev g, const __grid_constant__ CfaDev cfa, const T *__restrict__ src,
+                                   T *__restrict__ out) {
+  __shared__ uint8_t cfa_pat[CFA ? 48 * 48 : 1];
+  if (CFA) {
+    for (int i = threadIdx.x; i < 48 * 48; i += blockDim.x) cfa_pat[i] = cfa.pat[i];
+    __syncthreads();
+  }
+  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= g.nwidth * g.nheight) return;
+  size_t row = idx / g.nwidth, col = idx - row * g.nwidth;
+  const float frow = (float)row, frow1 = (float)(row + 1), fcol = (float)col, fcol1 = (float)(col + 1);
+  // per-row terms (scaling.rs:77-82)
+  float rfrom_x = g.tl0 + g.skip_y_x * frow;
+  float rto_x = g.tl0 + g.skip_y_x * frow1;
+  float rfrom_y = g.tl1 + g.skip_y_y * frow;
+  float rto_y = g.tl1 + g.skip_y_y * frow1;
+  float rcenter_x = g.tl0 + (g.skip_y_x * frow) + __fdiv_rn(g.skip_y_x, 2.0f) - 0.5f;
+  float rcenter_y = g.tl1 + (g.skip_y_y * frow) + __fdiv_rn(g.skip_y_y, 2.0f) - 0.5f;
+  // per-pixel window (scaling.rs:84-89)
+  size_t from_x = min(g.width - 1, f2usize(floorf(rfrom_x + (g.skip_x_x * fcol))));
+  size_t to_x = min(g.width - 1, f2usize(floorf(rto_x + (g.skip_x_x * fcol1))));
+  size_t from_y = min(g.height - 1, f2usize(floorf(rfrom_y + (g.skip_x_y * fcol))));
+  size_t to_y = min(g.height - 1, f2usize(floorf(rto_y + (g.skip_x_y * fcol1))));
+  float center_x = rcenter_x + (g.skip_x_x * fcol) + __fdiv_rn(g.skip_x_x, 2.0f);
+  float center_y = rcenter_y + (g.skip_x_y * fcol) + __fdiv_rn(g.skip_x_y, 2.0f);
+
+  float sums[4] = {0.f, 0.f, 0.f, 0.f}, counts[4] = {0.f, 0.f, 0.f, 0.f};
+  const int comps = g.components;
+  for (size_t y = from_y; y <= to_y; y++) {
+    float delta_y = __fdiv_rn((float)y - center_y, g.skip_y_y);
+    float dy2 = delta_y * delta_y;
+    for (size_t x = from_x; x <= to_x; x++) {
+      float delta_x = __fdiv_rn((float)x - center_x, g.skip_x_x);
+      float factor = 1.0f - (delta_x * delta_x) - dy2;
+      factor = factor < 0.0f ? 0.0f : factor;
+      if (CFA) {
+        int c = cfa_pat[(y % 48) * 48 + (x % 48)];
+        float v = as_f32(src[y * g.width + x]) * factor;
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+          if (c == k) { sums[k] += v; counts[k] += factor; }
+      } else {
+        const T *p = src + (y * g.width + x) * comps;
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+          if (k < comps) { sums[k] += as_f32(p[k]) * factor; counts[k] += factor; }
+      }
+    }
+  }
+  T *o = out + idx * comps;
+#pragma unroll
+  for (int k = 0; k < 4; k++)
+    if (k < comps) o[k] = counts[k] > 0.0f ? from_f32<T>(__fdiv_rn(sums[k], counts[k])) : from_f32<T>(0.0f);
+}
+
+static XformDev make_xform(const XformGeom &g) {
+  XformDev d;
+  d.tl0 = (float)g.tl[0];
+  d.tl1 = (float)g.tl[1];
+  // scaling.rs:69-72 — f32 host arithmetic (this file's host code is built with -ffp-contract=off)
+  d.skip_x_x = ((float)g.tr[0] - (float)g.tl[0]) / (float)(g.nwidth - 1);
+  d.skip_x_y = ((float)g.tr[1] - (float)g.tl[1]) / (float)(g.nwidth - 1);
+  d.skip_y_x = ((float)g.bl[0] - (float)g.tl[0]) / (float)(g.nheight - 1);
+  d.skip_y_y = ((float)g.bl[1] - (float)g.tl[1]) / (float)(g.nheight - 1);
+  d.width = g.width; d.height = g.height; d.nwidth = g.nwidth; d.nheight = g.nheight;
+  d.components = (int)g.components;
+  return d;
+}
+
+static const CfaDev kNoCfa = {};
+
+cudaError_t launch_transform_f32(cudaStream_t s, const XformGeom &g, const CfaDev *cfa, const float *src, float *out) {
+  size_t n = g.nwidth * g.nheight;
+  if (n == 0) return cudaSuccess;
+  XformDev d = make_xform(g);
+  if (cfa)
+    k_transform_buffer<float, true><<<grid_for(n, 128), 128, 0, s>>>(d, *cfa, src, out);
+  else
+    k_transform_buffer<float, false><<<grid_for(n, 128), 128, 0, s>>>(d, kNoCfa, src, out);
+  return cudaGetLastError();
+}
+cudaError_t launch_transform_u8(cudaStream_t s, const XformGeom &g, const uint8_t *src, uint8_t *out) {
+  size_t n = g.nwidth * g.nheight;
+  if (n == 0) return cudaSuccess;
+  k_transform_buffer<uint8_t, false><<<grid_for(n, 128), 128, 0, s>>>(make_xform(g), kNoCfa, src, out);
+  return cudaGetLastError();
+}
+cudaError_t launch_transform_u16(cudaStream_t s, const XformGeom &g, const uint16_t *src, uint16_t *out) {
+  size_t n = g.nwidth * g.nheight;
+  if (n == 0) return cudaSuccess;
+  k_transform_buffer<uint16_t, false><<<grid_for(n, 128), 128, 0, s>>>(make_xform(g), kNoCfa, src, out);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------ K4 to_lab (colorspaces.rs:89-112)
+
+__global__ void k_tolab(const __grid_constant__ ColorParams P, const float2 *__restrict__ lut_lab,
+                        const float *__restrict__ in, size_t npix, float *__restrict__ out) {
+  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= npix) return;
+  float4 p = reinterpret_cast<const float4 *>(in)[idx];
+  LutGlobal lab{lut_lab};
+  float l, a, b;
+  camera_to_lab(P, lab, p.x, p.y, p.z, p.w, l, a, b);
+  out[idx * 3 + 0] = l;
+  out[idx * 3 + 1] = a;
+  out[idx * 3 + 2] = b;
+}
+cudaError_t launch_tolab(cudaStream_t s, const ColorParams &P, const float2 *lut_lab, const float *in, size_t npix,
+                         float *out) {
+  if (npix == 0) return cudaSuccess;
+  k_tolab<<<grid_for(npix, 256), 256, 0, s>>>(P, lut_lab, in, npix, out);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------ K5 basecurve (curves.rs:33-49)
+
+__global__ void k_basecurve(const __grid_constant__ SplineDev sp, const float *__restrict__ in, size_t npix,
+                            float *__restrict__ out) {
+  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= npix) return;
+  out[idx * 3 + 0] = spline_eval(sp, in[idx * 3 + 0]);
+  out[idx * 3 + 1] = in[idx * 3 + 1];
+  out[idx * 3 + 2] = in[idx * 3 + 2];
+}
+cudaError_t launch_basecurve(cudaStream_t s, const SplineDev &sp, const float *in, size_t npix, float *out) {
+  if (npix == 0) return cudaSuccess;
+  k_basecurve<<<grid_for(npix, 256), 256, 0, s>>>(sp, in, npix, out);
+  return cudaGetLastError();
+}
+
+__global__ void k_spline_eval(const __grid_constant__ SplineDev sp, const float *__restrict__ in, size_t n,
+                              float *__restrict__ out) {
+  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx < n) out[idx] = spline_eval(sp, in[idx]);
+}
+cudaError_t launch_spline_eval(cudaStream_t s, const SplineDev &sp, const float *in, size_t n, float *out) {
+  if (n == 0) return cudaSuccess;
+  k_spline_eval<<<grid_for(n, 256), 256, 0, s>>>(sp, in, n, out);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------ K6 from_lab (colorspaces.rs:127-137)
+
+__global__ void k_fromlab(const __grid_constant__ ColorParams P, const float *__restrict__ in, size_t npix,
+                          float *__restrict__ out) {
+  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= npix) return;
+  float r, g, b;
+  lab_to_rgb(P, in[idx * 3 + 0], in[idx * 3 + 1], in[idx * 3 + 2], r, g, b);
+  out[idx * 3 + 0] = r;
+  out[idx * 3 + 1] = g;
+  out[idx * 3 + 2] = b;
+}
+cudaError_t launch_fromlab(cudaStream_t s, const ColorParams &P, const float *in, size_t npix, float *out) {
+  if (npix == 0) return cudaSuccess;
+  k_fromlab<<<grid_for(npix, 256), 256, 0, s>>>(P, in, npix, out);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------ K7 gamma (gamma.rs:16-26)
+
+__global__ void k_gamma(const float2 *__restrict__ lut_gamma, const float *__restrict__ in, size_t nelem,
+                        float *__restrict__ out) {
+  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= nelem) return;
+  LutGlobal gam{lut_gamma};
+  out[idx] = gamma_elem(gam, in[idx]);
+}
+cudaError_t launch_gamma(cudaStream_t s, const float2 *lut_gamma, const float *in, size_t nelem, float *out) {
+  if (nelem == 0) return cudaSuccess;
+  k_gamma<<<grid_for(nelem, 256), 256, 0, s>>>(lut_gamma, in, nelem, out);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------ K8 pack (pipeline.rs:408-414,455-461)
+
+__global__ void k_pack8(const float *__restrict__ in, size_t nelem, uint8_t *__restrict__ out) {
+  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= nelem) return;
+  out[idx] = (uint8_t)output8bit(in[idx]);
+}
+__global__ void k_pack16(const float *__restrict__ in, size_t nelem, uint16_t *__restrict__ out) {
+  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= nelem) return;
+  out[idx] = (uint16_t)output16bit(in[idx]);
+}
+cudaError_t launch_pack8(cudaStream_t s, const float *in, size_t nelem, uint8_t *out) {
+  if (nelem == 0) return cudaSuccess;
+  k_pack8<<<grid_for(nelem, 256), 256, 0, s>>>(in, nelem, out);
+  return cudaGetLastError();
+}
+cudaError_t launch_pack16(cudaStream_t s, const float *in, size_t nelem, uint16_t *out) {
+  if (nelem == 0) return cudaSuccess;
+  k_pack16<<<grid_for(nelem, 256), 256, 0, s>>>(in, nelem, out);
+  return cudaGetLastError();
+}
+
+// image 0.24 DynamicImage::to_rgb8 of a 16-bit raster / to_rgb16 of an 8-bit raster (pipeline.rs:384,431; the
+// crate is not in the reference tree: (v + 128) / 257 and v * 257 are its published conversions; unpinned)
+__global__ void k_rgb16_to_8(const uint16_t *__restrict__ in, size_t n, uint8_t *__restrict__ out) {
+  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx < n) out[idx] = (uint8_t)(((uint32_t)in[idx] + 128u) / 257u);
+}
+__global__ void k_rgb8_to_16(const uint8_t *__restrict__ in, size_t n, uint16_t *__restrict__ out) {
+  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx < n) out[idx] = (uint16_t)((uint32_t)in[idx] * 257u);
+}
+cudaError_t launch_rgb16_to_8(cudaStream_t s, const uint16_t *in, size_t n, uint8_t *out) {
+  if (n == 0) return cudaSuccess;
+  k_rgb16_to_8<<<grid_for(n, 256), 256, 0, s>>>(in, n, out);
+  return cudaGetLastError();
+}
+cudaError_t launch_rgb8_to_16(cudaStream_t s, const uint8_t *in, size_t n, uint16_t *out) {
+  if (n == 0) return cudaSuccess;
+  k_rgb8_to_16<<<grid_for(n, 256), 256, 0, s>>>(in, n, out);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------ K9 rotate_buffer (transform.rs:87-144)
+// Pure gather copy of 3-channel pixels; bit-exact by construction.  When transposing, a 32x32 pixel tile
+// goes through shared memory so that both the global reads and the global writes are row-contiguous.
+
+__global__ void k_rotate(const float *__restrict__ in, long sw, long sh, int transpose, long base_offset, long x_step,
+                         long y_step, long ow, long oh, float *__restrict__ out) {
+  __shared__ float tile[32][32 * 3 + 1];
+  long tx0 = (long)blockIdx.x * 32, ty0 = (long)blockIdx.y * 32;  // output tile origin
+  if (!transpose) {
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+      long row = ty0 + r;
+      if (row >= oh) break;
+      long line_offset = base_offset + y_step * row;
+      for (int e = threadIdx.x; e < 96; e += blockDim.x) {
+        long col = tx0 + e / 3;
+        int c = e % 3;
+        if (col < ow) out[(row * ow + col) * 3 + c] = in[line_offset + x_step * col + c];
+      }
+    }
+    return;
+  }
+  // transpose: output (row, col) reads source pixel at offset base + y_step*row + x_step*col where x_step is
+  // a whole source row: source rows run along output columns.  Load the tile by source rows.
+  for (int cc = threadIdx.y; cc < 32; cc += blockDim.y) {  // output col == one source row
+    long col = tx0 + cc;
+    if (col >= ow) break;
+    for (int e = threadIdx.x; e < 96; e += blockDim.x) {  // output row == position along the source row
+      int rr = e / 3, c = e % 3;
+      long row = ty0 + rr;
+      // y_step is +-3 here, so for flipped reads walk the source row backwards
+      if (row < oh) tile[cc][rr * 3 + c] = in[base_offset + y_step * row + x_step * col + c];
+    }
+  }
+  __syncthreads();
+  for (int rr = threadIdx.y; rr < 32; rr += blockDim.y) {
+    long row = ty0 + rr;
+    if (row >= oh) break;
+    for (int e = threadIdx.x; e < 96; e += blockDim.x) {
+      int cc = e / 3, c = e % 3;
+      long col = tx0 + cc;
+      if (col < ow) out[(row * ow + col) * 3 + c] = tile[cc][rr * 3 + c];
+    }
+  }
+}
+
+cudaError_t launch_rotate(cudaStream_t s, const float *in, size_t w, size_t h, int transpose, int flip_x, int flip_y,
+                          float *out) {
+  if (w == 0 || h == 0) return cudaSuccess;
+  long width = (long)w, height = (long)h;
+  long base_offset = 0, x_step = 3, y_step = width * 3;
+  if (flip_x) { x_step = -x_step; base_offset += (width - 1) * 3; }
+  if (flip_y) { y_step = -y_step; base_offset += width * (height - 1) * 3; }
+  long ow = width, oh = height;
+  if (transpose) {
+    ow = height; oh = width;
+    long t = x_step; x_step = y_step; y_step = t;
+  }
+  dim3 block(32, 8), grid((unsigned)((ow + 31) / 32), (unsigned)((oh + 31) / 32));
+  k_rotate<<<grid, block, 0, s>>>(in, width, height, transpose, base_offset, x_step, y_step, ow, oh, out);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------ synthetic CFA frames
+
+__device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
+  x += 0x9E3779B97F4A7C15ull;
+  x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+  x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+  return x ^ (x >> 31);
+}
+__global__ void k_synth(uint64_t seed, size_t width, size_t row0, size_t rows, uint16_t *__restrict__ out) {
+  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= width * rows) return;
+  uint64_t i = (uint64_t)(row0 * width + idx);
+  out[idx] = (uint16_t)(splitmix64(seed ^ i) & 16383u);
+}
+cudaError_t launch_synth(cudaStream_t s, uint64_t seed, size_t width, size_t row0, size_t rows, uint16_t *out) {
+  size_t n = width * rows;
+  if (n == 0) return cudaSuccess;
+  k_synth<<<grid_for(n, 256), 256, 0, s>>>(seed, width, row0, rows, out);
+  return cudaGetLastError();
+}
+
+}  // namespace ipb

@@ -1,0 +1,272 @@
+/*
+ * ipb200.h — C ABI of imagepipe-b200 (libipb200.so): the B200-native (sm_100a) replacement for
+ * the OpBuffer hot path of pedrocr/imagepipe.
+ *
+ * This header is the drop-in boundary: it is exactly what a Rust `extern "C"` block in the
+ * reference would bind (INTEGRATION.md shows that block and the `impl ImageOp` shims).  Plain
+ * pointers and sizes only; no torch / CUDA types in any signature (a CUDA stream is passed as an
+ * opaque `void *`).  Every entry point cites the reference interface it replaces; paths are
+ * relative to the reference tree (pedrocr/imagepipe @ 65ca96ce).
+ *
+ * Conventions
+ *  - every function that can fail returns an ipb_status (0 == IPB_OK); the message for the last
+ *    failure on a context is ipb_last_error(ctx).  Nothing aborts the host process (the reference
+ *    panics on invariant violations: scaling.rs:133,148, transform.rs:88,98).
+ *  - calls on one ipb_ctx are ordered on its CUDA stream; entry points that return host data
+ *    synchronise before returning, everything else is asynchronous — call ipb_ctx_synchronize().
+ *    Distinct contexts are independent and may be used from different threads.
+ *  - there is NO CPU fallback: every op runs a CUDA kernel or returns IPB_ERR_CUDA.
+ */
+#ifndef IPB200_H
+#define IPB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+#if defined(__GNUC__)
+#pragma GCC visibility push(default)
+#endif
+
+#define IPB_VERSION 100 /* 0.1.0 */
+
+typedef enum ipb_status {
+  IPB_OK = 0,
+  IPB_ERR_INVALID = 1,     /* bad argument / null pointer / size mismatch */
+  IPB_ERR_BAD_COLORS = 2,  /* op given a buffer with the wrong channel count (reference: assert_eq! panic) */
+  IPB_ERR_BAD_CFA = 3,     /* CFA pattern string rawloader::CFA::new would panic on */
+  IPB_ERR_CUDA = 4,        /* CUDA runtime / driver error, or no usable device */
+  IPB_ERR_UNSUPPORTED = 5, /* combination outside the hot path */
+  IPB_ERR_NOMEM = 6
+} ipb_status;
+
+typedef struct ipb_ctx ipb_ctx;           /* device + stream + uploaded LUTs/constants */
+typedef struct ipb_buffer ipb_buffer;     /* device-resident OpBuffer (src/buffer.rs:4-11), ref-counted like Arc<OpBuffer> */
+typedef struct ipb_pipeline ipb_pipeline; /* Pipeline (src/pipeline.rs:245-249) */
+
+/* ------------------------------------------------------------------ parameter PODs
+ * 1:1 with the reference's serde structs so the Rust side can fill them field by field. */
+
+/* OpGoFloat — src/ops/gofloat.rs:4-12 */
+typedef struct ipb_gofloat {
+  size_t crop_top, crop_right, crop_bottom, crop_left;
+  int is_cfa;
+  float blacklevels[4];
+  float whitelevels[4];
+} ipb_gofloat;
+
+/* OpDemosaic — src/ops/demosaic.rs:4-6; `cfa` is the rawloader CFA pattern string (≤144 chars, NUL terminated) */
+typedef struct ipb_demosaic {
+  char cfa[148];
+} ipb_demosaic;
+
+/* OpRotateCrop — src/ops/rotatecrop.rs:10-18 (input_ratio/output_size are the op's private state) */
+typedef struct ipb_rotatecrop {
+  float crop_top, crop_right, crop_bottom, crop_left, rotation;
+  float input_ratio;
+  int has_output_size;
+  size_t output_width, output_height;
+} ipb_rotatecrop;
+
+/* OpToLab — src/ops/colorspaces.rs:5-10 */
+typedef struct ipb_tolab {
+  float cam_to_xyz[3][4];
+  float cam_to_xyz_normalized[3][4];
+  float xyz_to_cam[4][3];
+  float wb_coeffs[4];
+} ipb_tolab;
+
+/* OpBaseCurve — src/ops/curves.rs:6-9 (points: Vec<(f32,f32)>, capped at 32) */
+#define IPB_MAX_CURVE_POINTS 32
+typedef struct ipb_basecurve {
+  float exposure;
+  size_t npoints;
+  float points[IPB_MAX_CURVE_POINTS][2];
+} ipb_basecurve;
+
+/* OpTransform / Rotation — src/ops/transform.rs:6-19 */
+enum { IPB_ROT_NORMAL = 0, IPB_ROT_90 = 1, IPB_ROT_180 = 2, IPB_ROT_270 = 3 };
+typedef struct ipb_transform {
+  int rotation;
+  int fliph, flipv;
+} ipb_transform;
+
+/* PipelineSettings — src/pipeline.rs:110-118 */
+typedef struct ipb_settings {
+  size_t maxwidth, maxheight, demosaic_width, demosaic_height;
+  int linear;
+  int use_fastpath;
+} ipb_settings;
+
+/* ImageSource — src/pipeline.rs:46-50.  RAW_* is rawloader::RawImage{width,height,cpp,data}
+ * (Integer = u16 / Float = f32), RGB8/RGB16 is the `image` crate's to_rgb8()/to_rgb16() raster.
+ * `data` may live on the host (pageable or pinned) or, with on_device != 0, on the context's GPU. */
+enum { IPB_SRC_RAW_U16 = 0, IPB_SRC_RAW_F32 = 1, IPB_SRC_RGB8 = 2, IPB_SRC_RGB16 = 3 };
+typedef struct ipb_source {
+  int kind;
+  size_t width, height, cpp;
+  const void *data;
+  int on_device;
+} ipb_source;
+
+/* PipelineOps — src/pipeline.rs:154-164 (OpFromLab and OpGamma have no fields) */
+typedef struct ipb_ops {
+  ipb_gofloat gofloat;
+  ipb_demosaic demosaic;
+  ipb_rotatecrop rotatecrop;
+  ipb_tolab tolab;
+  ipb_basecurve basecurve;
+  ipb_transform transform;
+} ipb_ops;
+
+/* Row stripe of a frame for multi-GPU sharding (no reference equivalent).
+ * The source passed with a stripe holds only rows [src_row0, src_row0 + source.height) of a
+ * full frame `full_height` rows tall; the call produces output rows [out_row0, out_row1) of the
+ * full-frame result.  Use ipb_pipeline_stripe_rows() to learn which source rows a stripe needs. */
+typedef struct ipb_stripe {
+  size_t full_height;
+  size_t src_row0;
+  size_t out_row0, out_row1;
+} ipb_stripe;
+
+/* ------------------------------------------------------------------ context */
+
+int ipb_version(void);
+/* stream: a cudaStream_t to run on (e.g. torch's current stream) or NULL for a private stream. */
+int ipb_ctx_create(int device, void *stream, ipb_ctx **out);
+void ipb_ctx_destroy(ipb_ctx *ctx);
+int ipb_ctx_set_stream(ipb_ctx *ctx, void *stream);
+int ipb_ctx_synchronize(ipb_ctx *ctx);
+const char *ipb_last_error(const ipb_ctx *ctx); /* ctx == NULL: last ipb_ctx_create failure of this thread */
+/* number of CUDA kernels this context has launched so far (bench.py's gpu_launches) */
+unsigned long long ipb_ctx_launch_count(const ipb_ctx *ctx);
+/* pinned host memory for the host<->device paths (plain cudaHostAlloc/cudaFreeHost) */
+int ipb_host_alloc(size_t bytes, void **out);
+void ipb_host_free(void *p);
+
+/* plain device memory for sources and destinations that live on the GPU (stream-ordered on the context's
+ * stream; upload/download synchronise before returning) */
+int ipb_device_alloc(ipb_ctx *ctx, size_t bytes, void **out);
+int ipb_device_free(ipb_ctx *ctx, void *dptr);
+int ipb_device_upload(ipb_ctx *ctx, void *dptr, const void *host, size_t bytes);
+int ipb_device_download(ipb_ctx *ctx, void *host, const void *dptr, size_t bytes);
+
+/* ------------------------------------------------------------------ OpBuffer — src/buffer.rs */
+
+/* OpBuffer::new (buffer.rs:24-32): zero-filled device buffer */
+int ipb_buffer_new(ipb_ctx *ctx, size_t width, size_t height, size_t colors, int monochrome, ipb_buffer **out);
+/* host Vec<f32> -> device OpBuffer (same interleaved row-major layout, buffer.rs:4-11) */
+int ipb_buffer_upload(ipb_ctx *ctx, size_t width, size_t height, size_t colors, int monochrome,
+                      const float *host, ipb_buffer **out);
+/* wrap caller-owned device memory (not freed on release) */
+int ipb_buffer_wrap(ipb_ctx *ctx, size_t width, size_t height, size_t colors, int monochrome, void *dptr,
+                    ipb_buffer **out);
+/* device OpBuffer -> host Vec<f32>; synchronises */
+int ipb_buffer_download(ipb_ctx *ctx, const ipb_buffer *buf, float *host);
+void ipb_buffer_retain(ipb_buffer *buf);  /* Arc::clone */
+void ipb_buffer_release(ipb_buffer *buf); /* drop(Arc) */
+size_t ipb_buffer_width(const ipb_buffer *buf);
+size_t ipb_buffer_height(const ipb_buffer *buf);
+size_t ipb_buffer_colors(const ipb_buffer *buf);
+int ipb_buffer_monochrome(const ipb_buffer *buf);
+void *ipb_buffer_device_ptr(const ipb_buffer *buf);
+
+/* ------------------------------------------------------------------ ImageOp::run — src/pipeline.rs:82-108
+ * One entry per op of PipelineOps, same order as all_ops! (pipeline.rs:211-226).  `*out` receives a
+ * new reference; ops that pass their input through (the reference returns the same Arc) return `in`
+ * retained, so callers always release `*out` exactly once. */
+
+/* OpGoFloat::run — gofloat.rs:50-62 (run_raw :84-169, run_other :171-201) */
+int ipb_gofloat_run(ipb_ctx *ctx, const ipb_gofloat *op, const ipb_source *image, ipb_buffer **out);
+/* OpDemosaic::run — demosaic.rs:27-61 (full() :67-119; scaled_demosaic / scale_down_opbuf scaling.rs:132-160) */
+int ipb_demosaic_run(ipb_ctx *ctx, const ipb_demosaic *op, const ipb_settings *settings, ipb_buffer *in,
+                     ipb_buffer **out);
+/* OpRotateCrop::run — rotatecrop.rs:39-64 (OpBuffer::transform buffer.rs:62-79) */
+int ipb_rotatecrop_run(ipb_ctx *ctx, const ipb_rotatecrop *op, ipb_buffer *in, ipb_buffer **out);
+/* OpToLab::run — colorspaces.rs:89-112 */
+int ipb_tolab_run(ipb_ctx *ctx, const ipb_tolab *op, ipb_buffer *in, ipb_buffer **out);
+/* OpBaseCurve::run — curves.rs:33-49 */
+int ipb_basecurve_run(ipb_ctx *ctx, const ipb_basecurve *op, ipb_buffer *in, ipb_buffer **out);
+/* OpFromLab::run — colorspaces.rs:127-137 */
+int ipb_fromlab_run(ipb_ctx *ctx, ipb_buffer *in, ipb_buffer **out);
+/* OpGamma::run — gamma.rs:16-26 */
+int ipb_gamma_run(ipb_ctx *ctx, const ipb_settings *settings, ipb_buffer *in, ipb_buffer **out);
+/* OpTransform::run — transform.rs:56-73 (rotate_buffer :87-144); bit-exact data movement */
+int ipb_transform_run(ipb_ctx *ctx, const ipb_transform *op, ipb_buffer *in, ipb_buffer **out);
+
+/* ImageOp::transform_forward / transform_reverse / reset — host-only size negotiation
+ * (gofloat.rs:64-82, rotatecrop.rs:66-86,111-163, transform.rs:75-84) and scaling.rs:8-32 */
+void ipb_gofloat_transform_forward(const ipb_gofloat *op, size_t w, size_t h, size_t *ow, size_t *oh);
+void ipb_rotatecrop_transform_forward(ipb_rotatecrop *op, size_t w, size_t h, size_t *ow, size_t *oh);
+void ipb_rotatecrop_transform_reverse(ipb_rotatecrop *op, size_t w, size_t h, size_t *ow, size_t *oh);
+void ipb_rotatecrop_reset(ipb_rotatecrop *op);
+void ipb_transform_transform_forward(const ipb_transform *op, size_t w, size_t h, size_t *ow, size_t *oh);
+void ipb_scaling_size(size_t w, size_t h, size_t maxw, size_t maxh, size_t *ow, size_t *oh);
+float ipb_calculate_scale(size_t w, size_t h, size_t maxw, size_t maxh);
+
+/* SplineFunc::new(&op->points).interpolate(v) for n host values — curves.rs:68-157 (OpBaseCurve::get_spline,
+ * :53-55: the exposure field is not applied).  Coefficients are built on the host, evaluated by a kernel. */
+int ipb_spline_eval(ipb_ctx *ctx, const ipb_basecurve *op, const float *in, float *out, size_t n);
+
+/* output8bit / output16bit pack loops — pipeline.rs:408-414,455-461, color_conversions.rs:323-330.
+ * dst holds width*height*3 elements, on the host (dst_on_device == 0; synchronises) or the device. */
+int ipb_pack_8bit(ipb_ctx *ctx, const ipb_buffer *in, uint8_t *dst, int dst_on_device);
+int ipb_pack_16bit(ipb_ctx *ctx, const ipb_buffer *in, uint16_t *dst, int dst_on_device);
+
+/* scale_down_srgb / scale_down_srgb16 — scaling.rs:162-182 (the non-raw fast path's resampler) */
+int ipb_scale_down_srgb(ipb_ctx *ctx, const uint8_t *src, size_t w, size_t h, size_t nw, size_t nh, uint8_t *dst,
+                        int on_device);
+int ipb_scale_down_srgb16(ipb_ctx *ctx, const uint16_t *src, size_t w, size_t h, size_t nw, size_t nh,
+                          uint16_t *dst, int on_device);
+
+/* ------------------------------------------------------------------ Pipeline — src/pipeline.rs:257-470 */
+
+/* PipelineOps::new for everything that does not need rawloader metadata (pipeline.rs:166-179):
+ * raw sources get basecurve [(0.5,0.6)], is_cfa=1, wb 1.0; other sources get the sRGB matrices. */
+void ipb_ops_default(ipb_ops *ops, const ipb_source *image);
+/* Pipeline::new_from_source (pipeline.rs:274-284).  ops == NULL: ipb_ops_default(). The source's pixel
+ * data is NOT copied: it must stay valid until the pipeline is destroyed or the source replaced. */
+int ipb_pipeline_create(ipb_ctx *ctx, const ipb_source *image, const ipb_ops *ops, ipb_pipeline **out);
+void ipb_pipeline_destroy(ipb_pipeline *p);
+/* pipeline.ops / pipeline.globals.settings are public fields in the reference; these return mutable views */
+ipb_ops *ipb_pipeline_ops(ipb_pipeline *p);
+ipb_settings *ipb_pipeline_settings(ipb_pipeline *p);
+int ipb_pipeline_set_source(ipb_pipeline *p, const ipb_source *image);
+/* 1 (default): Pipeline::run may use the fused raw->sRGB kernel when the op chain allows it;
+ * 0: always run op by op (one kernel + one OpBuffer per op, like the reference). */
+int ipb_pipeline_set_fused(ipb_pipeline *p, int fused);
+/* size walk of Pipeline::run (pipeline.rs:313-338): final output size; also sets settings.demosaic_* */
+int ipb_pipeline_output_size(ipb_pipeline *p, size_t *width, size_t *height);
+/* Pipeline::run(None) — pipeline.rs:311-375; result is a 3-channel f32 OpBuffer */
+int ipb_pipeline_run(ipb_pipeline *p, ipb_buffer **out);
+/* Pipeline::output_8bit / output_16bit — pipeline.rs:377-469 (incl. the non-raw fast path).
+ * dst capacity is in elements; *width/*height receive the image size. dst_on_device == 0 synchronises. */
+int ipb_pipeline_output_8bit(ipb_pipeline *p, uint8_t *dst, size_t dst_capacity, int dst_on_device, size_t *width,
+                             size_t *height);
+int ipb_pipeline_output_16bit(ipb_pipeline *p, uint16_t *dst, size_t dst_capacity, int dst_on_device,
+                              size_t *width, size_t *height);
+
+/* Row-stripe sharding (multi-GPU).  Only for the fused raw CFA path with a
+ * Normal orientation and no rotatecrop. */
+/* which source rows [*src_row0, *src_row1) are needed to produce output rows [out_row0, out_row1) */
+int ipb_pipeline_stripe_rows(ipb_pipeline *p, size_t out_row0, size_t out_row1, size_t *src_row0, size_t *src_row1);
+/* like output_8bit but the pipeline's source holds only the rows named by `stripe`; the pipeline must have
+ * been created with image.height == stripe->full_height semantics via ipb_pipeline_set_stripe_source(). */
+int ipb_pipeline_set_stripe_source(ipb_pipeline *p, const ipb_source *rows, const ipb_stripe *stripe);
+int ipb_pipeline_output_8bit_stripe(ipb_pipeline *p, uint8_t *dst, size_t dst_capacity, int dst_on_device,
+                                    size_t *width, size_t *rows);
+
+/* ------------------------------------------------------------------ synthetic input (bench/tests)
+ * v(i) = splitmix64(seed ^ i) mod 16384 for the pixel with linear index i = row*width + col of the
+ * full frame; writes rows [row0, row0+rows) to device memory dptr. */
+int ipb_synth_cfa_u16(ipb_ctx *ctx, uint64_t seed, size_t width, size_t row0, size_t rows, uint16_t *dptr);
+
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+#ifdef __cplusplus
+}
+#endif
+#endif /* IPB200_H */

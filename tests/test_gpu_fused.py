@@ -1,0 +1,151 @@
+"""GPU parity of the fused raw->sRGB kernels (through Pipeline::run / output_8bit / output_16bit of the C ABI)
+against the CPU oracle's op-by-op pipeline.  Bit-exact on f32, u8 and u16."""
+import numpy as np
+import pytest
+
+import common
+from common import assert_bit_exact
+
+pytestmark = pytest.mark.gpu
+
+
+def both(ip, orc, ctx, data, params, settings=None, on_device=False):
+    po = orc.make_pipeline(data, "raw", params, settings)
+    pg = common.make_ipb_pipeline(ip, data, "raw", params, settings, ctx=ctx, on_device=on_device)
+    return po, pg
+
+
+@pytest.mark.parametrize("cfa", ["RGGB", "BGGR", "GRBG", "GBRG"])
+@pytest.mark.parametrize("shape", [(40, 64), (67, 301), (130, 523)])
+def test_full_bayer_f32(ip, orc, ctx, cfa, shape):
+    data = common.synth_cfa(shape[1], shape[0])
+    po, pg = both(ip, orc, ctx, data, common.raw_params(cfa=cfa))
+    want = orc.pipeline_run(po)
+    got = pg.run().to_numpy()
+    assert_bit_exact(got, want, f"fused full {cfa} {shape}")
+
+
+@pytest.mark.parametrize("cfa", [common.XTRANS, "RGEB", "RGBE" * 4, "GMYE"])
+def test_full_other_cfas(ip, orc, ctx, cfa):
+    data = common.synth_cfa(277, 95, seed=5)
+    matrix = common.CAM_TO_XYZ.copy()
+    matrix[:, 3] = [0.05, 0.1, -0.02]  # give the E channel a weight
+    po, pg = both(ip, orc, ctx, data, common.raw_params(cfa=cfa, matrix=matrix, wb=[1.8, 1.0, 1.4, 1.1]))
+    assert_bit_exact(pg.run().to_numpy(), orc.pipeline_run(po), f"fused full {cfa}")
+
+
+@pytest.mark.parametrize("crops", [(0, 0, 0, 0), (3, 5, 2, 7), (1, 0, 0, 1)])
+def test_full_outputs_8_and_16(ip, orc, ctx, crops):
+    data = common.smooth_cfa(410, 133)
+    params = common.raw_params(cfa="GRBG", crops=crops)
+    po, pg = both(ip, orc, ctx, data, params)
+    want8 = orc.pipeline_output_8bit(po)
+    got8 = pg.output_8bit()
+    assert (got8.width, got8.height) == (want8.shape[1], want8.shape[0])
+    assert_bit_exact(got8.to_numpy(), want8, "output_8bit")
+    want16 = orc.pipeline_output_16bit(po)  # sets linear = true
+    got16 = pg.output_16bit()
+    assert_bit_exact(got16.to_numpy(), want16, "output_16bit")
+
+
+def test_fused_equals_unfused_on_gpu(ip, ctx):
+    data = common.synth_cfa(1031, 517, seed=11)
+    pg = common.make_ipb_pipeline(ip, data, "raw", common.raw_params(), ctx=ctx)
+    fused = pg.run().to_numpy()
+    n0 = ctx.launch_count
+    pg.set_fused(False)
+    unfused = pg.run().to_numpy()
+    assert ctx.launch_count - n0 >= 6  # gofloat, demosaic, to_lab, basecurve, from_lab, gamma
+    assert_bit_exact(fused, unfused, "fused vs op-by-op")
+
+
+@pytest.mark.parametrize("cfa,shape,maxw,maxh", [("RGGB", (200, 300), 75, 0), ("RGGB", (203, 311), 77, 0),
+                                                 ("BGGR", (160, 240), 0, 20), (common.XTRANS, (180, 270), 60, 0),
+                                                 ("RGGB", (120, 180), 100, 0)])
+def test_scaled_pipeline(ip, orc, ctx, cfa, shape, maxw, maxh):
+    """maxwidth/maxheight: scaled_demosaic (fused), or full()+scale_down_opbuf (op by op) below minscale."""
+    data = common.synth_cfa(shape[1], shape[0], seed=21)
+    st = {"maxwidth": maxw, "maxheight": maxh}
+    po, pg = both(ip, orc, ctx, data, common.raw_params(cfa=cfa), st)
+    want = orc.pipeline_run(po)
+    got = pg.run().to_numpy()
+    assert_bit_exact(got, want, f"scaled {cfa} {shape}")
+    po, pg = both(ip, orc, ctx, data, common.raw_params(cfa=cfa), st)
+    assert_bit_exact(pg.output_8bit().to_numpy(), orc.pipeline_output_8bit(po), "scaled output_8bit")
+
+
+@pytest.mark.parametrize("rotation,fliph", [(1, False), (2, True), (3, False)])
+def test_orientation_after_fused(ip, orc, ctx, rotation, fliph):
+    data = common.synth_cfa(150, 90, seed=31)
+    params = common.raw_params(rotation=rotation, fliph=fliph)
+    po, pg = both(ip, orc, ctx, data, params, {"maxwidth": 100})
+    want = orc.pipeline_output_8bit(po)
+    got = pg.output_8bit()
+    assert (got.width, got.height) == (want.shape[1], want.shape[0])
+    assert_bit_exact(got.to_numpy(), want, "orientation")
+
+
+def test_device_resident_source_and_destination(ip, orc, ctx):
+    data = common.synth_cfa(512, 128, seed=41)
+    po, pg = both(ip, orc, ctx, data, common.raw_params(), on_device=True)
+    dst = ip.DeviceArray(512 * 128 * 3, ctx)
+    img = pg.output_8bit(dst=dst)
+    assert (img.width, img.height) == (512, 128)
+    assert_bit_exact(dst.to_numpy(np.uint8, (128, 512, 3)), orc.pipeline_output_8bit(po), "device in/out")
+
+
+@pytest.mark.parametrize("maxw", [0, 150])
+def test_row_stripes_equal_whole_frame(ip, ctx, maxw):
+    """Sharding property: stitching stripes (each given only the source rows stripe_rows() names) == whole frame."""
+    h, w = 264, 600
+    data = common.synth_cfa(w, h, seed=51)
+    st = {"maxwidth": maxw}
+    whole = common.make_ipb_pipeline(ip, data, "raw", common.raw_params(), st, ctx=ctx).output_8bit().to_numpy()
+    oh = whole.shape[0]
+    parts = []
+    bounds = [0, oh // 3, oh // 3 + 1, (2 * oh) // 3, oh]
+    for r0, r1 in zip(bounds[:-1], bounds[1:]):
+        pg = common.make_ipb_pipeline(ip, data, "raw", common.raw_params(), st, ctx=ctx)
+        s0, s1 = pg.stripe_rows(r0, r1)
+        rows = np.ascontiguousarray(data[s0:s1])
+        pg.set_stripe_source(ip.ImageSource.Raw(rows), s0, r0, r1)
+        parts.append(pg.output_8bit_stripe(rows=r1 - r0, width=whole.shape[1]).to_numpy())
+    assert_bit_exact(np.concatenate(parts, 0), whole, "stripes")
+
+
+def test_stripe_missing_rows_is_an_error(ip, ctx):
+    data = common.synth_cfa(64, 64)
+    pg = common.make_ipb_pipeline(ip, data, "raw", common.raw_params(), ctx=ctx)
+    pg.set_stripe_source(ip.ImageSource.Raw(np.ascontiguousarray(data[10:20])), 10, 10, 20)
+    with pytest.raises(ip.IpbError):
+        pg.output_8bit_stripe(rows=10, width=64)  # rows 9 and 20 (the halo) are missing
+
+
+def test_synthetic_generator_matches_host(ip, ctx):
+    d = ip.synth_cfa_u16(common.SEED + 3, 1000, 17, 9, ctx=ctx)
+    assert_bit_exact(d.to_numpy(), common.synth_cfa(1000, 9, common.SEED + 3, row0=17), "synth")
+
+
+def test_full_size_c2_frame(ip, orc, ctx):
+    """BASELINE config 2 at full size: 6000x4000 RGGB -> 8-bit sRGB, whole frame against the oracle."""
+    data = common.synth_cfa(6000, 4000)
+    po, pg = both(ip, orc, ctx, data, common.raw_params())
+    got = pg.output_8bit().to_numpy()
+    want = orc.pipeline_output_8bit(po)
+    assert_bit_exact(got, want, "C2 frame")
+
+
+def test_full_size_c4_scaled(ip, orc, ctx):
+    """BASELINE config 4 frame: 6000x4000 -> 1500x1000 through scaled_demosaic."""
+    data = common.synth_cfa(6000, 4000, seed=common.SEED + 1)
+    po, pg = both(ip, orc, ctx, data, common.raw_params(), {"maxwidth": 1500, "maxheight": 1000})
+    got = pg.output_8bit()
+    assert (got.width, got.height) == (1500, 1000)
+    assert_bit_exact(got.to_numpy(), orc.pipeline_output_8bit(po), "C4 frame")
+
+
+def test_xtrans_c3_rows(ip, orc, ctx):
+    """BASELINE config 3 width (8256) on a 96-row band of the X-Trans frame."""
+    data = common.synth_cfa(8256, 96, seed=common.SEED + 2)
+    po, pg = both(ip, orc, ctx, data, common.raw_params(cfa=common.XTRANS))
+    assert_bit_exact(pg.output_8bit().to_numpy(), orc.pipeline_output_8bit(po), "C3 band")
