@@ -357,20 +357,20 @@ class OpTransform(_capi.Transform, _SizeMixin):
     transform_reverse = transform_forward
 
 
-# rawloader Orientation -> (transpose, flip_x, flip_y) -> the (rotation, fliph, flipv) OpTransform fields that
-# produce it (transform.rs:24-36); used by the orientation KATs of transform.rs:167-278.
-ORIENTATIONS = {
-    "Normal": (Rotation.Normal, False, False), "Unknown": (Rotation.Normal, False, False),
-    "VerticalFlip": (Rotation.Normal, False, True), "HorizontalFlip": (Rotation.Normal, True, False),
-    "Rotate180": (Rotation.Rotate180, False, False), "Transpose": (Rotation.Rotate90, False, True),
-    "Rotate90": (Rotation.Rotate90, False, False), "Rotate270": (Rotation.Rotate270, False, False),
-    "Transverse": (Rotation.Rotate270, True, False),
+# rawloader Orientation::to_flips -> (transpose, flip_x, flip_y); pinned by the golden bitmaps of transform.rs:167-278
+ORIENTATION_FLIPS = {
+    "Normal": (False, False, False), "Unknown": (False, False, False), "VerticalFlip": (False, False, True),
+    "HorizontalFlip": (False, True, False), "Rotate180": (False, True, True), "Transpose": (True, False, False),
+    "Rotate90": (True, False, True), "Rotate270": (True, True, False), "Transverse": (True, True, True),
 }
 
 
 def rotate_buffer(buf, orientation):
-    """transform.rs:87-144 for a named rawloader Orientation; Normal/Unknown return a copy like the reference."""
-    rot, fh, fv = ORIENTATIONS[orientation]
+    """rotate_buffer(buf, &orientation) of transform.rs:87-144 for a named rawloader Orientation, expressed through
+    the OpTransform fields whose run() derives exactly these flips (transform.rs:56-66).  Normal / Unknown pass
+    the same buffer through (the reference's rotate_buffer clones it; the values are identical)."""
+    t, fx, fy = ORIENTATION_FLIPS[orientation]
+    rot, fh, fv = (Rotation.Rotate90, fx, not fy) if t else (Rotation.Normal, fx, fy)
     op = OpTransform(rot, int(fh), int(fv))
     g = PipelineGlobals.mock(16, 16, ctx=buf.ctx)
     return op.run(g, buf)

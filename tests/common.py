@@ -115,8 +115,9 @@ def assert_bit_exact(got, want, what=""):
     assert got.shape == want.shape, f"{what}: shape {got.shape} != {want.shape}"
     if got.dtype == np.float32:
         g, w = bits(got), bits(want)
-        # +0.0 and -0.0 are distinct bit patterns; NaN payloads are compared as-is
-        bad = g != w
+        # +0.0 and -0.0 are distinct bit patterns.  Any NaN equals any NaN: x86 and the GPU generate different
+        # default-NaN payloads for the same invalid operation, and the reference does not define them.
+        bad = (g != w) & ~(np.isnan(got) & np.isnan(want))
     else:
         bad = got != want
     n = int(bad.sum())
