@@ -147,6 +147,9 @@ def lib():
         "ipb_pipeline_stripe_rows": (i, [vp, sz, sz, szp, szp]),
         "ipb_pipeline_set_stripe_source": (i, [vp, vp, vp]),
         "ipb_pipeline_output_8bit_stripe": (i, [vp, vp, sz, i, szp, szp]),
+        "ipb_pipeline_set_tma": (i, [vp, i]),
+        "ipb_selftest_gamma8": (i, [vp, C.POINTER(C.c_ulonglong)]),
+        "ipb_gamma_pack_8bit": (i, [vp, vp, sz, vp]),
         "ipb_synth_cfa_u16": (i, [vp, C.c_uint64, sz, sz, sz, vp]),
     }
     for name, (res, args) in sigs.items():

@@ -44,20 +44,40 @@ __device__ __forceinline__ float div_rc(float x, float d, float rc) {
 
 // glibc 2.39 cbrtf (sysdeps/ieee754/flt-32/s_cbrtf.c) restated for finite x > 0; checked bit-identical to
 // the host libm over [2^-7, 64).  Only used by the out-of-table fallback of the Lab transfer
-// function (color_conversions.rs:103-104,123), i.e. for XYZ ratios above 1.0.
-static __device__ __noinline__ float cbrt_glibc(float x) {
-  const double factor[5] = {1.0 / 1.5874010519681994748, 1.0 / 1.2599210498948731648, 1.0,
-                            1.2599210498948731648, 1.5874010519681994748};
+// function (color_conversions.rs:103-104,123), i.e. for XYZ ratios above 1.0.  The double-precision Halley step
+// is kept in FP64 (half rate on B200): its rounding to f32 is what makes the result glibc's and not the
+// correctly rounded cube root.
+static __device__ __forceinline__ float cbrt_glibc(float x) {
   if (!(x < __int_as_float(0x7f800000))) return x + x;  // inf / NaN
-  int bits = __float_as_int(x);
-  int ex = (bits >> 23) & 0xff;
+  const int bits = __float_as_int(x);
+  const int ex = (bits >> 23) & 0xff;
   if (ex == 0) return cbrtf(x);  // subnormal: never reached by the hot path (x > 1)
-  int xe = ex - 126;
-  float xm = __int_as_float((bits & 0x007fffff) | 0x3f000000);  // frexpf: [0.5, 1)
-  float u = (float)(0.492659620528969547 + (0.697570460207922770 - 0.191502161678719066 * (double)xm) * (double)xm);
-  float t2 = u * u * u;
-  float ym = (float)((double)u * ((double)t2 + 2.0 * (double)xm) / (2.0 * (double)t2 + (double)xm) * factor[2 + xe % 3]);
-  return scalbnf(ym, xe / 3);
+  const int xe = ex - 126;       // frexpf exponent
+  const float xm = __int_as_float((bits & 0x007fffff) | 0x3f000000);  // frexpf mantissa: [0.5, 1)
+  const double dxm = (double)xm;
+  const float u = (float)(0.492659620528969547 + (0.697570460207922770 - 0.191502161678719066 * dxm) * dxm);
+  const float t2 = u * u * u;
+  // factor[2 + xe % 3] of the glibc table {1/cbrt(4), 1/cbrt(2), 1, cbrt(2), cbrt(4)}
+  const int q3 = xe / 3, m3 = xe - 3 * q3;  // C truncation: m3 in {-2..2}
+  double fac = 1.0;
+  fac = m3 == 1 ? 1.2599210498948731648 : fac;
+  fac = m3 == 2 ? 1.5874010519681994748 : fac;
+  fac = m3 == -1 ? 1.0 / 1.2599210498948731648 : fac;
+  fac = m3 == -2 ? 1.0 / 1.5874010519681994748 : fac;
+  const float ym = (float)((double)u * ((double)t2 + 2.0 * dxm) / (2.0 * (double)t2 + dxm) * fac);
+  return scalbnf(ym, q3);
+}
+
+// The analytic branch of XYZ_LAB_TRANSFORM.lookup (color_conversions.rs:102-104,120-124) plus the two table-branch
+// inputs the masked fast lerp does not handle (-0.0 and NaN).  Called for values with !in_table().
+static __device__ __noinline__ float lab_f_slow(float v) {
+  const float e = 216.0f / 24389.0f;
+  const float k = 24389.0f / 27.0f;
+  if (v > 1.0f) return cbrt_glibc(v);
+  if (v < 0.0f) return IPB_DIVC(k * v + 16.0f, 116.0f);  // v < 0 is never > e
+  if (v != v) return v;                                  // NaN takes the table branch: a = NaN
+  (void)e;
+  return IPB_DIVC(k * 0.0f + 16.0f, 116.0f);             // -0.0: table[0] + 0 * (table[1] - table[0])
 }
 
 // ---------------------------------------------------------------- TransformLookup (color_conversions.rs:80-115)
@@ -92,12 +112,7 @@ __device__ __forceinline__ float lut_lerp(const Lut &lut, float val) {
 // XYZ_LAB_TRANSFORM.lookup — color_conversions.rs:120-124 with the analytic fallback outside [0,1]
 template <class Lut>
 __device__ __forceinline__ float lab_f(const Lut &lut, float v) {
-  if (v < 0.0f || v > 1.0f) {
-    const float e = 216.0f / 24389.0f;
-    const float k = 24389.0f / 27.0f;
-    if (v > e) return cbrt_glibc(v);
-    return IPB_DIVC(k * v + 16.0f, 116.0f);
-  }
+  if (v < 0.0f || v > 1.0f) return lab_f_slow(v);
   return lut_lerp(lut, v);
 }
 

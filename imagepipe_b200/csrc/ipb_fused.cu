@@ -6,9 +6,21 @@
 //   k_fused_scaled  the same chain with scaled_demosaic (scaling.rs:132-145) in place of full() — the branch
 //                   OpDemosaic::run takes for scale >= 2 (Bayer) / 3 (X-Trans), demosaic.rs:47-50.
 //
-// Both are persistent kernels: one CTA per SM, both 8192-entry {v,dv} tables (128 KB) resident in shared
-// memory for the whole launch, CTAs walking tiles round-robin.  Arithmetic is the per-pixel code of
-// ipb_device.cuh, compiled -fmad=false: results are bit-identical to the reference's f32 arithmetic.
+// k_fused_full is a persistent kernel: one 1024-thread CTA per SM walks 256x16-pixel tiles round-robin.
+//   * the raw u16 tile (+1 px halo, 264x18 box) of the NEXT tile is fetched by TMA (cp.async.bulk.tensor.2d,
+//     completion on an mbarrier) into a two-stage ring while the current tile is computed;
+//   * a conversion phase applies gofloat once per sensor pixel (smem u16 -> smem f32);
+//   * the compute phase gives every thread four consecutive pixels: 3x6 window from shared memory, demosaic,
+//     then the colour chain on two pixel pairs;
+//   * both 8192-entry tables stay in shared memory for the whole launch.  For 8-bit output the gamma table is
+//     replaced by a threshold table that yields output8bit(gamma(v)) directly (see build in ipb_host.cu);
+//   * XYZ ratios outside [0,1] (the reference's analytic branch: glibc cbrtf in double precision, or the linear
+//     segment) are rare per lane but common per warp, so they are compacted into a per-warp queue and evaluated
+//     by a dense pass instead of twelve divergent calls.
+// Arithmetic is the per-pixel code of ipb_device.cuh, compiled -fmad=false: results are bit-identical to the
+// reference's f32 arithmetic (tests/test_gpu_fused.py compares against the CPU oracle bit for bit).
+#include <cuda.h>  // CUtensorMap (types only; cuTensorMapEncodeTiled is resolved at run time, no libcuda link)
+
 #include "ipb_internal.h"
 
 namespace ipb {
@@ -17,10 +29,14 @@ namespace {
 
 constexpr int kTW = 256;                  // tile width in pixels (64 four-pixel tasks per tile row = 2 warps)
 constexpr int kTH = 16;                   // tile height
-constexpr int kNT = 512;                  // threads per CTA
-constexpr int kTileStride = kTW + 8;      // floats per tile row: frame col tx0-4 .. tx0+kTW+3 (col tx0 at index 4)
+constexpr int kNT = 1024;                 // threads per CTA: one four-pixel task per thread per tile
+constexpr int kWarps = kNT / 32;
+constexpr int kTileStride = kTW + 8;      // elements per tile row: frame col tx0-4 .. tx0+kTW+3 (col tx0 at index 4)
 constexpr int kTileRows = kTH + 2;        // + one halo row above and below
+constexpr int kTileElems = kTileRows * kTileStride;
 constexpr int kMaxPatPos = 144;           // largest CFA period (12x12)
+constexpr int kQueueCap = 6 * 32;         // out-of-table queue: 2 pixels x 3 ratios per lane
+constexpr uint32_t kFull = 0xffffffffu;
 
 struct FullParams {
   const uint16_t *raw;
@@ -32,26 +48,56 @@ struct FullParams {
   void *out;
   float black, range, range_rc;
   int exact_rc;
-  const float2 *lut_lab, *lut_gamma;
+  const float2 *lut_lab, *lut_out;
   int tiles_x, tiles_y;
   int pw, ph;                   // CFA period
-  int bayer;                    // 2x2 RGB Bayer: specialised interior path
+  int use_tma;
+  int gamma8;                   // lut_out is the 8-bit threshold table
 };
 
 struct Smem {
   float2 lut_lab[kLutEntries];
-  float2 lut_gamma[kLutEntries];
-  float tile[kTileRows * kTileStride];
+  float2 lut_out[kLutEntries];  // gamma {v, dv}; 8-bit output: {threshold, base} (Gamma8Entry)
+  float tile[kTileElems];
+  alignas(128) uint16_t raw[2][kTileElems];
+  float queue[kWarps][kQueueCap];
+  float spl[kMaxSplinePts][8];  // per segment: x, y, c1, c2, c3
   uint2 taps[kMaxPatPos];       // per pattern position: 9-bit tap masks of colours 0..3, 16 bits each
+  alignas(8) unsigned long long mbar[2];
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-__device__ __forceinline__ void load_luts(float2 *s_lab, float2 *s_gam, const float2 *lab, const float2 *gam) {
+// ---------------------------------------------------------------- TMA + mbarrier (PTX)
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, int x, int y, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+      "l"(map), "r"(x), "r"(y), "r"(bar)
+      : "memory");
+}
+
+__device__ __forceinline__ void load_luts(float2 *s_lab, float2 *s_out, const float2 *lab, const float2 *outl) {
   const uint4 *a = reinterpret_cast<const uint4 *>(lab);
-  const uint4 *b = reinterpret_cast<const uint4 *>(gam);
+  const uint4 *b = reinterpret_cast<const uint4 *>(outl);
   uint4 *da = reinterpret_cast<uint4 *>(s_lab);
-  uint4 *db = reinterpret_cast<uint4 *>(s_gam);
+  uint4 *db = reinterpret_cast<uint4 *>(s_out);
   for (int i = threadIdx.x; i < kLutEntries / 2; i += blockDim.x) {
     da[i] = __ldg(a + i);
     db[i] = __ldg(b + i);
@@ -60,7 +106,8 @@ __device__ __forceinline__ void load_luts(float2 *s_lab, float2 *s_gam, const fl
 
 // demosaic.rs:77-90 for every position of the CFA period: which of the nine 3x3 taps feed which colour bin.
 // Taps of the centre's own colour other than the centre itself go to the discarded fifth bin.
-__device__ __forceinline__ void build_taps(Smem &sm, const CfaDev &cfa, int pw, int ph) {
+template <class S>
+__device__ __forceinline__ void build_taps(S &sm, const CfaDev &cfa, int pw, int ph) {
   for (int pos = threadIdx.x; pos < pw * ph; pos += blockDim.x) {
     int pr = pos / pw, pc = pos - pr * pw;
     int pix = cfa.pat[pr * 48 + pc];
@@ -127,42 +174,230 @@ __device__ __forceinline__ void store_px4(void *out, size_t pix_index, int n, co
   }
 }
 
+// 8-bit output already quantised (q = 12 bytes in 12 registers)
+__device__ __forceinline__ void store_px4_bytes(void *out, size_t pix_index, int n, const uint32_t q[12]) {
+  uint8_t *o = reinterpret_cast<uint8_t *>(out) + pix_index * 3;
+  if (n == 4 && ((reinterpret_cast<uintptr_t>(o) & 3) == 0)) {
+    uint32_t *o4 = reinterpret_cast<uint32_t *>(o);
+    o4[0] = q[0] | (q[1] << 8) | (q[2] << 16) | (q[3] << 24);
+    o4[1] = q[4] | (q[5] << 8) | (q[6] << 16) | (q[7] << 24);
+    o4[2] = q[8] | (q[9] << 8) | (q[10] << 16) | (q[11] << 24);
+  } else {
+    for (int j = 0; j < n * 3; j++) o[j] = (uint8_t)q[j];
+  }
+}
+
+// ---------------------------------------------------------------- colour chain on a pixel pair
+
+// The fast side of XYZ_LAB_TRANSFORM.lookup for any bit pattern: in-table values take the exact lerp, anything else
+// reads a masked (valid) entry whose result the caller replaces with lab_f_slow().
+__device__ __forceinline__ float lab_lerp_masked(uint32_t lut_base, float val) {
+  float pos = val * kLutMax;
+  float tf = __fadd_rd(pos, 8388608.0f);
+  float base = tf - 8388608.0f;
+  float a = pos - base;
+  uint32_t off = (__float_as_uint(tf) << 3) & 0xfff8u;
+  float2 e;
+  asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(e.x), "=f"(e.y) : "r"(lut_base + off));
+  return e.x + a * e.y;
+}
+// true when lookup() takes the table branch with a key the masked lerp computes correctly: +0.0 <= v <= 1.0
+__device__ __forceinline__ bool in_table(float v) { return __float_as_uint(v) <= 0x3f800000u; }
+
+// SplineFunc::interpolate (curves.rs:126-157) from the per-segment table in shared memory.
+__device__ __forceinline__ float spline_eval_smem(const float (*spl)[8], const SplineDev &s, float val) {
+  int seg = 0;
+  for (int j = 1; j < s.nseg; j++) seg = (val >= s.x[j]) ? j : seg;
+  const float4 c = *reinterpret_cast<const float4 *>(spl[seg]);
+  const float c3 = spl[seg][4];
+  float diff = val - c.x;
+  float res = c.y + c.z * diff + c.w * diff * diff + c3 * diff * diff * diff;
+  const int last = s.n - 1;
+  res = (val <= s.x[0]) ? s.y[0] : res;
+  res = (val >= s.x[last]) ? s.y[last] : res;
+  res = (val != val) ? s.y[(s.nseg - 1) / 2] : res;
+  return res;
+}
+
+// 8-bit output of one channel: output8bit(apply_srgb_gamma(clamp(v))) through the threshold table
+__device__ __forceinline__ uint32_t gamma8(uint32_t lut_base, float v) {
+  float vc = fminf(fmaxf(v, 0.0f), 1.0f);
+  float pos = vc * kLutMax;
+  float tf = __fadd_rd(pos, 8388608.0f);
+  uint32_t off = (__float_as_uint(tf) << 3) & 0xfff8u;
+  float thr;
+  uint32_t base;
+  asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=f"(thr), "=r"(base) : "r"(lut_base + off));
+  return base + (vc >= thr ? 1u : 0u);
+}
+
+// to_lab + basecurve + from_lab (+ gamma) for two pixels; out-of-table XYZ ratios go through the warp queue.
+// All 32 lanes of the warp must call this together.
+template <int OUT>
+__device__ __forceinline__ void chain_pair(const ColorParams &P, const Smem &sm, float *queue, uint32_t lab_base,
+                                           uint32_t out_base, bool g8, const float r[2], const float g[2], const float b[2],
+                                           const float e[2], float orr[2], float og[2], float ob[2], uint32_t q8[6]) {
+  const int lane = threadIdx.x & 31;
+  float xr[2], yr[2], zr[2];
+#pragma unroll
+  for (int j = 0; j < 2; j++) {
+    float cr = fminf(r[j] * P.mul[0], 1.0f);
+    float cg = fminf(g[j] * P.mul[1], 1.0f);
+    float cb = fminf(b[j] * P.mul[2], 1.0f);
+    float x = cr * P.cm[0] + cg * P.cm[1] + cb * P.cm[2];
+    float y = cr * P.cm[4] + cg * P.cm[5] + cb * P.cm[6];
+    float z = cr * P.cm[8] + cg * P.cm[9] + cb * P.cm[10];
+    if (P.use_e) {
+      float ce = fminf(e[j] * P.mul[3], 1.0f);
+      x = x + ce * P.cm[3];
+      y = y + ce * P.cm[7];
+      z = z + ce * P.cm[11];
+    }
+    xr[j] = IPB_DIVC(x, 0.95047f);
+    yr[j] = y;  // y / 1.0
+    zr[j] = IPB_DIVC(z, 1.08883f);
+  }
+  float f[6] = {lab_lerp_masked(lab_base, xr[0]), lab_lerp_masked(lab_base, yr[0]), lab_lerp_masked(lab_base, zr[0]),
+                lab_lerp_masked(lab_base, xr[1]), lab_lerp_masked(lab_base, yr[1]), lab_lerp_masked(lab_base, zr[1])};
+  const float v[6] = {xr[0], yr[0], zr[0], xr[1], yr[1], zr[1]};
+  bool oor[6];
+  bool any = false;
+#pragma unroll
+  for (int k = 0; k < 6; k++) { oor[k] = !in_table(v[k]); any |= oor[k]; }
+  if (__any_sync(kFull, any)) {
+    // compact the out-of-table values of the whole warp into the queue, evaluate densely, scatter back
+    const uint32_t lt = (1u << lane) - 1u;
+    int n = 0;
+    int slot[6];
+#pragma unroll
+    for (int k = 0; k < 6; k++) {
+      const uint32_t bal = __ballot_sync(kFull, oor[k]);
+      slot[k] = n + __popc(bal & lt);
+      if (oor[k]) queue[slot[k]] = v[k];
+      n += __popc(bal);
+    }
+    __syncwarp();
+    for (int i = lane; i < n; i += 32) queue[i] = lab_f_slow(queue[i]);
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < 6; k++)
+      if (oor[k]) f[k] = queue[slot[k]];
+    __syncwarp();
+  }
+#pragma unroll
+  for (int j = 0; j < 2; j++) {
+    const float fx = f[3 * j], fy = f[3 * j + 1], fz = f[3 * j + 2];
+    float l = 116.0f * fy - 16.0f;
+    float a = 500.0f * (fx - fy);
+    float bb = 200.0f * (fy - fz);
+    l = IPB_DIVC(l, 100.0f);
+    a = IPB_DIVC(a + 127.0f, 255.0f);
+    bb = IPB_DIVC(bb + 127.0f, 255.0f);
+    if (P.sp.n > 0) l = spline_eval_smem(sm.spl, P.sp, l);
+    float rr, gg, bl;
+    lab_to_rgb(P, l, a, bb, rr, gg, bl);
+    if (OUT == kOutU8 && g8) {
+      q8[3 * j] = gamma8(out_base, rr);
+      q8[3 * j + 1] = gamma8(out_base, gg);
+      q8[3 * j + 2] = gamma8(out_base, bl);
+    } else {
+      if (!P.linear) {
+        const LutShared gam{out_base};
+        rr = gamma_elem(gam, rr);
+        gg = gamma_elem(gam, gg);
+        bl = gamma_elem(gam, bl);
+      }
+      if (OUT == kOutU8) {
+        q8[3 * j] = output8bit(rr);
+        q8[3 * j + 1] = output8bit(gg);
+        q8[3 * j + 2] = output8bit(bl);
+      }
+      orr[j] = rr; og[j] = gg; ob[j] = bl;
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------- full resolution
 
-template <int OUT>
+template <int OUT, bool BAYER>
 __global__ void __launch_bounds__(kNT, 1)
 k_fused_full(const __grid_constant__ FullParams p, const __grid_constant__ CfaDev cfa,
-             const __grid_constant__ ColorParams P) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+             const __grid_constant__ ColorParams P, const __grid_constant__ CUtensorMap tmap) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   Smem &sm = *reinterpret_cast<Smem *>(smem_raw);
   const int tid = threadIdx.x;
+  const int ntiles = p.tiles_x * p.tiles_y;
+  const uint32_t bar0 = smem_u32(&sm.mbar[0]);
+  constexpr uint32_t kStageBytes = kTileElems * sizeof(uint16_t);
 
-  load_luts(sm.lut_lab, sm.lut_gamma, p.lut_lab, p.lut_gamma);
+  auto issue_tile = [&](int t, int stage) {  // one thread: arm the stage's barrier and start the bulk tensor copy
+    const int tyi = t / p.tiles_x, txi = t - tyi * p.tiles_x;
+    const int x = txi * kTW - 4 + p.crop_x;
+    const int y = p.out_row0 + tyi * kTH - 1 + p.crop_y - p.src_row0;
+    mbar_expect_tx(bar0 + 8 * stage, kStageBytes);
+    tma_load_2d(smem_u32(sm.raw[stage]), &tmap, x, y, bar0 + 8 * stage);
+  };
+
+  if (p.use_tma && tid == 0) {
+    mbar_init(bar0, 1);
+    mbar_init(bar0 + 8, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    if ((int)blockIdx.x < ntiles) issue_tile(blockIdx.x, 0);
+  }
+  load_luts(sm.lut_lab, sm.lut_out, p.lut_lab, p.lut_out);
   build_taps(sm, cfa, p.pw, p.ph);
-  const LutShared lab{smem_u32(sm.lut_lab)}, gam{smem_u32(sm.lut_gamma)};
+  for (int i = tid; i < kMaxSplinePts; i += kNT) {
+    sm.spl[i][0] = P.sp.x[i]; sm.spl[i][1] = P.sp.y[i]; sm.spl[i][2] = P.sp.c1[i]; sm.spl[i][3] = P.sp.c2[i];
+    sm.spl[i][4] = P.sp.c3[i];
+  }
+  const uint32_t lab_base = smem_u32(sm.lut_lab), out_base = smem_u32(sm.lut_out);
+  float *queue = sm.queue[tid >> 5];
+  const bool g8 = OUT == kOutU8 && p.gamma8 != 0;
 
   // Bayer phase (cropped-frame coordinates): colour of the pixel at (row&1, col&1)
   const int c00 = cfa.pat[0], c10 = cfa.pat[48];
 
-  const int ntiles = p.tiles_x * p.tiles_y;
-  for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+  int it = 0;
+  for (int t = blockIdx.x; t < ntiles; t += gridDim.x, it++) {
     const int tyi = t / p.tiles_x, txi = t - tyi * p.tiles_x;
     const int ty0 = p.out_row0 + tyi * kTH, tx0 = txi * kTW;
-    __syncthreads();  // previous tile fully consumed (and, first time round, tables complete)
+    const int stage = it & 1;
+    __syncthreads();  // previous tile fully consumed (and, first time round, tables and barriers ready)
 
-    // ---- stage the tile: gofloat once per sensor pixel, zero outside the frame
-    for (int i = tid; i < kTileRows * (kTW + 2); i += kNT) {
-      const int r = i / (kTW + 2), c = i - r * (kTW + 2);
-      const int y = ty0 - 1 + r, x = tx0 - 1 + c;
-      float v = 0.0f;
-      if (y >= 0 && y < p.height && x >= 0 && x < p.width) {
-        const int sr = y + p.crop_y - p.src_row0;
-        if (sr >= 0 && sr < p.src_rows) {
-          const uint16_t rawv = __ldg(p.raw + (long long)sr * p.raw_pitch + p.crop_x + x);
-          v = golevel((float)rawv, p.black, p.range, p.range_rc, p.exact_rc);
+    if (p.use_tma) {
+      if (tid == 0 && t + (int)gridDim.x < ntiles) issue_tile(t + gridDim.x, stage ^ 1);  // prefetch the next tile
+      mbar_wait(bar0 + 8 * stage, (it >> 1) & 1);
+      // ---- gofloat once per sensor pixel: eight u16 -> eight f32 per thread
+      const uint16_t *rs = sm.raw[stage];
+      for (int g8 = tid; g8 < kTileElems / 8; g8 += kNT) {
+        const uint4 pk = *reinterpret_cast<const uint4 *>(rs + g8 * 8);
+        const uint32_t w4[4] = {pk.x, pk.y, pk.z, pk.w};
+        float v[8];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          v[2 * k] = golevel((float)(w4[k] & 0xffffu), p.black, p.range, p.range_rc, p.exact_rc);
+          v[2 * k + 1] = golevel((float)(w4[k] >> 16), p.black, p.range, p.range_rc, p.exact_rc);
         }
+        float4 *dst = reinterpret_cast<float4 *>(sm.tile + g8 * 8);
+        dst[0] = make_float4(v[0], v[1], v[2], v[3]);
+        dst[1] = make_float4(v[4], v[5], v[6], v[7]);
       }
-      sm.tile[r * kTileStride + c + 3] = v;
+    } else {
+      // ---- fallback staging for sources TMA cannot describe (base or pitch not 16-byte aligned)
+      for (int i = tid; i < kTileRows * (kTW + 2); i += kNT) {
+        const int r = i / (kTW + 2), c = i - r * (kTW + 2);
+        const int y = ty0 - 1 + r, x = tx0 - 1 + c;
+        float v = 0.0f;
+        if (y >= 0 && y < p.height && x >= 0 && x < p.width) {
+          const int sr = y + p.crop_y - p.src_row0;
+          if (sr >= 0 && sr < p.src_rows) {
+            const uint16_t rawv = __ldg(p.raw + (long long)sr * p.raw_pitch + p.crop_x + x);
+            v = golevel((float)rawv, p.black, p.range, p.range_rc, p.exact_rc);
+          }
+        }
+        sm.tile[r * kTileStride + c + 3] = v;
+      }
     }
     __syncthreads();
 
@@ -173,7 +408,7 @@ k_fused_full(const __grid_constant__ FullParams p, const __grid_constant__ CfaDe
       const bool live = y < p.out_row1 && x0 < p.width;
       const int npx = live ? min(4, p.width - x0) : 0;
       const bool interior = y >= 1 && y <= p.height - 2 && x0 >= 1 && x0 + 4 <= p.width - 1;
-      const bool fast = p.bayer && __all_sync(0xffffffffu, !live || interior);
+      const bool fast = BAYER && __all_sync(kFull, !live || interior);
 
       // 3 x 6 window: rows y-1..y+1, cols x0-1..x0+4
       float w[3][6];
@@ -212,15 +447,17 @@ k_fused_full(const __grid_constant__ FullParams p, const __grid_constant__ CfaDe
           ce[j] = 0.0f;
         }
       } else {
+        // generic CFA / frame border: per-position tap masks, out-of-frame taps dropped from sum and count.
+        // With TMA staging the tile holds whatever lies outside the cropped frame; the masks never select it.
         const int pr = y % p.ph;
         int pc = x0 % p.pw;
 #pragma unroll
         for (int j = 0; j < 4; j++) {
           const int x = x0 + j;
           uint32_t valid = 0x1ffu;
-          if (y == 0) valid &= ~0x007u;
-          if (y == p.height - 1) valid &= ~0x1c0u;
-          if (x == 0) valid &= ~0x049u;
+          if (y <= 0) valid &= ~0x007u;
+          if (y >= p.height - 1) valid &= ~0x1c0u;
+          if (x <= 0) valid &= ~0x049u;
           if (x >= p.width - 1) valid &= ~0x124u;
           const uint2 mm = sm.taps[pr * p.pw + pc];
           pc = (pc + 1 == p.pw) ? 0 : pc + 1;
@@ -235,9 +472,14 @@ k_fused_full(const __grid_constant__ FullParams p, const __grid_constant__ CfaDe
       }
 
       float orr[4], og[4], ob[4];
-#pragma unroll
-      for (int j = 0; j < 4; j++) color_chain(P, lab, gam, cr[j], cg[j], cb[j], ce[j], orr[j], og[j], ob[j]);
-      if (live) store_px4<OUT>(p.out, (size_t)(y - p.out_row0) * p.width + x0, npx, orr, og, ob);
+      uint32_t q8[12];
+      chain_pair<OUT>(P, sm, queue, lab_base, out_base, g8, cr, cg, cb, ce, orr, og, ob, q8);
+      chain_pair<OUT>(P, sm, queue, lab_base, out_base, g8, cr + 2, cg + 2, cb + 2, ce + 2, orr + 2, og + 2, ob + 2, q8 + 6);
+      if (live) {
+        const size_t pix = (size_t)(y - p.out_row0) * p.width + x0;
+        if (OUT == kOutU8) store_px4_bytes(p.out, pix, npx, q8);
+        else store_px4<OUT>(p.out, pix, npx, orr, og, ob);
+      }
     }
   }
 }
@@ -265,12 +507,14 @@ struct SmemScaled {
   uint8_t pat[48 * 48];
 };
 
+constexpr int kNTScaled = 512;
+
 __device__ __forceinline__ int f2i_sat(float f) {  // Rust `f as usize` for the values met here (>= 0, < 2^31)
   return (int)min(__float2uint_rz(f), 0x7fffffffu);
 }
 
 template <int OUT>
-__global__ void __launch_bounds__(kNT, 1)
+__global__ void __launch_bounds__(kNTScaled, 1)
 k_fused_scaled(const __grid_constant__ ScaledParams p, const __grid_constant__ CfaDev cfa,
                const __grid_constant__ ColorParams P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -281,7 +525,8 @@ k_fused_scaled(const __grid_constant__ ScaledParams p, const __grid_constant__ C
   const LutShared lab{smem_u32(sm.lut_lab)}, gam{smem_u32(sm.lut_gamma)};
 
   const long long npix = (long long)(p.out_row1 - p.out_row0) * p.nwidth;
-  for (long long idx = (long long)blockIdx.x * kNT + threadIdx.x; idx < npix; idx += (long long)gridDim.x * kNT) {
+  for (long long idx = (long long)blockIdx.x * kNTScaled + threadIdx.x; idx < npix;
+       idx += (long long)gridDim.x * kNTScaled) {
     const int row = p.out_row0 + (int)(idx / p.nwidth), col = (int)(idx % p.nwidth);
     const float frow = (float)row, frow1 = (float)(row + 1), fcol = (float)col, fcol1 = (float)(col + 1);
     // scaling.rs:77-89 with topleft = (0,0), skip_x_y = skip_y_x = 0
@@ -324,6 +569,40 @@ k_fused_scaled(const __grid_constant__ ScaledParams p, const __grid_constant__ C
   }
 }
 
+// ---------------------------------------------------------------------------------------- gamma8 checks
+
+// every non-negative f32 bit pattern up to 1.0, plus negative / >1 / NaN inputs via the sign and top bits
+__global__ void k_gamma8_selftest(const float2 *__restrict__ lut_gamma, const float2 *__restrict__ lut_gamma8,
+                                  unsigned long long *mismatches) {
+  const LutGlobal gam{lut_gamma};
+  unsigned long long bad = 0;
+  const uint32_t nthreads = gridDim.x * blockDim.x, t0 = blockIdx.x * blockDim.x + threadIdx.x;
+  for (uint64_t b = t0; b <= 0xffffffffull; b += nthreads) {
+    const uint32_t bits = (uint32_t)b;
+    // [0, 1.0] exhaustively; elsewhere (negative, > 1, inf, NaN) every 4099th pattern
+    if (bits > 0x3f800000u && (bits % 4099u) != 0u) continue;
+    const float v = __uint_as_float(bits);
+    const uint32_t want = output8bit(gamma_elem(gam, v));
+    const float vc = fminf(fmaxf(v, 0.0f), 1.0f);
+    const float pos = vc * kLutMax;
+    const float tf = __fadd_rd(pos, 8388608.0f);
+    const float2 e = __ldg(lut_gamma8 + (__float_as_uint(tf) & 0x1fffu));
+    const uint32_t got = __float_as_uint(e.y) + (vc >= e.x ? 1u : 0u);
+    bad += got != want;
+  }
+  if (bad) atomicAdd(mismatches, bad);
+}
+
+__global__ void k_gamma8_pack(const float2 *__restrict__ lut_gamma8, const float *__restrict__ in, size_t n,
+                              uint8_t *__restrict__ out) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float vc = fminf(fmaxf(in[i], 0.0f), 1.0f);
+  const float tf = __fadd_rd(vc * kLutMax, 8388608.0f);
+  const float2 e = __ldg(lut_gamma8 + (__float_as_uint(tf) & 0x1fffu));
+  out[i] = (uint8_t)(__float_as_uint(e.y) + (vc >= e.x ? 1u : 0u));
+}
+
 thread_local const char *g_fused_err = "";
 
 template <class K>
@@ -331,9 +610,66 @@ cudaError_t set_smem(K kernel, size_t bytes) {
   return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
 }
 
+// cuTensorMapEncodeTiled through the runtime's driver entry point table: libipb200.so does not link libcuda,
+// so it still loads (and exports its symbols) on a box without a driver.
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = [] {
+    void *f = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &qres) != cudaSuccess ||
+        qres != cudaDriverEntryPointSuccess)
+      f = nullptr;
+    return (EncodeTiledFn)f;
+  }();
+  return fn;
+}
+
+// 2-D u16 tensor map over the source rows present in `raw` (un-cropped sensor width), box = one staged tile.
+bool make_raw_tmap(CUtensorMap *map, const uint16_t *raw, size_t pitch_elems, size_t width_elems, size_t rows) {
+  EncodeTiledFn enc = encode_tiled_fn();
+  if (!enc) return false;
+  if ((reinterpret_cast<uintptr_t>(raw) & 15) || ((pitch_elems * sizeof(uint16_t)) & 15) || rows == 0) return false;
+  const cuuint64_t dims[2] = {(cuuint64_t)width_elems, (cuuint64_t)rows};
+  const cuuint64_t strides[1] = {(cuuint64_t)(pitch_elems * sizeof(uint16_t))};
+  const cuuint32_t box[2] = {(cuuint32_t)kTileStride, (cuuint32_t)kTileRows};
+  const cuuint32_t estr[2] = {1, 1};
+  return enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, const_cast<uint16_t *>(raw), dims, strides, box, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+template <int OUT>
+cudaError_t launch_full_kind(cudaStream_t s, const FullParams &p, const CfaDev &cfa, const ColorParams &P,
+                             const CUtensorMap &tmap, int grid, bool bayer) {
+  const size_t smem = sizeof(Smem);
+  cudaError_t e;
+  if (bayer) {
+    if ((e = set_smem(k_fused_full<OUT, true>, smem)) != cudaSuccess) return e;
+    k_fused_full<OUT, true><<<grid, kNT, smem, s>>>(p, cfa, P, tmap);
+  } else {
+    if ((e = set_smem(k_fused_full<OUT, false>, smem)) != cudaSuccess) return e;
+    k_fused_full<OUT, false><<<grid, kNT, smem, s>>>(p, cfa, P, tmap);
+  }
+  return cudaGetLastError();
+}
+
 }  // namespace
 
 const char *fused_last_error() { return g_fused_err; }
+
+cudaError_t launch_gamma8_selftest(cudaStream_t s, const float2 *lut_gamma, const float2 *lut_gamma8,
+                                   unsigned long long *mismatches) {
+  k_gamma8_selftest<<<148 * 8, 256, 0, s>>>(lut_gamma, lut_gamma8, mismatches);
+  return cudaGetLastError();
+}
+cudaError_t launch_gamma8_pack(cudaStream_t s, const float2 *lut_gamma8, const float *in, size_t n, uint8_t *out) {
+  if (n == 0) return cudaSuccess;
+  k_gamma8_pack<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(lut_gamma8, in, n, out);
+  return cudaGetLastError();
+}
 
 static bool is_rgb_bayer(const CfaDev &cfa) {
   if (cfa.width != 2 || cfa.height != 2) return false;
@@ -359,30 +695,23 @@ cudaError_t launch_fused_full(cudaStream_t s, const FusedArgs &a, const CfaDev &
   p.out_row0 = (int)a.out_row0; p.out_row1 = (int)a.out_row1;
   p.out = a.out;
   p.black = a.black; p.range = a.range; p.range_rc = a.range_rc; p.exact_rc = a.exact_rc;
-  p.lut_lab = a.lut_lab; p.lut_gamma = a.lut_gamma;
+  p.lut_lab = a.lut_lab;
+  p.gamma8 = (a.out_kind == kOutU8 && !P.linear && a.lut_gamma8) ? 1 : 0;
+  p.lut_out = p.gamma8 ? a.lut_gamma8 : a.lut_gamma;
   p.tiles_x = (p.width + kTW - 1) / kTW;
   p.tiles_y = (p.out_row1 - p.out_row0 + kTH - 1) / kTH;
   p.pw = cfa.width; p.ph = cfa.height;
-  p.bayer = is_rgb_bayer(cfa) ? 1 : 0;
+  CUtensorMap tmap;
+  memset(&tmap, 0, sizeof(tmap));
+  p.use_tma = (a.use_tma && make_raw_tmap(&tmap, a.raw, a.raw_pitch, a.raw_pitch, a.src_rows)) ? 1 : 0;
+  const bool bayer = is_rgb_bayer(cfa);
   const int ntiles = p.tiles_x * p.tiles_y;
   const int grid = ntiles < sm_count ? ntiles : sm_count;
-  const size_t smem = sizeof(Smem);
-  cudaError_t e;
   switch (a.out_kind) {
-    case kOutF32:
-      if ((e = set_smem(k_fused_full<kOutF32>, smem)) != cudaSuccess) return e;
-      k_fused_full<kOutF32><<<grid, kNT, smem, s>>>(p, cfa, P);
-      break;
-    case kOutU8:
-      if ((e = set_smem(k_fused_full<kOutU8>, smem)) != cudaSuccess) return e;
-      k_fused_full<kOutU8><<<grid, kNT, smem, s>>>(p, cfa, P);
-      break;
-    default:
-      if ((e = set_smem(k_fused_full<kOutU16>, smem)) != cudaSuccess) return e;
-      k_fused_full<kOutU16><<<grid, kNT, smem, s>>>(p, cfa, P);
-      break;
+    case kOutF32: return launch_full_kind<kOutF32>(s, p, cfa, P, tmap, grid, bayer);
+    case kOutU8: return launch_full_kind<kOutU8>(s, p, cfa, P, tmap, grid, bayer);
+    default: return launch_full_kind<kOutU16>(s, p, cfa, P, tmap, grid, bayer);
   }
-  return cudaGetLastError();
 }
 
 cudaError_t launch_fused_scaled(cudaStream_t s, const FusedArgs &a, const CfaDev &cfa, const ColorParams &P,
@@ -402,22 +731,22 @@ cudaError_t launch_fused_scaled(cudaStream_t s, const FusedArgs &a, const CfaDev
   p.skip_x = ((float)((long)a.width - 1) - 0.0f) / (float)(a.out_width - 1);
   p.skip_y = ((float)((long)a.height - 1) - 0.0f) / (float)(a.out_height - 1);
   const long long npix = (long long)(p.out_row1 - p.out_row0) * p.nwidth;
-  long long blocks = (npix + kNT - 1) / kNT;
+  long long blocks = (npix + kNTScaled - 1) / kNTScaled;
   const int grid = (int)(blocks < sm_count ? blocks : sm_count);
   const size_t smem = sizeof(SmemScaled);
   cudaError_t e;
   switch (a.out_kind) {
     case kOutF32:
       if ((e = set_smem(k_fused_scaled<kOutF32>, smem)) != cudaSuccess) return e;
-      k_fused_scaled<kOutF32><<<grid, kNT, smem, s>>>(p, cfa, P);
+      k_fused_scaled<kOutF32><<<grid, kNTScaled, smem, s>>>(p, cfa, P);
       break;
     case kOutU8:
       if ((e = set_smem(k_fused_scaled<kOutU8>, smem)) != cudaSuccess) return e;
-      k_fused_scaled<kOutU8><<<grid, kNT, smem, s>>>(p, cfa, P);
+      k_fused_scaled<kOutU8><<<grid, kNTScaled, smem, s>>>(p, cfa, P);
       break;
     default:
       if ((e = set_smem(k_fused_scaled<kOutU16>, smem)) != cudaSuccess) return e;
-      k_fused_scaled<kOutU16><<<grid, kNT, smem, s>>>(p, cfa, P);
+      k_fused_scaled<kOutU16><<<grid, kNTScaled, smem, s>>>(p, cfa, P);
       break;
   }
   return cudaGetLastError();

@@ -30,6 +30,7 @@ struct ipb_ctx {
   bool own_stream = false;
   int sm_count = 0;
   float2 *lut_lab = nullptr, *lut_gamma = nullptr, *lut_rev = nullptr;  // device {v, dv} tables
+  float2 *lut_gamma8 = nullptr;  // device {threshold, base} table: output8bit(apply_srgb_gamma(v)) per segment
   std::string err;
   unsigned long long launches = 0;
 };
@@ -49,6 +50,7 @@ struct ipb_pipeline {
   ipb_ops ops{};
   ipb_settings settings{};
   int fused = 1;
+  int use_tma = 1;
   // row-stripe source (multi-GPU / chunked transfers)
   bool has_stripe = false;
   ipb_stripe stripe{};
@@ -368,6 +370,70 @@ bool golevel_rc_exact(float black, float range, float rc) {
   return true;
 }
 
+
+// ---- 8-bit gamma threshold table.
+// g(v) = output8bit(SRGB_GAMMA_TRANSFORM.lookup(v)) for v in [0,1] (gamma.rs:21 + pipeline.rs:408-414) is a
+// non-decreasing step function of v: inside table segment `key` every operation of the lerp
+// (pos = v*8191, a = pos - key, t[key] + a*dt with dt >= 0) and of output8bit (v*256, clamp, trunc) is monotone
+// under round-to-nearest, and the segment ends meet because t[key] + dt == t[key+1] exactly (Sterbenz).  One
+// segment spans at most 256*12.92/8191 < 1 output steps, so g is known from {g(first v of the segment), the
+// smallest v where it steps up}.  The device evaluates base + (v >= threshold): identical bytes, ~half the
+// instructions.  Everything below is verified while building; on any violation the table is not used.
+float gamma_lerp_host(const float *t, float v) {
+  float pos = v * (float)(kLutEntries - 1);
+  float base = truncf(pos);
+  int key = (int)base;
+  float a = pos - base;
+  return t[key] + a * (t[key + 1] - t[key]);
+}
+uint32_t out8_host(float v) {  // color_conversions.rs:323-325
+  float t = v * 256.0f;
+  t = t > 0.0f ? t : 0.0f;  // max(0): NaN -> 0
+  t = t < 255.0f ? t : 255.0f;
+  return (uint32_t)t;
+}
+uint32_t g8_host(const float *t, float v) { return out8_host(gamma_lerp_host(t, v)); }
+float f_from_bits(uint32_t b) { float f; memcpy(&f, &b, 4); return f; }
+uint32_t bits_of(float f) { uint32_t b; memcpy(&b, &f, 4); return b; }
+int key_of(float v) { return (int)truncf(v * (float)(kLutEntries - 1)); }
+
+struct Gamma8Entry { float thr; uint32_t base; };
+
+bool build_gamma8(const float *t, std::vector<Gamma8Entry> *out) {
+  out->assign(kLutEntries, Gamma8Entry{2.0f, 0u});
+  const uint32_t one = bits_of(1.0f);
+  // first float (by bit pattern; non-negative floats order like their bits) of every segment
+  std::vector<uint32_t> first(kLutEntries + 1);
+  for (int key = 0; key < kLutEntries; key++) {
+    uint32_t lo = 0, hi = one;  // smallest bits b with key_of(b) >= key; key_of is monotone in b
+    while (lo < hi) {
+      uint32_t mid = lo + (hi - lo) / 2;
+      if (key_of(f_from_bits(mid)) >= key) hi = mid; else lo = mid + 1;
+    }
+    first[key] = lo;
+  }
+  first[kLutEntries] = one + 1;
+  uint32_t prev_top = 0;
+  for (int key = 0; key < kLutEntries; key++) {
+    const uint32_t b0 = first[key], b1 = first[key + 1] - 1;  // segment = bit patterns [b0, b1]
+    if (b1 < b0 || key_of(f_from_bits(b0)) != key || key_of(f_from_bits(b1)) != key) return false;
+    const uint32_t base = g8_host(t, f_from_bits(b0)), top = g8_host(t, f_from_bits(b1));
+    if (base < prev_top || top < base || top > base + 1) return false;
+    prev_top = top;
+    Gamma8Entry e{2.0f, base};
+    if (top == base + 1) {
+      uint32_t lo = b0 + 1, hi = b1;  // smallest b with g8 == top
+      while (lo < hi) {
+        uint32_t mid = lo + (hi - lo) / 2;
+        if (g8_host(t, f_from_bits(mid)) > base) hi = mid; else lo = mid + 1;
+      }
+      e.thr = f_from_bits(lo);
+    }
+    (*out)[key] = e;
+  }
+  return true;
+}
+
 int upload_lut(ipb_ctx *ctx, const float *t, float2 **out) {
   std::vector<float2> host(kLutEntries);
   for (int i = 0; i < kLutEntries; i++) host[i] = make_float2(t[i], t[i + 1] - t[i]);
@@ -471,6 +537,20 @@ int ipb_ctx_create(int device, void *stream, ipb_ctx **out) {
   if ((rc = upload_lut(ctx, T.lab, &ctx->lut_lab)) != IPB_OK) return bail(rc);
   if ((rc = upload_lut(ctx, T.fwd, &ctx->lut_gamma)) != IPB_OK) return bail(rc);
   if ((rc = upload_lut(ctx, T.rev, &ctx->lut_rev)) != IPB_OK) return bail(rc);
+  {
+    static std::vector<Gamma8Entry> g8;
+    static bool g8_ok = false;
+    static std::once_flag once;
+    std::call_once(once, [&] { g8_ok = build_gamma8(T.fwd, &g8); });
+    if (g8_ok) {
+      static_assert(sizeof(Gamma8Entry) == sizeof(float2), "table entry layout");
+      if ((e = cudaMalloc((void **)&ctx->lut_gamma8, kLutEntries * sizeof(float2))) != cudaSuccess ||
+          (e = cudaMemcpy(ctx->lut_gamma8, g8.data(), kLutEntries * sizeof(float2), cudaMemcpyHostToDevice)) != cudaSuccess) {
+        ctx->err = cudaGetErrorString(e);
+        return bail(IPB_ERR_CUDA);
+      }
+    }
+  }
   *out = ctx;
   return IPB_OK;
 }
@@ -482,6 +562,7 @@ void ipb_ctx_destroy(ipb_ctx *ctx) {
   if (ctx->lut_lab) cudaFree(ctx->lut_lab);
   if (ctx->lut_gamma) cudaFree(ctx->lut_gamma);
   if (ctx->lut_rev) cudaFree(ctx->lut_rev);
+  if (ctx->lut_gamma8) cudaFree(ctx->lut_gamma8);
   if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -1182,6 +1263,8 @@ static int run_fused(ipb_pipeline *p, const FusedPlan &plan, int out_kind, size_
   a.exact_rc = golevel_rc_exact(a.black, a.range, a.range_rc) ? 1 : 0;
   a.lut_lab = ctx->lut_lab;
   a.lut_gamma = ctx->lut_gamma;
+  a.lut_gamma8 = ctx->lut_gamma8;
+  a.use_tma = p->use_tma;
   cudaError_t e = plan.mode == kFusedFull ? launch_fused_full(ctx->stream, a, plan.cfa, P, ctx->sm_count)
                                           : launch_fused_scaled(ctx->stream, a, plan.cfa, P, ctx->sm_count);
   if (e != cudaSuccess) return fail(ctx, IPB_ERR_CUDA, "fused kernel: %s %s", cudaGetErrorString(e), fused_last_error());
@@ -1408,6 +1491,41 @@ int ipb_pipeline_output_8bit_stripe(ipb_pipeline *p, uint8_t *dst, size_t dst_ca
   }
   if (width) *width = plan.out_width;
   if (rows) *rows = r1 - r0;
+  return IPB_OK;
+}
+
+int ipb_pipeline_set_tma(ipb_pipeline *p, int use_tma) {
+  if (!p) return IPB_ERR_INVALID;
+  p->use_tma = use_tma != 0;
+  return IPB_OK;
+}
+
+int ipb_selftest_gamma8(ipb_ctx *ctx, unsigned long long *mismatches) {
+  IPB_TRY(enter(ctx));
+  if (!mismatches) return fail(ctx, IPB_ERR_INVALID, "null pointer");
+  if (!ctx->lut_gamma8) return fail(ctx, IPB_ERR_UNSUPPORTED, "the 8-bit gamma threshold table failed its build-time checks");
+  unsigned long long *d;
+  IPB_CUDA(ctx, cudaMallocAsync((void **)&d, sizeof(*d), ctx->stream));
+  IPB_CUDA(ctx, cudaMemsetAsync(d, 0, sizeof(*d), ctx->stream));
+  IPB_LAUNCH(ctx, launch_gamma8_selftest(ctx->stream, ctx->lut_gamma, ctx->lut_gamma8, d));
+  IPB_CUDA(ctx, cudaMemcpyAsync(mismatches, d, sizeof(*d), cudaMemcpyDeviceToHost, ctx->stream));
+  IPB_CUDA(ctx, cudaFreeAsync(d, ctx->stream));
+  IPB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return IPB_OK;
+}
+
+int ipb_gamma_pack_8bit(ipb_ctx *ctx, const float *in, size_t n, uint8_t *out) {
+  IPB_TRY(enter(ctx));
+  if (!in || !out) return fail(ctx, IPB_ERR_INVALID, "null pointer");
+  if (!ctx->lut_gamma8) return fail(ctx, IPB_ERR_UNSUPPORTED, "the 8-bit gamma threshold table failed its build-time checks");
+  float *d;
+  IPB_CUDA(ctx, cudaMallocAsync((void **)&d, (n ? n : 1) * 5, ctx->stream));
+  uint8_t *o = (uint8_t *)(d + n);
+  IPB_CUDA(ctx, cudaMemcpyAsync(d, in, n * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+  IPB_LAUNCH(ctx, launch_gamma8_pack(ctx->stream, ctx->lut_gamma8, d, n, o));
+  IPB_CUDA(ctx, cudaMemcpyAsync(out, o, n, cudaMemcpyDeviceToHost, ctx->stream));
+  IPB_CUDA(ctx, cudaFreeAsync(d, ctx->stream));
+  IPB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return IPB_OK;
 }
 

@@ -42,6 +42,7 @@ struct FusedArgs {
   int exact_rc;
   const float2 *lut_lab;   // device tables {v, dv}
   const float2 *lut_gamma;
+  const float2 *lut_gamma8;  // 8-bit output: {threshold, base} per table segment (ipb_host.cu build_gamma8)
   int use_tma;             // full-res kernel: stage tiles with TMA (needs 16B-aligned base and pitch)
 };
 
@@ -77,5 +78,11 @@ cudaError_t launch_fused_full(cudaStream_t s, const FusedArgs &a, const CfaDev &
 cudaError_t launch_fused_scaled(cudaStream_t s, const FusedArgs &a, const CfaDev &cfa, const ColorParams &P,
                                 int sm_count);
 const char *fused_last_error();
+// self-test of the 8-bit gamma threshold table: every f32 in [0,1] (and a few outside) through gamma8() vs
+// output8bit(gamma_elem()); *mismatches (device) receives the count
+cudaError_t launch_gamma8_selftest(cudaStream_t s, const float2 *lut_gamma, const float2 *lut_gamma8,
+                                   unsigned long long *mismatches);
+// gamma + 8-bit pack of arbitrary floats through the threshold table (tests)
+cudaError_t launch_gamma8_pack(cudaStream_t s, const float2 *lut_gamma8, const float *in, size_t n, uint8_t *out);
 
 }  // namespace ipb

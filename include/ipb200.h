@@ -237,6 +237,9 @@ int ipb_pipeline_set_source(ipb_pipeline *p, const ipb_source *image);
 /* 1 (default): Pipeline::run may use the fused raw->sRGB kernel when the op chain allows it;
  * 0: always run op by op (one kernel + one OpBuffer per op, like the reference). */
 int ipb_pipeline_set_fused(ipb_pipeline *p, int fused);
+/* 1 (default): the full-resolution fused kernel stages raw tiles with TMA when the source allows it (16-byte
+ * aligned base and row pitch); 0: always use the plain-load staging path.  Results are identical. */
+int ipb_pipeline_set_tma(ipb_pipeline *p, int use_tma);
 /* size walk of Pipeline::run (pipeline.rs:313-338): final output size; also sets settings.demosaic_* */
 int ipb_pipeline_output_size(ipb_pipeline *p, size_t *width, size_t *height);
 /* Pipeline::run(None) — pipeline.rs:311-375; result is a 3-channel f32 OpBuffer */
@@ -257,6 +260,14 @@ int ipb_pipeline_stripe_rows(ipb_pipeline *p, size_t out_row0, size_t out_row1, 
 int ipb_pipeline_set_stripe_source(ipb_pipeline *p, const ipb_source *rows, const ipb_stripe *stripe);
 int ipb_pipeline_output_8bit_stripe(ipb_pipeline *p, uint8_t *dst, size_t dst_capacity, int dst_on_device,
                                     size_t *width, size_t *rows);
+
+/* ------------------------------------------------------------------ self-checks of derived tables
+ * The fused 8-bit path evaluates output8bit(apply_srgb_gamma(v)) (gamma.rs:21, color_conversions.rs:323-325)
+ * through a per-segment threshold table derived from SRGB_GAMMA_TRANSFORM.  ipb_selftest_gamma8 compares it on
+ * the device with the plain lerp + quantise code for every f32 in [0,1] and a sample of all other bit patterns;
+ * ipb_gamma_pack_8bit runs it on n host floats (tests compare with the oracle). */
+int ipb_selftest_gamma8(ipb_ctx *ctx, unsigned long long *mismatches);
+int ipb_gamma_pack_8bit(ipb_ctx *ctx, const float *in, size_t n, uint8_t *out);
 
 /* ------------------------------------------------------------------ synthetic input (bench/tests)
  * v(i) = splitmix64(seed ^ i) mod 16384 for the pixel with linear index i = row*width + col of the

@@ -149,3 +149,66 @@ def test_xtrans_c3_rows(ip, orc, ctx):
     data = common.synth_cfa(8256, 96, seed=common.SEED + 2)
     po, pg = both(ip, orc, ctx, data, common.raw_params(cfa=common.XTRANS))
     assert_bit_exact(pg.output_8bit().to_numpy(), orc.pipeline_output_8bit(po), "C3 band")
+
+
+def test_gamma8_threshold_table_exhaustive(ip, ctx):
+    """The fused 8-bit path's threshold table against the plain gamma lerp + output8bit on the device: every f32 in
+    [0, 1] and a sample of all other bit patterns (negative, > 1, inf, NaN)."""
+    import ctypes as C
+    n = C.c_ulonglong(1)
+    rc = ip.lib().ipb_selftest_gamma8(ctx.handle, C.byref(n))
+    assert rc == 0, ip.lib().ipb_last_error(ctx.handle)
+    assert n.value == 0
+
+
+def test_gamma8_against_oracle(ip, orc, ctx):
+    """gamma.rs:21 + color_conversions.rs:323-325 through the threshold table vs the oracle's OpGamma + output8bit,
+    on random floats, the table knots, and values around every 8-bit step."""
+    rng = np.random.default_rng(7)
+    knots = (np.arange(8193, dtype=np.float32) / np.float32(8191)).astype(np.float32)
+    vals = [rng.random(300000, dtype=np.float32), rng.normal(0.5, 0.6, 100000).astype(np.float32), knots,
+            np.nextafter(knots, np.float32(0)), np.nextafter(knots, np.float32(2)),
+            np.array([-0.0, 0.0, 1.0, 1.5, -1.0, np.inf, -np.inf, np.nan, 0.0031308, 0.00313], np.float32)]
+    v = np.concatenate(vals).astype(np.float32)
+    v = np.resize(v, (v.size // 3) * 3)
+    L = orc.lib()
+    st = orc.Settings()
+    buf = orc.buffer_from_numpy(v.reshape(1, -1, 3))
+    want_f = orc.buffer_to_numpy(L.orc_gamma_run(C_byref(st), buf))[0].reshape(-1)
+    L.orc_buffer_free(buf)
+    assert not np.isnan(want_f).any()  # OpGamma clamps NaN to 0 before the table (gamma.rs:21)
+    want = np.clip(want_f * np.float32(256), 0, 255).astype(np.uint8)  # output8bit, color_conversions.rs:323-325
+    got = np.empty(v.size, np.uint8)
+    rc = ip.lib().ipb_gamma_pack_8bit(ctx.handle, v.ctypes.data, v.size, got.ctypes.data)
+    assert rc == 0, ip.lib().ipb_last_error(ctx.handle)
+    assert_bit_exact(got, want, "gamma8 vs oracle")
+
+
+def C_byref(x):
+    import ctypes as C
+    return C.byref(x)
+
+
+@pytest.mark.parametrize("cfa,shape,crops", [("RGGB", (70, 520), (0, 0, 0, 0)), ("GBRG", (53, 523), (0, 0, 0, 0)),
+                                             ("BGGR", (96, 1032), (3, 5, 2, 7)), (common.XTRANS, (60, 528), (0, 0, 0, 0))])
+def test_tma_and_plain_staging_agree(ip, orc, ctx, cfa, shape, crops):
+    """The TMA-staged and the plain-load staging of the full-resolution kernel give the oracle's bytes; widths that
+    are / are not a multiple of 8 samples exercise both the tensor-map path and its automatic fallback."""
+    data = common.synth_cfa(shape[1], shape[0], seed=61)
+    params = common.raw_params(cfa=cfa, crops=crops)
+    want = orc.pipeline_output_8bit(orc.make_pipeline(data, "raw", params))
+    for on_device in (False, True):
+        for tma in (1, 0):
+            pg = common.make_ipb_pipeline(ip, data, "raw", params, ctx=ctx, on_device=on_device)
+            assert ip.lib().ipb_pipeline_set_tma(pg.handle, tma) == 0
+            assert_bit_exact(pg.output_8bit().to_numpy(), want, f"{cfa} tma={tma} dev={on_device}")
+
+
+def test_natural_frame_mostly_in_table(ip, orc, ctx):
+    """A smooth frame (few out-of-table XYZ ratios: the warp queue is mostly idle) and a clipped one (every pixel
+    beyond white: the queue is full)."""
+    for data in (common.smooth_cfa(777, 211), np.full((64, 512), 16383, np.uint16)):
+        po, pg = both(ip, orc, ctx, data, common.raw_params())
+        assert_bit_exact(pg.output_8bit().to_numpy(), orc.pipeline_output_8bit(po), "natural/clipped u8")
+        po, pg = both(ip, orc, ctx, data, common.raw_params())
+        assert_bit_exact(pg.run().to_numpy(), orc.pipeline_run(po), "natural/clipped f32")
