@@ -6,8 +6,8 @@
 //   k_fused_scaled  the same chain with scaled_demosaic (scaling.rs:132-145) in place of full() — the branch
 //                   OpDemosaic::run takes for scale >= 2 (Bayer) / 3 (X-Trans), demosaic.rs:47-50.
 //
-// k_fused_full is a persistent kernel: one 1024-thread CTA per SM walks 256x16-pixel tiles round-robin.
-//   * the raw u16 tile (+1 px halo, 264x18 box) of the NEXT tile is fetched by TMA (cp.async.bulk.tensor.2d,
+// k_fused_full is a persistent kernel: one 1024-thread CTA per SM walks 128x32-pixel tiles round-robin.
+//   * the raw u16 tile (+1 px halo, 144x34 box) of the NEXT tile is fetched by TMA (cp.async.bulk.tensor.2d,
 //     completion on an mbarrier) into a two-stage ring while the current tile is computed;
 //   * a conversion phase applies gofloat once per sensor pixel (smem u16 -> smem f32);
 //   * the compute phase gives every thread four consecutive pixels: 3x6 window from shared memory, demosaic,
@@ -27,13 +27,15 @@ namespace ipb {
 
 namespace {
 
-constexpr int kTW = 256;                  // tile width in pixels (64 four-pixel tasks per tile row = 2 warps)
-constexpr int kTH = 16;                   // tile height
+constexpr int kTW = 128;                  // tile width in pixels: 32 four-pixel tasks per tile row = one warp per row
+constexpr int kTH = 32;                   // tile height (TMA boxes are at most 256 elements per dimension)
 constexpr int kNT = 1024;                 // threads per CTA: one four-pixel task per thread per tile
 constexpr int kWarps = kNT / 32;
-constexpr int kTileStride = kTW + 8;      // elements per tile row: frame col tx0-4 .. tx0+kTW+3 (col tx0 at index 4)
+constexpr int kTileStride = kTW + 16;     // elements per tile row: frame col tx0-8 .. tx0+kTW+7 (col tx0 at index 8); TMA needs
+                                          // the box's first column on a 16-byte boundary (probed: tools/microbench/tma_probe.cu)
 constexpr int kTileRows = kTH + 2;        // + one halo row above and below
 constexpr int kTileElems = kTileRows * kTileStride;
+constexpr int kStageElems = (kTileElems * 2 + 127) / 128 * 64;  // raw stage padded to a 128-byte multiple
 constexpr int kMaxPatPos = 144;           // largest CFA period (12x12)
 constexpr int kQueueCap = 6 * 32;         // out-of-table queue: 2 pixels x 3 ratios per lane
 constexpr uint32_t kFull = 0xffffffffu;
@@ -59,7 +61,7 @@ struct Smem {
   float2 lut_lab[kLutEntries];
   float2 lut_out[kLutEntries];  // gamma {v, dv}; 8-bit output: {threshold, base} (Gamma8Entry)
   float tile[kTileElems];
-  alignas(128) uint16_t raw[2][kTileElems];
+  alignas(128) uint16_t raw[2][kStageElems];
   float queue[kWarps][kQueueCap];
   float spl[kMaxSplinePts][8];  // per segment: x, y, c1, c2, c3
   uint2 taps[kMaxPatPos];       // per pattern position: 9-bit tap masks of colours 0..3, 16 bits each
@@ -206,8 +208,12 @@ __device__ __forceinline__ bool in_table(float v) { return __float_as_uint(v) <=
 
 // SplineFunc::interpolate (curves.rs:126-157) from the per-segment table in shared memory.
 __device__ __forceinline__ float spline_eval_smem(const float (*spl)[8], const SplineDev &s, float val) {
-  int seg = 0;
-  for (int j = 1; j < s.nseg; j++) seg = (val >= s.x[j]) ? j : seg;
+  // last knot <= val among x[1..nseg): the common curves have one or two interior knots (constant-bank compares)
+  int seg = (val >= s.x[1]) ? 1 : 0;  // with nseg == 1, x[1] is the last point and the end clamp below wins
+  if (s.nseg > 2) {
+    seg = (val >= s.x[2]) ? 2 : seg;
+    for (int j = 3; j < s.nseg; j++) seg = (val >= s.x[j]) ? j : seg;
+  }
   const float4 c = *reinterpret_cast<const float4 *>(spl[seg]);
   const float c3 = spl[seg][4];
   float diff = val - c.x;
@@ -317,6 +323,15 @@ __device__ __forceinline__ void chain_pair(const ColorParams &P, const Smem &sm,
   }
 }
 
+// one thread: arm the stage's barrier with the box size and start the bulk tensor copy of tile (txi, tyi)
+__device__ __forceinline__ void issue_tile(const FullParams &p, const CUtensorMap *tmap, uint32_t raw_stage,
+                                           uint32_t bar, int txi, int tyi) {
+  const int x = txi * kTW - 8 + p.crop_x;  // multiple of 8 samples: the launcher checks crop_x % 8 == 0
+  const int y = p.out_row0 + tyi * kTH - 1 + p.crop_y - p.src_row0;
+  mbar_expect_tx(bar, kTileElems * (uint32_t)sizeof(uint16_t));
+  tma_load_2d(raw_stage, tmap, x, y, bar);
+}
+
 // ---------------------------------------------------------------------------------------- full resolution
 
 template <int OUT, bool BAYER>
@@ -328,22 +343,16 @@ k_fused_full(const __grid_constant__ FullParams p, const __grid_constant__ CfaDe
   const int tid = threadIdx.x;
   const int ntiles = p.tiles_x * p.tiles_y;
   const uint32_t bar0 = smem_u32(&sm.mbar[0]);
-  constexpr uint32_t kStageBytes = kTileElems * sizeof(uint16_t);
 
-  auto issue_tile = [&](int t, int stage) {  // one thread: arm the stage's barrier and start the bulk tensor copy
-    const int tyi = t / p.tiles_x, txi = t - tyi * p.tiles_x;
-    const int x = txi * kTW - 4 + p.crop_x;
-    const int y = p.out_row0 + tyi * kTH - 1 + p.crop_y - p.src_row0;
-    mbar_expect_tx(bar0 + 8 * stage, kStageBytes);
-    tma_load_2d(smem_u32(sm.raw[stage]), &tmap, x, y, bar0 + 8 * stage);
-  };
+  int tyi = (int)blockIdx.x / p.tiles_x, txi = (int)blockIdx.x - tyi * p.tiles_x;
+  const int step_y = (int)gridDim.x / p.tiles_x, step_x = (int)gridDim.x - step_y * p.tiles_x;
 
   if (p.use_tma && tid == 0) {
     mbar_init(bar0, 1);
     mbar_init(bar0 + 8, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    if ((int)blockIdx.x < ntiles) issue_tile(blockIdx.x, 0);
+    if ((int)blockIdx.x < ntiles) issue_tile(p, &tmap, smem_u32(sm.raw[0]), bar0, txi, tyi);
   }
   load_luts(sm.lut_lab, sm.lut_out, p.lut_lab, p.lut_out);
   build_taps(sm, cfa, p.pw, p.ph);
@@ -360,13 +369,15 @@ k_fused_full(const __grid_constant__ FullParams p, const __grid_constant__ CfaDe
 
   int it = 0;
   for (int t = blockIdx.x; t < ntiles; t += gridDim.x, it++) {
-    const int tyi = t / p.tiles_x, txi = t - tyi * p.tiles_x;
     const int ty0 = p.out_row0 + tyi * kTH, tx0 = txi * kTW;
+    txi += step_x; tyi += step_y;
+    if (txi >= p.tiles_x) { txi -= p.tiles_x; tyi++; }
     const int stage = it & 1;
     __syncthreads();  // previous tile fully consumed (and, first time round, tables and barriers ready)
 
     if (p.use_tma) {
-      if (tid == 0 && t + (int)gridDim.x < ntiles) issue_tile(t + gridDim.x, stage ^ 1);  // prefetch the next tile
+      if (tid == 0 && t + (int)gridDim.x < ntiles)  // prefetch the next tile
+        issue_tile(p, &tmap, smem_u32(sm.raw[stage ^ 1]), bar0 + 8 * (stage ^ 1), txi, tyi);
       mbar_wait(bar0 + 8 * stage, (it >> 1) & 1);
       // ---- gofloat once per sensor pixel: eight u16 -> eight f32 per thread
       const uint16_t *rs = sm.raw[stage];
@@ -396,7 +407,7 @@ k_fused_full(const __grid_constant__ FullParams p, const __grid_constant__ CfaDe
             v = golevel((float)rawv, p.black, p.range, p.range_rc, p.exact_rc);
           }
         }
-        sm.tile[r * kTileStride + c + 3] = v;
+        sm.tile[r * kTileStride + c + 7] = v;
       }
     }
     __syncthreads();
@@ -412,7 +423,7 @@ k_fused_full(const __grid_constant__ FullParams p, const __grid_constant__ CfaDe
 
       // 3 x 6 window: rows y-1..y+1, cols x0-1..x0+4
       float w[3][6];
-      const float *tp = sm.tile + r * kTileStride + 4 * q + 3;
+      const float *tp = sm.tile + r * kTileStride + 4 * q + 7;
 #pragma unroll
       for (int k = 0; k < 3; k++) {
         const float4 mid = *reinterpret_cast<const float4 *>(tp + k * kTileStride + 1);
@@ -703,7 +714,7 @@ cudaError_t launch_fused_full(cudaStream_t s, const FusedArgs &a, const CfaDev &
   p.pw = cfa.width; p.ph = cfa.height;
   CUtensorMap tmap;
   memset(&tmap, 0, sizeof(tmap));
-  p.use_tma = (a.use_tma && make_raw_tmap(&tmap, a.raw, a.raw_pitch, a.raw_pitch, a.src_rows)) ? 1 : 0;
+  p.use_tma = (a.use_tma && (a.crop_x % 8) == 0 && make_raw_tmap(&tmap, a.raw, a.raw_pitch, a.raw_pitch, a.src_rows)) ? 1 : 0;
   const bool bayer = is_rgb_bayer(cfa);
   const int ntiles = p.tiles_x * p.tiles_y;
   const int grid = ntiles < sm_count ? ntiles : sm_count;
