@@ -37,7 +37,7 @@ constexpr int kTileRows = kTH + 2;        // + one halo row above and below
 constexpr int kTileElems = kTileRows * kTileStride;
 constexpr int kStageElems = (kTileElems * 2 + 127) / 128 * 64;  // raw stage padded to a 128-byte multiple
 constexpr int kMaxPatPos = 144;           // largest CFA period (12x12)
-constexpr int kQueueCap = 6 * 32;         // out-of-table queue: 2 pixels x 3 ratios per lane
+constexpr int kQueueCap = 12 * 32;        // out-of-table queue: 4 pixels x 3 ratios per lane
 constexpr uint32_t kFull = 0xffffffffu;
 
 struct FullParams {
@@ -190,21 +190,34 @@ __device__ __forceinline__ void store_px4_bytes(void *out, size_t pix_index, int
 }
 
 // ---------------------------------------------------------------- colour chain on a pixel pair
+// The pair (pixel j, pixel j+1) of a thread's four pixels travels through to_lab, basecurve, from_lab and gamma
+// as the two halves of packed f32x2 registers (FMUL2 / FFMA2): same IEEE results as the scalar code of
+// ipb_device.cuh with half the issue slots for the arithmetic.  Table look-ups, min/max and selects are per half.
 
-// The fast side of XYZ_LAB_TRANSFORM.lookup for any bit pattern: in-table values take the exact lerp, anything else
-// reads a masked (valid) entry whose result the caller replaces with lab_f_slow().
-__device__ __forceinline__ float lab_lerp_masked(uint32_t lut_base, float val) {
-  float pos = val * kLutMax;
-  float tf = __fadd_rd(pos, 8388608.0f);
-  float base = tf - 8388608.0f;
-  float a = pos - base;
-  uint32_t off = (__float_as_uint(tf) << 3) & 0xfff8u;
+// true when lookup() takes the table branch with a key the masked lerp computes correctly: +0.0 <= v <= 1.0
+__device__ __forceinline__ bool in_table(float v) { return __float_as_uint(v) <= 0x3f800000u; }
+
+struct LerpIdx {
+  F2 a;   // pos - trunc(pos)
+  F2 tf;  // 2^23 + floor(pos): the key sits in the low mantissa bits
+};
+// index part of TransformLookup::lookup for both halves: pos = v*max; key = trunc(pos); a = pos - trunc(pos)
+__device__ __forceinline__ LerpIdx lerp_index(const PkAdd &pk, F2 v) {
+  LerpIdx r;
+  const F2 pos = pk_mul(v, kLutMax);
+  r.tf = pk.add_rm(pos, 8388608.0f);
+  const F2 base = pk.add(r.tf, -8388608.0f);
+  r.a = pk.sub(pos, base);
+  return r;
+}
+// table part: v1 + a*(v2 - v1) from the {v1, v2 - v1} entry; the key is masked so that any bit pattern reads a valid
+// entry (values outside the table get their result from lab_f_slow() instead)
+__device__ __forceinline__ float lerp_fetch(uint32_t lut_base, float tf, float a) {
+  const uint32_t off = (__float_as_uint(tf) << 3) & 0xfff8u;
   float2 e;
   asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(e.x), "=f"(e.y) : "r"(lut_base + off));
   return e.x + a * e.y;
 }
-// true when lookup() takes the table branch with a key the masked lerp computes correctly: +0.0 <= v <= 1.0
-__device__ __forceinline__ bool in_table(float v) { return __float_as_uint(v) <= 0x3f800000u; }
 
 // SplineFunc::interpolate (curves.rs:126-157) from the per-segment table in shared memory.
 __device__ __forceinline__ float spline_eval_smem(const float (*spl)[8], const SplineDev &s, float val) {
@@ -218,108 +231,144 @@ __device__ __forceinline__ float spline_eval_smem(const float (*spl)[8], const S
   const float c3 = spl[seg][4];
   float diff = val - c.x;
   float res = c.y + c.z * diff + c.w * diff * diff + c3 * diff * diff * diff;
-  const int last = s.n - 1;
-  res = (val <= s.x[0]) ? s.y[0] : res;
-  res = (val >= s.x[last]) ? s.y[last] : res;
-  res = (val != val) ? s.y[(s.nseg - 1) / 2] : res;
+  res = (val <= s.x_first) ? s.y_first : res;
+  res = (val >= s.x_last) ? s.y_last : res;
+  res = (val != val) ? s.y_nan : res;
   return res;
 }
 
 // 8-bit output of one channel: output8bit(apply_srgb_gamma(clamp(v))) through the threshold table
-__device__ __forceinline__ uint32_t gamma8(uint32_t lut_base, float v) {
-  float vc = fminf(fmaxf(v, 0.0f), 1.0f);
-  float pos = vc * kLutMax;
-  float tf = __fadd_rd(pos, 8388608.0f);
-  uint32_t off = (__float_as_uint(tf) << 3) & 0xfff8u;
+__device__ __forceinline__ uint32_t gamma8_fetch(uint32_t lut_base, float tf, float vc) {
+  const uint32_t off = (__float_as_uint(tf) << 3) & 0xfff8u;
   float thr;
   uint32_t base;
   asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=f"(thr), "=r"(base) : "r"(lut_base + off));
   return base + (vc >= thr ? 1u : 0u);
 }
+__device__ __forceinline__ F2 clamp01(F2 v) {
+  return F2{fminf(fmaxf(v.x, 0.0f), 1.0f), fminf(fmaxf(v.y, 0.0f), 1.0f)};
+}
 
-// to_lab + basecurve + from_lab (+ gamma) for two pixels; out-of-table XYZ ratios go through the warp queue.
-// All 32 lanes of the warp must call this together.
+// camera_to_lab up to the XYZ ratios (color_conversions.rs:42-55,156-160) for two pixels
+__device__ __forceinline__ void xyz_ratios_pair(const ColorParams &P, const PkAdd &pk, const float r[2], const float g[2],
+                                                const float b[2], const float e[2], F2 &xr, F2 &yr, F2 &zr) {
+  // white balance, clip, 3x4 matrix with left-to-right sums
+  F2 cr = pk_mul(F2{r[0], r[1]}, P.mul[0]);
+  F2 cg = pk_mul(F2{g[0], g[1]}, P.mul[1]);
+  F2 cb = pk_mul(F2{b[0], b[1]}, P.mul[2]);
+  cr = F2{fminf(cr.x, 1.0f), fminf(cr.y, 1.0f)};
+  cg = F2{fminf(cg.x, 1.0f), fminf(cg.y, 1.0f)};
+  cb = F2{fminf(cb.x, 1.0f), fminf(cb.y, 1.0f)};
+  F2 x = pk.add(pk.add(pk_mul(cr, P.cm[0]), pk_mul(cg, P.cm[1])), pk_mul(cb, P.cm[2]));
+  F2 y = pk.add(pk.add(pk_mul(cr, P.cm[4]), pk_mul(cg, P.cm[5])), pk_mul(cb, P.cm[6]));
+  F2 z = pk.add(pk.add(pk_mul(cr, P.cm[8]), pk_mul(cg, P.cm[9])), pk_mul(cb, P.cm[10]));
+  if (P.use_e) {
+    F2 ce = pk_mul(F2{e[0], e[1]}, P.mul[3]);
+    ce = F2{fminf(ce.x, 1.0f), fminf(ce.y, 1.0f)};
+    x = pk.add(x, pk_mul(ce, P.cm[3]));
+    y = pk.add(y, pk_mul(ce, P.cm[7]));
+    z = pk.add(z, pk_mul(ce, P.cm[11]));
+  }
+  xr = IPB_PK_DIVC(x, 0.95047f);
+  yr = y;  // y / 1.0
+  zr = IPB_PK_DIVC(z, 1.08883f);
+}
+
+// XYZ_LAB_TRANSFORM.lookup of the four values of one channel (pixels 0..3 of the task): table lerp for every value,
+// then the out-of-table ones (the reference's analytic branch) join the warp queue.  Returns the new queue length.
+// slot[j] is where value j was queued (only meaningful when oor bit j is set).
+__device__ __forceinline__ int lab_lookup4(const PkAdd &pk, uint32_t lab_base, float *queue, uint32_t lt, int n, F2 va,
+                                           F2 vb, float f[4], int slot[4], uint32_t &oormask, int shift) {
+  const LerpIdx ia = lerp_index(pk, va), ib = lerp_index(pk, vb);
+  f[0] = lerp_fetch(lab_base, ia.tf.x, ia.a.x);
+  f[1] = lerp_fetch(lab_base, ia.tf.y, ia.a.y);
+  f[2] = lerp_fetch(lab_base, ib.tf.x, ib.a.x);
+  f[3] = lerp_fetch(lab_base, ib.tf.y, ib.a.y);
+  const float v[4] = {va.x, va.y, vb.x, vb.y};
+  bool oor[4];
+#pragma unroll
+  for (int j = 0; j < 4; j++) oor[j] = !in_table(v[j]);
+#pragma unroll
+  for (int j = 0; j < 4; j++) slot[j] = 0;
+  if (__any_sync(kFull, oor[0] | oor[1] | oor[2] | oor[3])) {  // whole channel in table across the warp: common
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const uint32_t bal = __ballot_sync(kFull, oor[j]);
+      if (bal != 0u) {
+        slot[j] = n + __popc(bal & lt);
+        if (oor[j]) { queue[slot[j]] = v[j]; oormask |= 1u << (shift + j); }
+        n += __popc(bal);
+      }
+    }
+  }
+  return n;
+}
+
+// Lab from the transfer-function values, basecurve, from_lab (+ gamma) for two pixels
 template <int OUT>
-__device__ __forceinline__ void chain_pair(const ColorParams &P, const Smem &sm, float *queue, uint32_t lab_base,
-                                           uint32_t out_base, bool g8, const float r[2], const float g[2], const float b[2],
-                                           const float e[2], float orr[2], float og[2], float ob[2], uint32_t q8[6]) {
-  const int lane = threadIdx.x & 31;
-  float xr[2], yr[2], zr[2];
-#pragma unroll
-  for (int j = 0; j < 2; j++) {
-    float cr = fminf(r[j] * P.mul[0], 1.0f);
-    float cg = fminf(g[j] * P.mul[1], 1.0f);
-    float cb = fminf(b[j] * P.mul[2], 1.0f);
-    float x = cr * P.cm[0] + cg * P.cm[1] + cb * P.cm[2];
-    float y = cr * P.cm[4] + cg * P.cm[5] + cb * P.cm[6];
-    float z = cr * P.cm[8] + cg * P.cm[9] + cb * P.cm[10];
-    if (P.use_e) {
-      float ce = fminf(e[j] * P.mul[3], 1.0f);
-      x = x + ce * P.cm[3];
-      y = y + ce * P.cm[7];
-      z = z + ce * P.cm[11];
-    }
-    xr[j] = IPB_DIVC(x, 0.95047f);
-    yr[j] = y;  // y / 1.0
-    zr[j] = IPB_DIVC(z, 1.08883f);
+__device__ __forceinline__ void lab_to_output_pair(const ColorParams &P, const PkAdd &pk, const Smem &sm,
+                                                   uint32_t out_base, bool g8, F2 fx, F2 fy, F2 fz, float orr[2],
+                                                   float og[2], float ob[2], uint32_t q8[6]) {
+  F2 l = pk.add(pk_mul(fy, 116.0f), -16.0f);
+  F2 a = pk_mul(pk.sub(fx, fy), 500.0f);
+  F2 bb = pk_mul(pk.sub(fy, fz), 200.0f);
+  l = IPB_PK_DIVC(l, 100.0f);
+  a = IPB_PK_DIVC(pk.add(a, 127.0f), 255.0f);
+  bb = IPB_PK_DIVC(pk.add(bb, 127.0f), 255.0f);
+  // ---- basecurve on L (curves.rs:45-47)
+  if (P.sp.n > 0) {
+    l.x = spline_eval_smem(sm.spl, P.sp, l.x);
+    l.y = spline_eval_smem(sm.spl, P.sp, l.y);
   }
-  float f[6] = {lab_lerp_masked(lab_base, xr[0]), lab_lerp_masked(lab_base, yr[0]), lab_lerp_masked(lab_base, zr[0]),
-                lab_lerp_masked(lab_base, xr[1]), lab_lerp_masked(lab_base, yr[1]), lab_lerp_masked(lab_base, zr[1])};
-  const float v[6] = {xr[0], yr[0], zr[0], xr[1], yr[1], zr[1]};
-  bool oor[6];
-  bool any = false;
-#pragma unroll
-  for (int k = 0; k < 6; k++) { oor[k] = !in_table(v[k]); any |= oor[k]; }
-  if (__any_sync(kFull, any)) {
-    // compact the out-of-table values of the whole warp into the queue, evaluate densely, scatter back
-    const uint32_t lt = (1u << lane) - 1u;
-    int n = 0;
-    int slot[6];
-#pragma unroll
-    for (int k = 0; k < 6; k++) {
-      const uint32_t bal = __ballot_sync(kFull, oor[k]);
-      slot[k] = n + __popc(bal & lt);
-      if (oor[k]) queue[slot[k]] = v[k];
-      n += __popc(bal);
+  // ---- lab_to_xyz + lab_to_rgb (color_conversions.rs:58-65,172-191)
+  const float ee = 216.0f / 24389.0f;
+  const float kk = 24389.0f / 27.0f;
+  const F2 cl = pk_mul(l, 100.0f);
+  const F2 ca = pk.add(pk_mul(a, 255.0f), -127.0f);
+  const F2 cbb = pk.add(pk_mul(bb, 255.0f), -127.0f);
+  const F2 ffy = IPB_PK_DIVC(pk.add(cl, 16.0f), 116.0f);
+  const F2 ffx = pk.add(IPB_PK_DIVC(ca, 500.0f), ffy);
+  const F2 ffz = pk.sub(ffy, IPB_PK_DIVC(cbb, 200.0f));
+  const F2 fx3 = pk_mul(pk_mul(ffx, ffx), ffx);
+  const F2 fy3 = pk_mul(pk_mul(ffy, ffy), ffy);
+  const F2 fz3 = pk_mul(pk_mul(ffz, ffz), ffz);
+  const F2 xlin = IPB_PK_DIVC(pk.add(pk_mul(ffx, 116.0f), -16.0f), kk);
+  const F2 ylin = IPB_PK_DIVC(cl, kk);
+  const F2 zlin = IPB_PK_DIVC(pk.add(pk_mul(ffz, 116.0f), -16.0f), kk);
+  const float ke = kk * ee;
+  const F2 xr2{fx3.x > ee ? fx3.x : xlin.x, fx3.y > ee ? fx3.y : xlin.y};
+  const F2 yr2{cl.x > ke ? fy3.x : ylin.x, cl.y > ke ? fy3.y : ylin.y};
+  const F2 zr2{fz3.x > ee ? fz3.x : zlin.x, fz3.y > ee ? fz3.y : zlin.y};
+  const F2 X = pk_mul(xr2, 0.95047f);
+  const F2 Y = yr2;  // * 1.0
+  const F2 Z = pk_mul(zr2, 1.08883f);
+  F2 rr = pk.add(pk.add(pk_mul(X, P.rgbm[0]), pk_mul(Y, P.rgbm[1])), pk_mul(Z, P.rgbm[2]));
+  F2 gg = pk.add(pk.add(pk_mul(X, P.rgbm[3]), pk_mul(Y, P.rgbm[4])), pk_mul(Z, P.rgbm[5]));
+  F2 bl = pk.add(pk.add(pk_mul(X, P.rgbm[6]), pk_mul(Y, P.rgbm[7])), pk_mul(Z, P.rgbm[8]));
+  // ---- gamma (gamma.rs:21) and quantisation
+  if (OUT == kOutU8 && g8) {
+    const F2 vr = clamp01(rr), vg = clamp01(gg), vb = clamp01(bl);
+    const F2 tr = pk.add_rm(pk_mul(vr, kLutMax), 8388608.0f);
+    const F2 tg = pk.add_rm(pk_mul(vg, kLutMax), 8388608.0f);
+    const F2 tb = pk.add_rm(pk_mul(vb, kLutMax), 8388608.0f);
+    q8[0] = gamma8_fetch(out_base, tr.x, vr.x);
+    q8[1] = gamma8_fetch(out_base, tg.x, vg.x);
+    q8[2] = gamma8_fetch(out_base, tb.x, vb.x);
+    q8[3] = gamma8_fetch(out_base, tr.y, vr.y);
+    q8[4] = gamma8_fetch(out_base, tg.y, vg.y);
+    q8[5] = gamma8_fetch(out_base, tb.y, vb.y);
+  } else {
+    if (!P.linear) {
+      const LerpIdx jr = lerp_index(pk, clamp01(rr)), jg = lerp_index(pk, clamp01(gg)), jb = lerp_index(pk, clamp01(bl));
+      rr = F2{lerp_fetch(out_base, jr.tf.x, jr.a.x), lerp_fetch(out_base, jr.tf.y, jr.a.y)};
+      gg = F2{lerp_fetch(out_base, jg.tf.x, jg.a.x), lerp_fetch(out_base, jg.tf.y, jg.a.y)};
+      bl = F2{lerp_fetch(out_base, jb.tf.x, jb.a.x), lerp_fetch(out_base, jb.tf.y, jb.a.y)};
     }
-    __syncwarp();
-    for (int i = lane; i < n; i += 32) queue[i] = lab_f_slow(queue[i]);
-    __syncwarp();
-#pragma unroll
-    for (int k = 0; k < 6; k++)
-      if (oor[k]) f[k] = queue[slot[k]];
-    __syncwarp();
-  }
-#pragma unroll
-  for (int j = 0; j < 2; j++) {
-    const float fx = f[3 * j], fy = f[3 * j + 1], fz = f[3 * j + 2];
-    float l = 116.0f * fy - 16.0f;
-    float a = 500.0f * (fx - fy);
-    float bb = 200.0f * (fy - fz);
-    l = IPB_DIVC(l, 100.0f);
-    a = IPB_DIVC(a + 127.0f, 255.0f);
-    bb = IPB_DIVC(bb + 127.0f, 255.0f);
-    if (P.sp.n > 0) l = spline_eval_smem(sm.spl, P.sp, l);
-    float rr, gg, bl;
-    lab_to_rgb(P, l, a, bb, rr, gg, bl);
-    if (OUT == kOutU8 && g8) {
-      q8[3 * j] = gamma8(out_base, rr);
-      q8[3 * j + 1] = gamma8(out_base, gg);
-      q8[3 * j + 2] = gamma8(out_base, bl);
-    } else {
-      if (!P.linear) {
-        const LutShared gam{out_base};
-        rr = gamma_elem(gam, rr);
-        gg = gamma_elem(gam, gg);
-        bl = gamma_elem(gam, bl);
-      }
-      if (OUT == kOutU8) {
-        q8[3 * j] = output8bit(rr);
-        q8[3 * j + 1] = output8bit(gg);
-        q8[3 * j + 2] = output8bit(bl);
-      }
-      orr[j] = rr; og[j] = gg; ob[j] = bl;
+    if (OUT == kOutU8) {
+      q8[0] = output8bit(rr.x); q8[1] = output8bit(gg.x); q8[2] = output8bit(bl.x);
+      q8[3] = output8bit(rr.y); q8[4] = output8bit(gg.y); q8[5] = output8bit(bl.y);
     }
+    orr[0] = rr.x; orr[1] = rr.y; og[0] = gg.x; og[1] = gg.y; ob[0] = bl.x; ob[1] = bl.y;
   }
 }
 
@@ -362,6 +411,7 @@ k_fused_full(const __grid_constant__ FullParams p, const __grid_constant__ CfaDe
   }
   const uint32_t lab_base = smem_u32(sm.lut_lab), out_base = smem_u32(sm.lut_out);
   float *queue = sm.queue[tid >> 5];
+  const int lane = tid & 31;
   const bool g8 = OUT == kOutU8 && p.gamma8 != 0;
 
   // Bayer phase (cropped-frame coordinates): colour of the pixel at (row&1, col&1)
@@ -484,8 +534,35 @@ k_fused_full(const __grid_constant__ FullParams p, const __grid_constant__ CfaDe
 
       float orr[4], og[4], ob[4];
       uint32_t q8[12];
-      chain_pair<OUT>(P, sm, queue, lab_base, out_base, g8, cr, cg, cb, ce, orr, og, ob, q8);
-      chain_pair<OUT>(P, sm, queue, lab_base, out_base, g8, cr + 2, cg + 2, cb + 2, ce + 2, orr + 2, og + 2, ob + 2, q8 + 6);
+      // ---- colour chain: pixels (0,1) and (2,3) as packed pairs; one queue flush for the task's 12 table look-ups
+      const PkAdd pk{P.one, P.mone};
+      F2 xa, ya, za, xb, yb, zb;
+      xyz_ratios_pair(P, pk, cr, cg, cb, ce, xa, ya, za);
+      xyz_ratios_pair(P, pk, cr + 2, cg + 2, cb + 2, ce + 2, xb, yb, zb);
+      float fxs[4], fys[4], fzs[4];
+      int sx[4], sy[4], sz[4];
+      uint32_t oormask = 0u;
+      const uint32_t lt = (1u << lane) - 1u;
+      int nq = 0;
+      nq = lab_lookup4(pk, lab_base, queue, lt, nq, xa, xb, fxs, sx, oormask, 0);
+      nq = lab_lookup4(pk, lab_base, queue, lt, nq, ya, yb, fys, sy, oormask, 4);
+      nq = lab_lookup4(pk, lab_base, queue, lt, nq, za, zb, fzs, sz, oormask, 8);
+      if (nq > 0) {  // warp-uniform
+        __syncwarp();
+        for (int i = lane; i < nq; i += 32) queue[i] = lab_f_slow(queue[i]);
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          if (oormask & (1u << j)) fxs[j] = queue[sx[j]];
+          if (oormask & (1u << (4 + j))) fys[j] = queue[sy[j]];
+          if (oormask & (1u << (8 + j))) fzs[j] = queue[sz[j]];
+        }
+        __syncwarp();
+      }
+      lab_to_output_pair<OUT>(P, pk, sm, out_base, g8, F2{fxs[0], fxs[1]}, F2{fys[0], fys[1]}, F2{fzs[0], fzs[1]}, orr, og,
+                              ob, q8);
+      lab_to_output_pair<OUT>(P, pk, sm, out_base, g8, F2{fxs[2], fxs[3]}, F2{fys[2], fys[3]}, F2{fzs[2], fzs[3]}, orr + 2,
+                              og + 2, ob + 2, q8 + 6);
       if (live) {
         const size_t pix = (size_t)(y - p.out_row0) * p.width + x0;
         if (OUT == kOutU8) store_px4_bytes(p.out, pix, npx, q8);
@@ -575,7 +652,7 @@ k_fused_scaled(const __grid_constant__ ScaledParams p, const __grid_constant__ C
 #pragma unroll
     for (int k = 0; k < 4; k++) px[k] = counts[k] > 0.0f ? __fdiv_rn(sums[k], counts[k]) : 0.0f;
     float r[4] = {0.f, 0.f, 0.f, 0.f}, g[4] = {0.f, 0.f, 0.f, 0.f}, b[4] = {0.f, 0.f, 0.f, 0.f};
-    color_chain(P, lab, gam, px[0], px[1], px[2], px[3], r[0], g[0], b[0]);
+    color_chain<true>(P, lab, gam, px[0], px[1], px[2], px[3], r[0], g[0], b[0]);
     store_px4<OUT>(p.out, (size_t)(idx), 1, r, g, b);
   }
 }

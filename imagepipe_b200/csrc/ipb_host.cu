@@ -242,6 +242,9 @@ bool build_spline(const ipb_basecurve *op, SplineDev *s) {
   }
   s->n = np;
   s->nseg = nc1 - 1;
+  s->x_first = s->x[0]; s->y_first = s->y[0];
+  s->x_last = s->x[np - 1]; s->y_last = s->y[np - 1];
+  s->y_nan = s->y[(s->nseg - 1) / 2];
   return true;
 }
 
@@ -1149,6 +1152,35 @@ struct FusedPlan {
   size_t out_width = 0, out_height = 0;                  // demosaic output == fused output
 };
 
+
+// The fused kernels divide by the colour chain's constants with a 3-instruction reciprocal form that equals IEEE
+// division only while the dividend and the quotient are finite and normal (or zero) — tools/verify_constdiv.c.
+// These bounds keep every dividend of the chain in that range for any u16 sample: levels within the u16 range and
+// at least one code value apart, white-balance multipliers and matrix entries zero or between 2^-20 and 64 in
+// magnitude.  Real camera metadata is far inside them; anything else runs op by op with IEEE division.
+static bool fused_params_bounded(const ipb_pipeline *p) {
+  const ipb_gofloat &g = p->ops.gofloat;
+  const float black = g.blacklevels[0], range = g.whitelevels[0] - g.blacklevels[0];
+  if (!std::isfinite(black) || !std::isfinite(range) || fabsf(black) > 65535.0f || !(fabsf(range) >= 1.0f) ||
+      fabsf(range) > 131072.0f)
+    return false;
+  float mul[4];
+  normalize_wbs(p->ops.tolab.wb_coeffs, mul);
+  auto ok = [](float v) { return std::isfinite(v) && (v == 0.0f || (fabsf(v) >= 9.5367431640625e-07f && fabsf(v) <= 64.0f)); };
+  for (int i = 0; i < 4; i++)
+    if (!ok(mul[i])) return false;
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 4; j++)
+      if (!ok(p->ops.tolab.cam_to_xyz_normalized[i][j])) return false;
+  const ipb_basecurve &c = p->ops.basecurve;
+  if (!std::isfinite(c.exposure) || fabsf(c.exposure) > 16.0f) return false;
+  for (size_t i = 0; i < c.npoints && i < IPB_MAX_CURVE_POINTS; i++)
+    if (!std::isfinite(c.points[i][0]) || !std::isfinite(c.points[i][1]) || fabsf(c.points[i][0]) > 1024.0f ||
+        fabsf(c.points[i][1]) > 1024.0f)
+      return false;
+  return true;
+}
+
 static int plan_fused(ipb_pipeline *p, FusedPlan *plan) {
   plan->mode = kNotFused;
   if (!p->fused) return IPB_OK;
@@ -1157,6 +1189,7 @@ static int plan_fused(ipb_pipeline *p, FusedPlan *plan) {
   if (!rc_noop(&p->ops.rotatecrop)) return IPB_OK;
   if (parse_cfa(p->ops.demosaic.cfa, &plan->cfa) != IPB_OK || plan->cfa.width == 0) return IPB_OK;
   if (p->ops.basecurve.npoints > IPB_MAX_CURVE_POINTS) return IPB_OK;
+  if (!fused_params_bounded(p)) return IPB_OK;
   if (img.width >= (1u << 30) || img.height >= (1u << 30)) return IPB_OK;
   size_t xywh[4];
   size_image(&p->ops.gofloat, img.width, img.height, xywh);
@@ -1186,6 +1219,8 @@ static int fill_color_params(ipb_pipeline *p, const FusedPlan &plan, ColorParams
   P->use_e = (has_e || !std::isfinite(P->cm[3]) || !std::isfinite(P->cm[7]) || !std::isfinite(P->cm[11]) ||
               !std::isfinite(P->mul[3])) ? 1 : 0;
   P->linear = p->settings.linear ? 1 : 0;
+  P->one = 1.0f;
+  P->mone = -1.0f;
   if (!build_spline(&p->ops.basecurve, &P->sp)) return fail(p->ctx, IPB_ERR_INVALID, "basecurve: degenerate curve");
   return IPB_OK;
 }

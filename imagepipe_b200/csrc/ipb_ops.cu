@@ -70,13 +70,13 @@ __global__ void k_gofloat_other(const T *__restrict__ src, size_t owidth, size_t
   float4 o;
   if (sizeof(T) == 1) {
     LutGlobal lut{lut_rev};
-    o.x = lut_lerp(lut, IPB_DIVC((float)p[0], 255.0f));
-    o.y = lut_lerp(lut, IPB_DIVC((float)p[1], 255.0f));
-    o.z = lut_lerp(lut, IPB_DIVC((float)p[2], 255.0f));
+    o.x = lut_lerp(lut, __fdiv_rn((float)p[0], 255.0f));
+    o.y = lut_lerp(lut, __fdiv_rn((float)p[1], 255.0f));
+    o.z = lut_lerp(lut, __fdiv_rn((float)p[2], 255.0f));
   } else {
-    o.x = IPB_DIVC((float)p[0], 65535.0f);
-    o.y = IPB_DIVC((float)p[1], 65535.0f);
-    o.z = IPB_DIVC((float)p[2], 65535.0f);
+    o.x = __fdiv_rn((float)p[0], 65535.0f);
+    o.y = __fdiv_rn((float)p[1], 65535.0f);
+    o.z = __fdiv_rn((float)p[2], 65535.0f);
   }
   o.w = 0.0f;
   reinterpret_cast<float4 *>(out)[idx] = o;
@@ -260,7 +260,7 @@ __global__ void k_tolab(const __grid_constant__ ColorParams P, const float2 *__r
   float4 p = reinterpret_cast<const float4 *>(in)[idx];
   LutGlobal lab{lut_lab};
   float l, a, b;
-  camera_to_lab(P, lab, p.x, p.y, p.z, p.w, l, a, b);
+  camera_to_lab<false>(P, lab, p.x, p.y, p.z, p.w, l, a, b);
   out[idx * 3 + 0] = l;
   out[idx * 3 + 1] = a;
   out[idx * 3 + 2] = b;
@@ -306,7 +306,7 @@ __global__ void k_fromlab(const __grid_constant__ ColorParams P, const float *__
   size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= npix) return;
   float r, g, b;
-  lab_to_rgb(P, in[idx * 3 + 0], in[idx * 3 + 1], in[idx * 3 + 2], r, g, b);
+  lab_to_rgb<false>(P, in[idx * 3 + 0], in[idx * 3 + 1], in[idx * 3 + 2], r, g, b);
   out[idx * 3 + 0] = r;
   out[idx * 3 + 1] = g;
   out[idx * 3 + 2] = b;

@@ -212,3 +212,16 @@ def test_natural_frame_mostly_in_table(ip, orc, ctx):
         assert_bit_exact(pg.output_8bit().to_numpy(), orc.pipeline_output_8bit(po), "natural/clipped u8")
         po, pg = both(ip, orc, ctx, data, common.raw_params())
         assert_bit_exact(pg.run().to_numpy(), orc.pipeline_run(po), "natural/clipped f32")
+
+
+@pytest.mark.parametrize("matrix_scale,wb", [(1000.0, common.WB), (1.0, [1e-9, 1.0, 1.5, 1.0]), (3e37, common.WB)])
+def test_unbounded_parameters_run_op_by_op(ip, orc, ctx, matrix_scale, wb):
+    """Outside the parameter bounds that make the fused kernels' constant divisions exact (ipb_host.cu
+    fused_params_bounded) Pipeline::run must fall back to one kernel per op (IEEE division) and still match."""
+    data = common.synth_cfa(301, 67, seed=71)
+    params = common.raw_params(matrix=common.CAM_TO_XYZ * np.float32(matrix_scale), wb=wb)
+    po, pg = both(ip, orc, ctx, data, params)
+    n0 = ctx.launch_count
+    got = pg.run().to_numpy()
+    assert ctx.launch_count - n0 >= 6
+    assert_bit_exact(got, orc.pipeline_run(po), "op-by-op fallback")

@@ -139,6 +139,27 @@ def test_tolab(ip, orc, ctx, rgbe, mono):
     assert_bit_exact(got.to_numpy(), want, "to_lab")
 
 
+@pytest.mark.parametrize("scale", [1.3, 7.0, 1000.0, 3e37])
+def test_lab_transfer_above_one(ip, orc, ctx, scale):
+    """XYZ ratios far above 1.0 take the reference's analytic branch: v.cbrt() == glibc cbrtf, which the device
+    restates (double-precision Halley step).  The matrix is scaled so the ratios cover (1, scale] (and +inf)."""
+    import ctypes as C
+    rng = np.random.default_rng(5)
+    rgbe = rng.random((37, 211, 4), dtype=np.float32)
+    rgbe[0, :8, :3] = 1.0
+    params = common.raw_params(matrix=common.CAM_TO_XYZ * np.float32(scale), wb=[1.0, 1.0, 1.0, 1.0])
+    ops = orc.Ops()
+    orc.fill_ops(ops, params)
+    ob = orc_buf(orc, rgbe, False)
+    want = run_orc(orc, orc.lib().orc_tolab_run, C.byref(ops.tolab), ob)
+    orc.lib().orc_buffer_free(ob)
+    p_ops = ip.PipelineOps()
+    common.fill_ipb_ops(p_ops, params)
+    g = ip.PipelineGlobals.mock(16, 16, ctx=ctx)
+    got = p_ops.tolab.run(g, ip.OpBuffer.from_numpy(rgbe, ctx=ctx))
+    assert_bit_exact(got.to_numpy(), want, f"to_lab x{scale}")
+
+
 @pytest.fixture(scope="module")
 def lab(orc):
     rng = np.random.default_rng(8)
