@@ -6,7 +6,8 @@
 //   k_fused_scaled  the same chain with scaled_demosaic (scaling.rs:132-145) in place of full() — the branch
 //                   OpDemosaic::run takes for scale >= 2 (Bayer) / 3 (X-Trans), demosaic.rs:47-50.
 //
-// k_fused_full is a persistent kernel: one 1024-thread CTA per SM walks 128x32-pixel tiles round-robin.
+// k_fused_full is a persistent kernel: one 1024-thread CTA per SM walks 128x32-pixel tiles round-robin, one
+// __syncthreads per tile.
 //   * the raw u16 tile (+1 px halo, 144x34 box) of the NEXT tile is fetched by TMA (cp.async.bulk.tensor.2d,
 //     completion on an mbarrier) into a two-stage ring while the current tile is computed;
 //   * a conversion phase applies gofloat once per sensor pixel (smem u16 -> smem f32);
@@ -60,13 +61,15 @@ struct FullParams {
 struct Smem {
   float2 lut_lab[kLutEntries];
   float2 lut_out[kLutEntries];  // gamma {v, dv}; 8-bit output: {threshold, base} (Gamma8Entry)
-  float tile[kTileElems];
-  alignas(128) uint16_t raw[2][kStageElems];
+  float tile[2][kTileElems];    // gofloat'ed tile, double buffered: tile t+1 is converted while tile t is computed
+  alignas(128) uint16_t raw[kStageElems];  // TMA destination: raw u16 box of the next tile
   float queue[kWarps][kQueueCap];
   float spl[kMaxSplinePts][8];  // per segment: x, y, c1, c2, c3
   uint2 taps[kMaxPatPos];       // per pattern position: 9-bit tap masks of colours 0..3, 16 bits each
-  alignas(8) unsigned long long mbar[2];
+  alignas(8) unsigned long long mbar;
+  int conv_ctr[2];              // dynamic chunk counters of the conversion phase (alternating per tile)
 };
+static_assert(sizeof(Smem) <= 232448, "Smem exceeds the 227 KB a CTA can opt in to");
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -391,17 +394,24 @@ k_fused_full(const __grid_constant__ FullParams p, const __grid_constant__ CfaDe
   Smem &sm = *reinterpret_cast<Smem *>(smem_raw);
   const int tid = threadIdx.x;
   const int ntiles = p.tiles_x * p.tiles_y;
-  const uint32_t bar0 = smem_u32(&sm.mbar[0]);
+  const uint32_t bar = smem_u32(&sm.mbar), raw_addr = smem_u32(sm.raw);
 
   int tyi = (int)blockIdx.x / p.tiles_x, txi = (int)blockIdx.x - tyi * p.tiles_x;
   const int step_y = (int)gridDim.x / p.tiles_x, step_x = (int)gridDim.x - step_y * p.tiles_x;
+  auto next_tile = [&](int &tx, int &ty) {
+    tx += step_x; ty += step_y;
+    if (tx >= p.tiles_x) { tx -= p.tiles_x; ty++; }
+  };
 
-  if (p.use_tma && tid == 0) {
-    mbar_init(bar0, 1);
-    mbar_init(bar0 + 8, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    if ((int)blockIdx.x < ntiles) issue_tile(p, &tmap, smem_u32(sm.raw[0]), bar0, txi, tyi);
+  if (tid == 0) {
+    sm.conv_ctr[0] = 0;
+    sm.conv_ctr[1] = 0;
+    if (p.use_tma) {
+      mbar_init(bar, 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      if ((int)blockIdx.x < ntiles) issue_tile(p, &tmap, raw_addr, bar, txi, tyi);
+    }
   }
   load_luts(sm.lut_lab, sm.lut_out, p.lut_lab, p.lut_out);
   build_taps(sm, cfa, p.pw, p.ph);
@@ -410,45 +420,41 @@ k_fused_full(const __grid_constant__ FullParams p, const __grid_constant__ CfaDe
     sm.spl[i][4] = P.sp.c3[i];
   }
   const uint32_t lab_base = smem_u32(sm.lut_lab), out_base = smem_u32(sm.lut_out);
-  float *queue = sm.queue[tid >> 5];
-  const int lane = tid & 31;
+  const int lane = tid & 31, warp = tid >> 5;
+  float *queue = sm.queue[warp];
   const bool g8 = OUT == kOutU8 && p.gamma8 != 0;
 
-  // Bayer phase (cropped-frame coordinates): colour of the pixel at (row&1, col&1)
-  const int c00 = cfa.pat[0], c10 = cfa.pat[48];
-
-  int it = 0;
-  for (int t = blockIdx.x; t < ntiles; t += gridDim.x, it++) {
-    const int ty0 = p.out_row0 + tyi * kTH, tx0 = txi * kTW;
-    txi += step_x; tyi += step_y;
-    if (txi >= p.tiles_x) { txi -= p.tiles_x; tyi++; }
-    const int stage = it & 1;
-    __syncthreads();  // previous tile fully consumed (and, first time round, tables and barriers ready)
-
+  // gofloat (gofloat.rs:122-130) once per sensor pixel, into tile buffer `buf`.  TMA path: the raw box is in shared
+  // memory; warps pull 32-thread chunks (eight samples per thread) from a counter so that whichever warps finish
+  // the previous tile's pixels first do the conversion.  Plain path: bounds-checked global loads, static split.
+  auto convert_tile = [&](int buf, int ctr, int ttx0, int tty0) {
+    float *tile = sm.tile[buf];
     if (p.use_tma) {
-      if (tid == 0 && t + (int)gridDim.x < ntiles)  // prefetch the next tile
-        issue_tile(p, &tmap, smem_u32(sm.raw[stage ^ 1]), bar0 + 8 * (stage ^ 1), txi, tyi);
-      mbar_wait(bar0 + 8 * stage, (it >> 1) & 1);
-      // ---- gofloat once per sensor pixel: eight u16 -> eight f32 per thread
-      const uint16_t *rs = sm.raw[stage];
-      for (int g8 = tid; g8 < kTileElems / 8; g8 += kNT) {
-        const uint4 pk = *reinterpret_cast<const uint4 *>(rs + g8 * 8);
-        const uint32_t w4[4] = {pk.x, pk.y, pk.z, pk.w};
-        float v[8];
+      constexpr int kChunks = (kTileElems / 8 + 31) / 32;
+      for (;;) {
+        int chunk = 0;
+        if (lane == 0) chunk = atomicAdd(&sm.conv_ctr[ctr], 1);
+        chunk = __shfl_sync(kFull, chunk, 0);
+        if (chunk >= kChunks) break;
+        const int g8i = chunk * 32 + lane;
+        if (g8i < kTileElems / 8) {
+          const uint4 pkd = *reinterpret_cast<const uint4 *>(sm.raw + g8i * 8);
+          const uint32_t w4[4] = {pkd.x, pkd.y, pkd.z, pkd.w};
+          float v[8];
 #pragma unroll
-        for (int k = 0; k < 4; k++) {
-          v[2 * k] = golevel((float)(w4[k] & 0xffffu), p.black, p.range, p.range_rc, p.exact_rc);
-          v[2 * k + 1] = golevel((float)(w4[k] >> 16), p.black, p.range, p.range_rc, p.exact_rc);
+          for (int k = 0; k < 4; k++) {
+            v[2 * k] = golevel((float)(w4[k] & 0xffffu), p.black, p.range, p.range_rc, p.exact_rc);
+            v[2 * k + 1] = golevel((float)(w4[k] >> 16), p.black, p.range, p.range_rc, p.exact_rc);
+          }
+          float4 *dst = reinterpret_cast<float4 *>(tile + g8i * 8);
+          dst[0] = make_float4(v[0], v[1], v[2], v[3]);
+          dst[1] = make_float4(v[4], v[5], v[6], v[7]);
         }
-        float4 *dst = reinterpret_cast<float4 *>(sm.tile + g8 * 8);
-        dst[0] = make_float4(v[0], v[1], v[2], v[3]);
-        dst[1] = make_float4(v[4], v[5], v[6], v[7]);
       }
     } else {
-      // ---- fallback staging for sources TMA cannot describe (base or pitch not 16-byte aligned)
       for (int i = tid; i < kTileRows * (kTW + 2); i += kNT) {
         const int r = i / (kTW + 2), c = i - r * (kTW + 2);
-        const int y = ty0 - 1 + r, x = tx0 - 1 + c;
+        const int y = tty0 - 1 + r, x = ttx0 - 1 + c;
         float v = 0.0f;
         if (y >= 0 && y < p.height && x >= 0 && x < p.width) {
           const int sr = y + p.crop_y - p.src_row0;
@@ -457,10 +463,32 @@ k_fused_full(const __grid_constant__ FullParams p, const __grid_constant__ CfaDe
             v = golevel((float)rawv, p.black, p.range, p.range_rc, p.exact_rc);
           }
         }
-        sm.tile[r * kTileStride + c + 7] = v;
+        tile[r * kTileStride + c + 7] = v;
       }
     }
-    __syncthreads();
+  };
+
+  // Bayer phase (cropped-frame coordinates): colour of the pixel at (row&1, col&1)
+  const int c00 = cfa.pat[0], c10 = cfa.pat[48];
+
+  // ---- prologue: tile 0 converted, tile 1 in flight
+  __syncthreads();  // tables, counters and the barrier are ready
+  if ((int)blockIdx.x < ntiles) {
+    if (p.use_tma) mbar_wait(bar, 0);
+    convert_tile(0, 0, txi * kTW, p.out_row0 + tyi * kTH);
+  }
+  __syncthreads();
+  {
+    int ntx = txi, nty = tyi;
+    next_tile(ntx, nty);
+    if (tid == 0 && p.use_tma && (int)(blockIdx.x + gridDim.x) < ntiles) issue_tile(p, &tmap, raw_addr, bar, ntx, nty);
+  }
+
+  int it = 0;
+  for (int t = blockIdx.x; t < ntiles; t += gridDim.x, it++) {
+    const int ty0 = p.out_row0 + tyi * kTH, tx0 = txi * kTW;
+    next_tile(txi, tyi);  // (txi, tyi) now name tile t + gridDim.x
+    const float *ctile = sm.tile[it & 1];
 
     // ---- four-pixel tasks: 64 per tile row, consecutive lanes on consecutive tasks
     for (int task = tid; task < (kTW / 4) * kTH; task += kNT) {
@@ -473,7 +501,7 @@ k_fused_full(const __grid_constant__ FullParams p, const __grid_constant__ CfaDe
 
       // 3 x 6 window: rows y-1..y+1, cols x0-1..x0+4
       float w[3][6];
-      const float *tp = sm.tile + r * kTileStride + 4 * q + 7;
+      const float *tp = ctile + r * kTileStride + 4 * q + 7;
 #pragma unroll
       for (int k = 0; k < 3; k++) {
         const float4 mid = *reinterpret_cast<const float4 *>(tp + k * kTileStride + 1);
@@ -567,6 +595,22 @@ k_fused_full(const __grid_constant__ FullParams p, const __grid_constant__ CfaDe
         const size_t pix = (size_t)(y - p.out_row0) * p.width + x0;
         if (OUT == kOutU8) store_px4_bytes(p.out, pix, npx, q8);
         else store_px4<OUT>(p.out, pix, npx, orr, og, ob);
+      }
+    }
+
+    // ---- convert the next tile (its raw box was requested one tile ago), then one barrier per tile
+    const bool have_next = t + (int)gridDim.x < ntiles;
+    if (have_next) {
+      if (p.use_tma) mbar_wait(bar, (it + 1) & 1);
+      convert_tile((it + 1) & 1, (it + 1) & 1, txi * kTW, p.out_row0 + tyi * kTH);
+    }
+    if (tid == 0) sm.conv_ctr[it & 1] = 0;  // idle during this tile (the conversion above counts on the other one)
+    __syncthreads();  // tile t consumed, tile t+1 converted, raw box free again
+    if (tid == 0) {
+      if (p.use_tma && t + 2 * (int)gridDim.x < ntiles) {
+        int ntx = txi, nty = tyi;
+        next_tile(ntx, nty);
+        issue_tile(p, &tmap, raw_addr, bar, ntx, nty);
       }
     }
   }

@@ -51,6 +51,10 @@ struct ipb_pipeline {
   ipb_settings settings{};
   int fused = 1;
   int use_tma = 1;
+  // golevel_rc_exact() result for the last (black, range) pair: the check walks all 65536 samples
+  bool rc_cached = false;
+  float rc_black = 0.0f, rc_range = 0.0f;
+  int rc_exact = 0;
   // row-stripe source (multi-GPU / chunked transfers)
   bool has_stripe = false;
   ipb_stripe stripe{};
@@ -1295,7 +1299,13 @@ static int run_fused(ipb_pipeline *p, const FusedPlan &plan, int out_kind, size_
   a.black = p->ops.gofloat.blacklevels[0];
   a.range = p->ops.gofloat.whitelevels[0] - a.black;  // gofloat.rs:86-89
   a.range_rc = 1.0f / a.range;
-  a.exact_rc = golevel_rc_exact(a.black, a.range, a.range_rc) ? 1 : 0;
+  if (!p->rc_cached || memcmp(&p->rc_black, &a.black, 4) != 0 || memcmp(&p->rc_range, &a.range, 4) != 0) {
+    p->rc_exact = golevel_rc_exact(a.black, a.range, a.range_rc) ? 1 : 0;
+    p->rc_black = a.black;
+    p->rc_range = a.range;
+    p->rc_cached = true;
+  }
+  a.exact_rc = p->rc_exact;
   a.lut_lab = ctx->lut_lab;
   a.lut_gamma = ctx->lut_gamma;
   a.lut_gamma8 = ctx->lut_gamma8;
