@@ -138,6 +138,104 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def run_c5(args, ip, common, torch, dist, ctx, stream, barrier, rank, world, local_rank, params, K, Wm, F):
+    """BASELINE config 5: one 11648x8736 RGGB frame cut into row stripes, one per rank; every frame of a step does the
+    halo exchange (NCCL send/recv of the stencil rows between neighbours) and one fused launch per rank."""
+    from imagepipe_b200 import _capi
+    from imagepipe_b200.sharded import DevicePtr, exchange_halos, plan_stripes, run_stripe_8bit
+    W5, H5 = 11648, 8736
+    mp5 = W5 * H5 / 1e6
+    dummy = ip.DeviceArray(64, ctx)
+    p = ip.Pipeline.new_from_source(ip.ImageSource(_capi.SRC_RAW_U16, W5, H5, 1, dummy), ctx=ctx)
+    common.fill_ipb_ops(p.ops, params)
+    lays = plan_stripes(p.ops, p.globals.settings, W5, H5, world)
+    me = lays[rank]
+    rows_out = me.out_row1 - me.out_row0
+    set_bytes = (me.src_row1 - me.src_row0) * W5 * 2 + rows_out * W5 * 3
+    nsets = max(2, -(-300_000_000 // set_bytes))  # rotating working set of >= 300 MB per GPU (L2 is 126 MB)
+    bufs, outs = [], []
+    with torch.cuda.stream(stream):
+        for i in range(nsets):
+            b = torch.zeros((me.src_row1 - me.src_row0, W5), dtype=torch.int16, device="cuda")
+            own = b[me.own_row0 - me.src_row0: me.own_row1 - me.src_row0]
+            ip.lib().ipb_synth_cfa_u16(ctx.handle, common.SEED + i, W5, me.own_row0, me.own_row1 - me.own_row0, own.data_ptr())
+            bufs.append(b)
+            outs.append(torch.empty((rows_out, W5, 3), dtype=torch.uint8, device="cuda"))
+
+    def step():
+        for j in range(F):
+            b, o = bufs[j % nsets], outs[j % nsets]
+            if world > 1:
+                exchange_halos(b, lays, rank)
+            run_stripe_8bit(p, b.data_ptr(), me, DevicePtr(o.data_ptr(), o.numel()))
+
+    with torch.cuda.stream(stream):
+        for _ in range(Wm):
+            step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = ctx.launch_count
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    with torch.cuda.stream(stream):
+        ev[0].record(stream)
+        for _ in range(K):
+            step()
+        ev[1].record(stream)
+    barrier()
+    clocks = sampler.stop()
+    launches = ctx.launch_count - launches0
+    t = torch.tensor([ev[0].elapsed_time(ev[1])], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    value = K * F * mp5 / (total_ms / 1e3)
+
+    # e2e: every rank's source rows (halo included: the host holds the whole frame) in pinned host memory, its output
+    # stripe back to pinned host memory, through the banded H2D / kernel / D2H path
+    src_rows = me.src_row1 - me.src_row0
+    host_in, _hin = pinned_array(ip, src_rows * W5 * 2, np.uint16, (src_rows, W5))
+    host_out, _hout = pinned_array(ip, rows_out * W5 * 3, np.uint8, (rows_out, W5, 3))
+    host_in[:] = bufs[0].cpu().numpy().view(np.uint16)
+    e2e_steps, e2e_frames = 3, 2
+    for _ in range(2):
+        run_stripe_8bit(p, host_in, me, host_out)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps * e2e_frames):
+        run_stripe_8bit(p, host_in, me, host_out)
+    torch.cuda.synchronize()
+    te = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = e2e_steps * e2e_frames * mp5 / float(te.item())
+    same = bool(np.array_equal(host_out, outs[0].cpu().numpy()))
+    if rank == 0:
+        peak, peak_kind = measured_peak()
+        launch_ms = total_ms / (K * F)
+        achieved = ALGO_BYTES_PER_PX * rows_out * W5 / (launch_ms / 1e3) / 1e9
+        line = {
+            "metric": METRIC, "value": value, "unit": "MP/s", "n_gpus": world, "steps": K, "warmup": Wm,
+            "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "C5: 11648x8736 RGGB Bayer -> 8-bit sRGB, row stripes + NCCL halo exchange",
+                       "frames_per_step": F, "buffer_sets": nsets, "stripe_rows": rows_out,
+                       "halo_rows": (me.own_row0 - me.src_row0) + (me.src_row1 - me.own_row1),
+                       "l2": f"inputs larger than L2: {nsets} rotating sets x {set_bytes / 1e6:.0f} MB per GPU",
+                       "parallelism": f"{world} row stripe(s), send/recv of stencil rows between neighbours"},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "kernel": "k_fused_full<u8> (one stripe, exchange included in the time)",
+                         "kernel_ms": launch_ms, "peak_kind": peak_kind,
+                         "algorithmic_bytes_per_launch": ALGO_BYTES_PER_PX * rows_out * W5},
+            "e2e": {"value": e2e_value, "unit": "MP/s", "h2d_bytes_per_step": e2e_frames * src_rows * W5 * 2,
+                    "d2h_bytes_per_step": e2e_frames * rows_out * W5 * 3, "steps": e2e_steps,
+                    "frames_per_step": e2e_frames, "matches_device_path": same,
+                    "note": "bytes are per rank; every rank copies its own stripe"},
+            "gpu_launches": int(launches), "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -145,8 +243,13 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--frames-per-step", type=int, default=FRAMES_PER_STEP)
+    ap.add_argument("--frames-per-step", type=int, default=None)
+    ap.add_argument("--workload", default="c2", choices=["c2", "c5"],
+                    help="c2 (default, the contract's line): 24 MP frames, replicas; c5: one 101.8 MP frame per step-frame, "
+                         "row stripes over the ranks with an NCCL halo exchange (strong scaling)")
     args = ap.parse_args()
+    if args.frames_per_step is None:
+        args.frames_per_step = FRAMES_PER_STEP if args.workload == "c2" else 8
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -175,6 +278,11 @@ def main():
 
     K, Wm, F = args.steps, max(3, args.warmup), args.frames_per_step
     params = workload_params()
+    if args.workload == "c5":
+        run_c5(args, ip, common, torch, dist, ctx, stream, barrier, rank, world, local_rank, params, K, Wm, F)
+        if world > 1:
+            dist.destroy_process_group()
+        return
     # NSETS distinct synthetic frames, generated on the device, and NSETS output buffers
     frames = [ip.synth_cfa_u16(common.SEED + rank * 1000 + i, W, 0, H, ctx=ctx) for i in range(NSETS)]
     outs = [ip.DeviceArray(W * H * 3, ctx) for _ in range(NSETS)]

@@ -145,6 +145,7 @@ def lib():
         "ipb_pipeline_output_8bit": (i, [vp, vp, sz, i, szp, szp]),
         "ipb_pipeline_output_16bit": (i, [vp, vp, sz, i, szp, szp]),
         "ipb_pipeline_stripe_rows": (i, [vp, sz, sz, szp, szp]),
+        "ipb_stripe_plan": (i, [vp, vp, sz, sz, sz, sz, szp, szp, szp, szp]),
         "ipb_pipeline_set_stripe_source": (i, [vp, vp, vp]),
         "ipb_pipeline_output_8bit_stripe": (i, [vp, vp, sz, i, szp, szp]),
         "ipb_pipeline_set_tma": (i, [vp, i]),

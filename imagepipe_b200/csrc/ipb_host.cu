@@ -33,6 +33,9 @@ struct ipb_ctx {
   float2 *lut_gamma8 = nullptr;  // device {threshold, base} table: output8bit(apply_srgb_gamma(v)) per segment
   std::string err;
   unsigned long long launches = 0;
+  // copy streams + events of the chunk-pipelined host<->device path (created on first use)
+  cudaStream_t copy_in = nullptr, copy_out = nullptr;
+  std::vector<cudaEvent_t> events;
 };
 
 struct ipb_buffer {
@@ -570,6 +573,9 @@ void ipb_ctx_destroy(ipb_ctx *ctx) {
   if (ctx->lut_gamma) cudaFree(ctx->lut_gamma);
   if (ctx->lut_rev) cudaFree(ctx->lut_rev);
   if (ctx->lut_gamma8) cudaFree(ctx->lut_gamma8);
+  if (ctx->copy_in) { cudaStreamSynchronize(ctx->copy_in); cudaStreamDestroy(ctx->copy_in); }
+  if (ctx->copy_out) { cudaStreamSynchronize(ctx->copy_out); cudaStreamDestroy(ctx->copy_out); }
+  for (cudaEvent_t e : ctx->events) cudaEventDestroy(e);
   if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -1260,34 +1266,21 @@ static int ensure_stage(ipb_ctx *ctx, void **buf, size_t *have, size_t need) {
   return IPB_OK;
 }
 
-// Launch the fused kernel for output rows [r0, r1) into `out` (device, row r0 first).
-static int run_fused(ipb_pipeline *p, const FusedPlan &plan, int out_kind, size_t r0, size_t r1, void *out) {
+// Launch the fused kernel for output rows [r0, r1) into `out` (device, row r0 first).  `raw_dev` holds the
+// un-cropped source rows [have0, have0 + have_rows) on the device.
+static int launch_fused_rows(ipb_pipeline *p, const FusedPlan &plan, const ColorParams &P, int out_kind, size_t r0,
+                             size_t r1, void *out, const uint16_t *raw_dev, size_t have0, size_t have_rows) {
   ipb_ctx *ctx = p->ctx;
-  ColorParams P;
-  IPB_TRY(fill_color_params(p, plan, &P));
-  // which source rows do we have?
-  const ipb_source &src = p->has_stripe ? p->stripe_rows : p->image;
-  const size_t have0 = p->has_stripe ? p->stripe.src_row0 : 0;
-  const size_t have1 = have0 + src.height;
   size_t need0, need1;
   fused_src_rows(p, plan, r0, r1, &need0, &need1);
-  if (need0 < have0 || need1 > have1)
+  if (need0 < have0 || need1 > have0 + have_rows)
     return fail(ctx, IPB_ERR_INVALID, "stripe holds source rows [%zu,%zu) but output rows [%zu,%zu) need [%zu,%zu)", have0,
-                have1, r0, r1, need0, need1);
-  const uint16_t *raw = (const uint16_t *)src.data;
-  if (!src.on_device) {
-    // copy just the rows this launch needs
-    const size_t bytes = (need1 - need0) * src.width * sizeof(uint16_t);
-    IPB_TRY(ensure_stage(ctx, &p->stage_in, &p->stage_in_bytes, bytes));
-    IPB_CUDA(ctx, cudaMemcpyAsync(p->stage_in, raw + (need0 - have0) * src.width, bytes, cudaMemcpyHostToDevice, ctx->stream));
-    raw = (const uint16_t *)p->stage_in;
-  } else {
-    raw += (need0 - have0) * src.width;
-  }
+                have0 + have_rows, r0, r1, need0, need1);
+  const size_t pitch = p->image.width;
   FusedArgs a;
   memset(&a, 0, sizeof(a));
-  a.raw = raw;
-  a.raw_pitch = src.width;
+  a.raw = raw_dev + (need0 - have0) * pitch;
+  a.raw_pitch = pitch;
   a.src_row0 = need0;
   a.src_rows = need1 - need0;
   a.crop_x = plan.crop_x; a.crop_y = plan.crop_y;
@@ -1314,6 +1307,128 @@ static int run_fused(ipb_pipeline *p, const FusedPlan &plan, int out_kind, size_
                                           : launch_fused_scaled(ctx->stream, a, plan.cfa, P, ctx->sm_count);
   if (e != cudaSuccess) return fail(ctx, IPB_ERR_CUDA, "fused kernel: %s %s", cudaGetErrorString(e), fused_last_error());
   ctx->launches++;
+  return IPB_OK;
+}
+
+// Output rows [r0, r1) through the fused kernel in one launch; a host-resident source is staged first.
+static int run_fused(ipb_pipeline *p, const FusedPlan &plan, int out_kind, size_t r0, size_t r1, void *out) {
+  ipb_ctx *ctx = p->ctx;
+  ColorParams P;
+  IPB_TRY(fill_color_params(p, plan, &P));
+  // which source rows do we have?
+  const ipb_source &src = p->has_stripe ? p->stripe_rows : p->image;
+  const size_t have0 = p->has_stripe ? p->stripe.src_row0 : 0;
+  const size_t have1 = have0 + src.height;
+  const uint16_t *raw = (const uint16_t *)src.data;
+  if (src.on_device) return launch_fused_rows(p, plan, P, out_kind, r0, r1, out, raw, have0, src.height);
+  size_t need0, need1;
+  fused_src_rows(p, plan, r0, r1, &need0, &need1);
+  if (need0 < have0 || need1 > have1)
+    return fail(ctx, IPB_ERR_INVALID, "stripe holds source rows [%zu,%zu) but output rows [%zu,%zu) need [%zu,%zu)", have0,
+                have1, r0, r1, need0, need1);
+  // copy just the rows this launch needs
+  const size_t bytes = (need1 - need0) * src.width * sizeof(uint16_t);
+  IPB_TRY(ensure_stage(ctx, &p->stage_in, &p->stage_in_bytes, bytes));
+  IPB_CUDA(ctx, cudaMemcpyAsync(p->stage_in, raw + (need0 - have0) * src.width, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  return launch_fused_rows(p, plan, P, out_kind, r0, r1, out, (const uint16_t *)p->stage_in, need0, need1 - need0);
+}
+
+static int ensure_copy_streams(ipb_ctx *ctx, size_t nevents) {
+  if (!ctx->copy_in) IPB_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_in, cudaStreamNonBlocking));
+  if (!ctx->copy_out) IPB_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_out, cudaStreamNonBlocking));
+  while (ctx->events.size() < nevents) {
+    cudaEvent_t e;
+    IPB_CUDA(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    ctx->events.push_back(e);
+  }
+  return IPB_OK;
+}
+
+// Host-resident source and/or destination: the frame is cut into bands of output rows and the three legs of every
+// band — H2D of the source rows it adds, the fused kernel, D2H of its output rows — run on three streams, so that
+// the copies of neighbouring bands overlap each other (PCIe is full duplex) and the kernel.  The kernel stays on the
+// context's stream.  Output rows [r0, r1); `dst` receives row r0 first.  Results are those of one whole-frame launch:
+// every launch works in full-frame coordinates.
+static int run_fused_banded(ipb_pipeline *p, const FusedPlan &plan, int out_kind, size_t elem_size, size_t r0, size_t r1,
+                            void *dst, int dst_on_device) {
+  ipb_ctx *ctx = p->ctx;
+  const ipb_source &src = p->has_stripe ? p->stripe_rows : p->image;
+  const size_t have0 = p->has_stripe ? p->stripe.src_row0 : 0;
+  const size_t have1 = have0 + src.height;
+  const bool src_host = !src.on_device, dst_host = !dst_on_device;
+  const size_t row_out_bytes = plan.out_width * 3 * elem_size;
+  const size_t row_in_bytes = src.width * sizeof(uint16_t);
+  // bands of about 8 MB of traffic, at most 16, a multiple of 32 output rows (the full-resolution kernel's tile height)
+  const size_t rows = r1 - r0;
+  size_t need0, need1;
+  fused_src_rows(p, plan, r0, r1, &need0, &need1);
+  if (need0 < have0 || need1 > have1)
+    return fail(ctx, IPB_ERR_INVALID, "stripe holds source rows [%zu,%zu) but output rows [%zu,%zu) need [%zu,%zu)", have0,
+                have1, r0, r1, need0, need1);
+  const size_t traffic = (src_host ? (need1 - need0) * row_in_bytes : 0) + (dst_host ? rows * row_out_bytes : 0);
+  size_t nbands = traffic / (8u << 20);
+  nbands = nbands < 1 ? 1 : (nbands > 16 ? 16 : nbands);
+  size_t band_rows = ((rows + nbands - 1) / nbands + 31) / 32 * 32;
+  nbands = (rows + band_rows - 1) / band_rows;
+  if (nbands <= 1 || (!src_host && !dst_host)) {
+    void *d = dst;
+    if (dst_host) {
+      IPB_TRY(ensure_stage(ctx, &p->stage_out, &p->stage_out_bytes, rows * row_out_bytes));
+      d = p->stage_out;
+    }
+    IPB_TRY(run_fused(p, plan, out_kind, r0, r1, d));
+    if (dst_host) IPB_CUDA(ctx, cudaMemcpyAsync(dst, d, rows * row_out_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    return IPB_OK;
+  }
+  ColorParams P;
+  IPB_TRY(fill_color_params(p, plan, &P));
+  IPB_TRY(ensure_copy_streams(ctx, 2 * nbands + 1));
+  const uint16_t *raw_dev = (const uint16_t *)src.data;
+  size_t dev0 = have0, dev_rows = src.height;
+  if (src_host) {
+    IPB_TRY(ensure_stage(ctx, &p->stage_in, &p->stage_in_bytes, (need1 - need0) * row_in_bytes));
+    raw_dev = (const uint16_t *)p->stage_in;
+    dev0 = need0;
+    dev_rows = need1 - need0;
+  }
+  uint8_t *out_dev = (uint8_t *)dst;
+  if (dst_host) {
+    IPB_TRY(ensure_stage(ctx, &p->stage_out, &p->stage_out_bytes, rows * row_out_bytes));
+    out_dev = (uint8_t *)p->stage_out;
+  }
+  // the copy streams start after whatever the context's stream has queued so far (it may still use the staging buffers)
+  cudaEvent_t e0 = ctx->events[2 * nbands];
+  IPB_CUDA(ctx, cudaEventRecord(e0, ctx->stream));
+  if (src_host) IPB_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_in, e0, 0));
+  if (dst_host) IPB_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_out, e0, 0));
+  size_t uploaded = need0;  // source rows [need0, uploaded) are on their way
+  for (size_t b = 0; b < nbands; b++) {
+    const size_t b0 = r0 + b * band_rows, b1 = b0 + band_rows < r1 ? b0 + band_rows : r1;
+    if (src_host) {
+      size_t s0, s1;
+      fused_src_rows(p, plan, b0, b1, &s0, &s1);
+      if (s1 > uploaded) {
+        IPB_CUDA(ctx, cudaMemcpyAsync((uint8_t *)p->stage_in + (uploaded - need0) * row_in_bytes,
+                                      (const uint8_t *)src.data + (uploaded - have0) * row_in_bytes,
+                                      (s1 - uploaded) * row_in_bytes, cudaMemcpyHostToDevice, ctx->copy_in));
+        uploaded = s1;
+      }
+      IPB_CUDA(ctx, cudaEventRecord(ctx->events[2 * b], ctx->copy_in));
+      IPB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->events[2 * b], 0));
+    }
+    uint8_t *band_out = out_dev + (b0 - r0) * row_out_bytes;
+    IPB_TRY(launch_fused_rows(p, plan, P, out_kind, b0, b1, band_out, raw_dev, dev0, dev_rows));
+    if (dst_host) {
+      IPB_CUDA(ctx, cudaEventRecord(ctx->events[2 * b + 1], ctx->stream));
+      IPB_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_out, ctx->events[2 * b + 1], 0));
+      IPB_CUDA(ctx, cudaMemcpyAsync((uint8_t *)dst + (b0 - r0) * row_out_bytes, band_out, (b1 - b0) * row_out_bytes,
+                                    cudaMemcpyDeviceToHost, ctx->copy_out));
+    }
+  }
+  if (dst_host) {  // the context's stream is "done" only when the last band has landed on the host
+    IPB_CUDA(ctx, cudaEventRecord(e0, ctx->copy_out));
+    IPB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, e0, 0));
+  }
   return IPB_OK;
 }
 
@@ -1439,16 +1554,8 @@ static int output_impl(ipb_pipeline *p, T *dst, size_t cap, int dst_on_device, s
   if (plan.mode != kNotFused && normal) {
     const size_t n = plan.out_width * plan.out_height * 3;
     if (n > cap) return fail(ctx, IPB_ERR_INVALID, "destination too small: %zu < %zu", cap, n);
-    T *d = dst;
-    if (!dst_on_device) {
-      IPB_TRY(ensure_stage(ctx, &p->stage_out, &p->stage_out_bytes, n * sizeof(T)));
-      d = (T *)p->stage_out;
-    }
-    IPB_TRY(run_fused(p, plan, want8 ? kOutU8 : kOutU16, 0, plan.out_height, d));
-    if (!dst_on_device) {
-      IPB_CUDA(ctx, cudaMemcpyAsync(dst, d, n * sizeof(T), cudaMemcpyDeviceToHost, ctx->stream));
-      IPB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    }
+    IPB_TRY(run_fused_banded(p, plan, want8 ? kOutU8 : kOutU16, sizeof(T), 0, plan.out_height, dst, dst_on_device));
+    if (!dst_on_device) IPB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     if (width) *width = plan.out_width;
     if (height) *height = plan.out_height;
     return IPB_OK;
@@ -1500,6 +1607,29 @@ int ipb_pipeline_stripe_rows(ipb_pipeline *p, size_t out_row0, size_t out_row1, 
   return IPB_OK;
 }
 
+int ipb_stripe_plan(const ipb_ops *ops, const ipb_settings *settings, size_t width, size_t height, size_t out_row0,
+                    size_t out_row1, size_t *src_row0, size_t *src_row1, size_t *out_width, size_t *out_height) {
+  if (!ops) return IPB_ERR_INVALID;
+  ipb_pipeline tmp;  // never touches a device: ctx stays null (failures land in the thread's create-error string)
+  tmp.image.kind = IPB_SRC_RAW_U16;
+  tmp.image.width = width;
+  tmp.image.height = height;
+  tmp.image.cpp = 1;
+  tmp.ops = *ops;
+  if (settings) tmp.settings = *settings;
+  else tmp.settings.use_fastpath = 1;
+  FusedPlan plan;
+  IPB_TRY(stripe_plan(&tmp, &plan));
+  if (out_width) *out_width = plan.out_width;
+  if (out_height) *out_height = plan.out_height;
+  if (out_row0 < out_row1) {
+    if (out_row1 > plan.out_height || !src_row0 || !src_row1)
+      return fail(nullptr, IPB_ERR_INVALID, "output rows [%zu,%zu) outside the %zu-row result", out_row0, out_row1, plan.out_height);
+    fused_src_rows(&tmp, plan, out_row0, out_row1, src_row0, src_row1);
+  }
+  return IPB_OK;
+}
+
 int ipb_pipeline_set_stripe_source(ipb_pipeline *p, const ipb_source *rows, const ipb_stripe *stripe) {
   if (!p || !rows || !stripe) return IPB_ERR_INVALID;
   if (rows->kind != IPB_SRC_RAW_U16 || rows->cpp != 1 || rows->width != p->image.width)
@@ -1524,16 +1654,8 @@ int ipb_pipeline_output_8bit_stripe(ipb_pipeline *p, uint8_t *dst, size_t dst_ca
   if (r0 >= r1 || r1 > plan.out_height) return fail(ctx, IPB_ERR_INVALID, "stripe output rows [%zu,%zu) outside the %zu-row result", r0, r1, plan.out_height);
   const size_t n = (r1 - r0) * plan.out_width * 3;
   if (n > dst_capacity) return fail(ctx, IPB_ERR_INVALID, "destination too small: %zu < %zu", dst_capacity, n);
-  uint8_t *d = dst;
-  if (!dst_on_device) {
-    IPB_TRY(ensure_stage(ctx, &p->stage_out, &p->stage_out_bytes, n));
-    d = (uint8_t *)p->stage_out;
-  }
-  IPB_TRY(run_fused(p, plan, kOutU8, r0, r1, d));
-  if (!dst_on_device) {
-    IPB_CUDA(ctx, cudaMemcpyAsync(dst, d, n, cudaMemcpyDeviceToHost, ctx->stream));
-    IPB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-  }
+  IPB_TRY(run_fused_banded(p, plan, kOutU8, 1, r0, r1, dst, dst_on_device));
+  if (!dst_on_device) IPB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   if (width) *width = plan.out_width;
   if (rows) *rows = r1 - r0;
   return IPB_OK;

@@ -255,6 +255,13 @@ int ipb_pipeline_output_16bit(ipb_pipeline *p, uint16_t *dst, size_t dst_capacit
  * Normal orientation and no rotatecrop. */
 /* which source rows [*src_row0, *src_row1) are needed to produce output rows [out_row0, out_row1) */
 int ipb_pipeline_stripe_rows(ipb_pipeline *p, size_t out_row0, size_t out_row1, size_t *src_row0, size_t *src_row1);
+/* The same question without a context or a GPU (pure host arithmetic: the size walk of pipeline.rs:313-338, the
+ * demosaic branch of demosaic.rs:41-60 and the window rows of scaling.rs:69-87): for a `width` x `height` u16 CFA
+ * source, *out_width / *out_height receive the size of the result and, when out_row0 < out_row1, [*src_row0, *src_row1)
+ * the source rows that output rows [out_row0, out_row1) need.  IPB_ERR_UNSUPPORTED when the chain cannot be sharded by
+ * rows (not the fused CFA path, or an orientation other than Normal).  Used by the sharding driver to size halos. */
+int ipb_stripe_plan(const ipb_ops *ops, const ipb_settings *settings, size_t width, size_t height, size_t out_row0,
+                    size_t out_row1, size_t *src_row0, size_t *src_row1, size_t *out_width, size_t *out_height);
 /* like output_8bit but the pipeline's source holds only the rows named by `stripe`; the pipeline must have
  * been created with image.height == stripe->full_height semantics via ipb_pipeline_set_stripe_source(). */
 int ipb_pipeline_set_stripe_source(ipb_pipeline *p, const ipb_source *rows, const ipb_stripe *stripe);
