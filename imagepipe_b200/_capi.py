@@ -149,6 +149,7 @@ def lib():
         "ipb_pipeline_set_stripe_source": (i, [vp, vp, vp]),
         "ipb_pipeline_output_8bit_stripe": (i, [vp, vp, sz, i, szp, szp]),
         "ipb_pipeline_set_tma": (i, [vp, i]),
+        "ipb_pipeline_set_band_mb": (i, [vp, i]),
         "ipb_selftest_gamma8": (i, [vp, C.POINTER(C.c_ulonglong)]),
         "ipb_gamma_pack_8bit": (i, [vp, vp, sz, vp]),
         "ipb_synth_cfa_u16": (i, [vp, C.c_uint64, sz, sz, sz, vp]),

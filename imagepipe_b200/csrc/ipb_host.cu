@@ -12,6 +12,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <new>
@@ -54,6 +55,7 @@ struct ipb_pipeline {
   ipb_settings settings{};
   int fused = 1;
   int use_tma = 1;
+  int band_mb = 16;  // host<->device paths: band size of the overlapped H2D / kernel / D2H schedule (0 = no bands)
   // golevel_rc_exact() result for the last (black, range) pair: the check walks all 65536 samples
   bool rc_cached = false;
   float rc_black = 0.0f, rc_range = 0.0f;
@@ -1366,8 +1368,9 @@ static int run_fused_banded(ipb_pipeline *p, const FusedPlan &plan, int out_kind
     return fail(ctx, IPB_ERR_INVALID, "stripe holds source rows [%zu,%zu) but output rows [%zu,%zu) need [%zu,%zu)", have0,
                 have1, r0, r1, need0, need1);
   const size_t traffic = (src_host ? (need1 - need0) * row_in_bytes : 0) + (dst_host ? rows * row_out_bytes : 0);
-  size_t nbands = traffic / (8u << 20);
-  nbands = nbands < 1 ? 1 : (nbands > 16 ? 16 : nbands);
+  const size_t band_mb = p->band_mb > 0 ? (size_t)p->band_mb : ((size_t)1 << 40);  // 0: one band
+  size_t nbands = traffic / (band_mb << 20);
+  nbands = nbands < 1 ? 1 : (nbands > 64 ? 64 : nbands);
   size_t band_rows = ((rows + nbands - 1) / nbands + 31) / 32 * 32;
   nbands = (rows + band_rows - 1) / band_rows;
   if (nbands <= 1 || (!src_host && !dst_host)) {
@@ -1401,6 +1404,17 @@ static int run_fused_banded(ipb_pipeline *p, const FusedPlan &plan, int out_kind
   IPB_CUDA(ctx, cudaEventRecord(e0, ctx->stream));
   if (src_host) IPB_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_in, e0, 0));
   if (dst_host) IPB_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_out, e0, 0));
+  // IPB_TRACE=1: time every leg with CUDA events and print the band timeline to stderr (debugging aid, slow)
+  static const bool trace = getenv("IPB_TRACE") != nullptr;
+  std::vector<cudaEvent_t> tev;
+  auto mark = [&](cudaStream_t st) {
+    if (!trace) return;
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    cudaEventRecord(e, st);
+    tev.push_back(e);
+  };
+  mark(ctx->stream);
   size_t uploaded = need0;  // source rows [need0, uploaded) are on their way
   for (size_t b = 0; b < nbands; b++) {
     const size_t b0 = r0 + b * band_rows, b1 = b0 + band_rows < r1 ? b0 + band_rows : r1;
@@ -1416,14 +1430,29 @@ static int run_fused_banded(ipb_pipeline *p, const FusedPlan &plan, int out_kind
       IPB_CUDA(ctx, cudaEventRecord(ctx->events[2 * b], ctx->copy_in));
       IPB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->events[2 * b], 0));
     }
+    mark(ctx->copy_in);
     uint8_t *band_out = out_dev + (b0 - r0) * row_out_bytes;
-    IPB_TRY(launch_fused_rows(p, plan, P, out_kind, b0, b1, band_out, raw_dev, dev0, dev_rows));
+    mark(ctx->stream);
+    static const bool nokernel = getenv("IPB_NOKERNEL") != nullptr;  // transfer-only timing experiment
+    if (!nokernel) IPB_TRY(launch_fused_rows(p, plan, P, out_kind, b0, b1, band_out, raw_dev, dev0, dev_rows));
+    mark(ctx->stream);
     if (dst_host) {
       IPB_CUDA(ctx, cudaEventRecord(ctx->events[2 * b + 1], ctx->stream));
       IPB_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_out, ctx->events[2 * b + 1], 0));
       IPB_CUDA(ctx, cudaMemcpyAsync((uint8_t *)dst + (b0 - r0) * row_out_bytes, band_out, (b1 - b0) * row_out_bytes,
                                     cudaMemcpyDeviceToHost, ctx->copy_out));
     }
+    mark(ctx->copy_out);
+  }
+  if (trace) {
+    cudaDeviceSynchronize();
+    fprintf(stderr, "band  h2d_done  k_start  k_end  d2h_done   (ms after the call started)\n");
+    for (size_t b = 0; b < nbands; b++) {
+      float t[4];
+      for (int k = 0; k < 4; k++) cudaEventElapsedTime(&t[k], tev[0], tev[1 + 4 * b + k]);
+      fprintf(stderr, "%4zu  %8.3f %8.3f %6.3f %9.3f\n", b, t[0], t[1], t[2], t[3]);
+    }
+    for (cudaEvent_t e : tev) cudaEventDestroy(e);
   }
   if (dst_host) {  // the context's stream is "done" only when the last band has landed on the host
     IPB_CUDA(ctx, cudaEventRecord(e0, ctx->copy_out));
@@ -1658,6 +1687,12 @@ int ipb_pipeline_output_8bit_stripe(ipb_pipeline *p, uint8_t *dst, size_t dst_ca
   if (!dst_on_device) IPB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   if (width) *width = plan.out_width;
   if (rows) *rows = r1 - r0;
+  return IPB_OK;
+}
+
+int ipb_pipeline_set_band_mb(ipb_pipeline *p, int megabytes) {
+  if (!p || megabytes < 0) return IPB_ERR_INVALID;
+  p->band_mb = megabytes;
   return IPB_OK;
 }
 

@@ -435,6 +435,10 @@ class Pipeline:
         """True (default): run may use the fused raw->sRGB kernel; False: one kernel + one OpBuffer per op."""
         _capi.check(self.ctx.handle, lib().ipb_pipeline_set_fused(self.handle, int(fused)))
 
+    def set_band_mb(self, megabytes):
+        """Host source/destination: band size of the overlapped H2D / kernel / D2H schedule (0 = whole-frame copies)."""
+        _capi.check(self.ctx.handle, lib().ipb_pipeline_set_band_mb(self.handle, int(megabytes)))
+
     def default_ops(self):
         return bytes(self.ops) == bytes(PipelineOps.new(self.globals.image))
 

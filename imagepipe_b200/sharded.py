@@ -97,9 +97,12 @@ def exchange_halos(buf, layouts, rank, group=None):
     samples per tensor row) whose own block is already in place — from the neighbouring ranks, and send them theirs.
     One batched isend/irecv per boundary; returns after the transfers are complete (on the GPU: enqueued on the
     current stream, which then waits for them — no host synchronisation)."""
+    import torch
     import torch.distributed as dist
     me = layouts[rank]
     ops = []
+    if buf.element_size() != 1:  # NCCL has no 16-bit integer type: move the rows as bytes
+        buf = buf.view(torch.uint8)
 
     def rows(lay_from, a, b):  # view of my buffer for frame rows [a, b)
         return buf[a - me.src_row0: b - me.src_row0]

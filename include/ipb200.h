@@ -240,6 +240,11 @@ int ipb_pipeline_set_fused(ipb_pipeline *p, int fused);
 /* 1 (default): the full-resolution fused kernel stages raw tiles with TMA when the source allows it (16-byte
  * aligned base and row pitch); 0: always use the plain-load staging path.  Results are identical. */
 int ipb_pipeline_set_tma(ipb_pipeline *p, int use_tma);
+/* Host-resident source and/or destination: output_8bit / output_16bit cut the frame into bands of about `megabytes`
+ * of PCIe traffic and overlap the H2D copy, the kernel and the D2H copy of neighbouring bands on three streams
+ * (default 16: lowest latency of a single call).  0 = one band: whole-frame copies, which use the PCIe link better
+ * when several host threads (each with its own context) keep both directions busy across frames.  Same results. */
+int ipb_pipeline_set_band_mb(ipb_pipeline *p, int megabytes);
 /* size walk of Pipeline::run (pipeline.rs:313-338): final output size; also sets settings.demosaic_* */
 int ipb_pipeline_output_size(ipb_pipeline *p, size_t *width, size_t *height);
 /* Pipeline::run(None) — pipeline.rs:311-375; result is a 3-channel f32 OpBuffer */
