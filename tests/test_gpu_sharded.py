@@ -55,13 +55,21 @@ def test_banded_host_path_equals_oracle(ip, orc, ctx, case):
     params = common.raw_params(crops=(3, 8, 5, 16) if case == "crop" else (0, 0, 0, 0))
     want = orc.pipeline_output_8bit(orc.make_pipeline(data, "raw", params, st))
     n0 = ctx.launch_count
-    got = common.make_ipb_pipeline(ip, data, "raw", params, st, ctx=ctx).output_8bit()
-    if case != "scaled":
-        assert ctx.launch_count - n0 > 1  # really ran in bands
+    pg = common.make_ipb_pipeline(ip, data, "raw", params, st, ctx=ctx)
+    pg.set_band_mb(4)
+    got = pg.output_8bit()
+    assert ctx.launch_count - n0 > 1  # really ran in bands
     assert_bit_exact(got.to_numpy(), want, f"banded {case}")
     # device-resident source, host destination: kernel / D2H overlap only
-    got = common.make_ipb_pipeline(ip, data, "raw", params, st, ctx=ctx, on_device=True).output_8bit()
-    assert_bit_exact(got.to_numpy(), want, f"banded {case}, device source")
+    pg = common.make_ipb_pipeline(ip, data, "raw", params, st, ctx=ctx, on_device=True)
+    pg.set_band_mb(2)
+    assert_bit_exact(pg.output_8bit().to_numpy(), want, f"banded {case}, device source")
+    # one band (whole-frame copies)
+    pg = common.make_ipb_pipeline(ip, data, "raw", params, st, ctx=ctx)
+    pg.set_band_mb(0)
+    n0 = ctx.launch_count
+    assert_bit_exact(pg.output_8bit().to_numpy(), want, f"unbanded {case}")
+    assert ctx.launch_count - n0 == 1
 
 
 def test_banded_16bit(ip, orc, ctx):
@@ -69,8 +77,9 @@ def test_banded_16bit(ip, orc, ctx):
     data = common.smooth_cfa(w, h)
     params = common.raw_params(cfa="GBRG")
     want = orc.pipeline_output_16bit(orc.make_pipeline(data, "raw", params))
-    got = common.make_ipb_pipeline(ip, data, "raw", params, ctx=ctx).output_16bit()
-    assert_bit_exact(got.to_numpy(), want, "banded output_16bit")
+    pg = common.make_ipb_pipeline(ip, data, "raw", params, ctx=ctx)
+    pg.set_band_mb(4)
+    assert_bit_exact(pg.output_16bit().to_numpy(), want, "banded output_16bit")
 
 
 # ---------------------------------------------------------------------------------------------- 2+ GPUs
