@@ -1190,6 +1190,14 @@ static bool fused_params_bounded(const ipb_pipeline *p) {
     if (!std::isfinite(c.points[i][0]) || !std::isfinite(c.points[i][1]) || fabsf(c.points[i][0]) > 1024.0f ||
         fabsf(c.points[i][1]) > 1024.0f)
       return false;
+  // the fused spline evaluation counts the knots at or below the value: knots must increase strictly, and the end
+  // values must not be -0.0 (they are returned through y + 0*d sums)
+  SplineDev sp;
+  if (!build_spline(&c, &sp)) return false;
+  for (int i = 0; i + 1 < sp.n; i++)
+    if (!(sp.x[i] < sp.x[i + 1])) return false;
+  if (sp.n > 0 && (std::signbit(sp.y_first) && sp.y_first == 0.0f)) return false;
+  if (sp.n > 0 && (std::signbit(sp.y_last) && sp.y_last == 0.0f)) return false;
   return true;
 }
 

@@ -5,7 +5,7 @@ demosaic::full, scaled_demosaic, to_lab with a camera matrix, basecurve with an 
 The reference is Rust and cannot run here, so these vectors come from a SECOND, independent restatement: scalar
 numpy-float32 loops written directly from the reference source (file:line cited at each function), sharing no code
 with oracle/oracle.c or the CUDA kernels.  Two independent restatements agreeing bit for bit is the strongest pin
-available without the reference binary.  Frames are tiny (hand-checkable: `full_rggb_6x6` has a worked example in
+available without the reference binary.  Frames are tiny (hand-checkable: `full_rggb_10x10` has a worked example in
 tests/test_golden.py).
 
     python tests/golden/make_golden.py        # rewrites tests/golden/*.npz
@@ -240,10 +240,10 @@ def synth(shape, seed, lo=0, hi=1024):
 
 def main():
     cases = {}
-    raw = synth((6, 6), 1)
-    raw[0, 0], raw[2, 3], raw[5, 5] = 10, 1023, 700       # below black, at white, ordinary
+    raw = synth((10, 10), 1)
+    raw[0, 0], raw[2, 3], raw[9, 9] = 10, 1023, 700       # below black, at white, ordinary
     g = gofloat_cfa(raw, 64.0, 1023.0, (0, 0, 0, 0))
-    cases["full_rggb_6x6"] = dict(raw=raw, black=64.0, white=1023.0, crops=(0, 0, 0, 0), cfa="RGGB", gofloat=g,
+    cases["full_rggb_10x10"] = dict(raw=raw, black=64.0, white=1023.0, crops=(0, 0, 0, 0), cfa="RGGB", gofloat=g,
                                   demosaic=demosaic_full(g, "RGGB"))
     raw = synth((14, 16), 2)
     g = gofloat_cfa(raw, 60.0, 1000.0, (1, 2, 1, 2))      # crops: 12x12 left
