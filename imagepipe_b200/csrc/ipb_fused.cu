@@ -641,18 +641,27 @@ struct ScaledParams {
   float skip_x, skip_y;         // skip_x_x, skip_y_y of scaling.rs:69-72 (skip_x_y == skip_y_x == 0 here)
 };
 
+constexpr int kPatStride = 56;   // pattern row: 48 columns + the first 8 again, so that x % 48 + k needs no wrap
+constexpr int kMaxCols = 8;      // widest window the register-resident fast path handles (scale < 7)
+
 struct SmemScaled {
   float2 lut_lab[kLutEntries];
   float2 lut_gamma[kLutEntries];
-  uint8_t pat[48 * 48];
+  uint8_t pat[48 * kPatStride];
 };
 
-constexpr int kNTScaled = 512;
+constexpr int kNTScaled = 1024;
 
 __device__ __forceinline__ int f2i_sat(float f) {  // Rust `f as usize` for the values met here (>= 0, < 2^31)
   return (int)min(__float2uint_rz(f), 0x7fffffffu);
 }
 
+// k_fused_scaled: one output pixel per thread (scaling.rs:76-127 with the CFA binning of :109-112), then the colour
+// chain.  The reference's per-tap arithmetic is kept expression by expression; what is shared between taps is
+// computed once: delta_x and 1 - delta_x^2 per window column (the reference recomputes them for every row),
+// delta_y^2 per window row.  A colour's weighted sum and weight sum travel as one packed f32x2 accumulator:
+// (v, 1) * (f, f) = (v*f, f) is one FMUL2 and the two additions one packed add, each half rounded exactly like the
+// reference's scalar `sums[c] += v*f; counts[c] += f` — and in the same tap order.
 template <int OUT>
 __global__ void __launch_bounds__(kNTScaled, 1)
 k_fused_scaled(const __grid_constant__ ScaledParams p, const __grid_constant__ CfaDev cfa,
@@ -660,9 +669,13 @@ k_fused_scaled(const __grid_constant__ ScaledParams p, const __grid_constant__ C
   extern __shared__ __align__(16) unsigned char smem_raw[];
   SmemScaled &sm = *reinterpret_cast<SmemScaled *>(smem_raw);
   load_luts(sm.lut_lab, sm.lut_gamma, p.lut_lab, p.lut_gamma);
-  for (int i = threadIdx.x; i < 48 * 48; i += blockDim.x) sm.pat[i] = cfa.pat[i];
+  for (int i = threadIdx.x; i < 48 * kPatStride; i += blockDim.x) {
+    const int r = i / kPatStride, c = i - r * kPatStride;
+    sm.pat[i] = cfa.pat[r * 48 + (c % 48)];
+  }
   __syncthreads();
   const LutShared lab{smem_u32(sm.lut_lab)}, gam{smem_u32(sm.lut_gamma)};
+  const PkAdd pk{P.one, P.mone};
 
   const long long npix = (long long)(p.out_row1 - p.out_row0) * p.nwidth;
   for (long long idx = (long long)blockIdx.x * kNTScaled + threadIdx.x; idx < npix;
@@ -682,27 +695,60 @@ k_fused_scaled(const __grid_constant__ ScaledParams p, const __grid_constant__ C
     const int to_y = min(p.height - 1, f2i_sat(floorf(rto_y + (0.0f * fcol1))));
     const float center_x = rcenter_x + (p.skip_x * fcol) + __fdiv_rn(p.skip_x, 2.0f);
     const float center_y = rcenter_y + (0.0f * fcol) + __fdiv_rn(0.0f, 2.0f);
+    const int nx = to_x - from_x + 1;
 
-    float sums[4] = {0.f, 0.f, 0.f, 0.f}, counts[4] = {0.f, 0.f, 0.f, 0.f};
-    for (int y = from_y; y <= to_y; y++) {
-      const float delta_y = __fdiv_rn((float)y - center_y, p.skip_y);
-      const float dy2 = delta_y * delta_y;
-      const uint16_t *rowp = p.raw + (long long)(y + p.crop_y - p.src_row0) * p.raw_pitch + p.crop_x;
-      const uint8_t *prow = sm.pat + (y % 48) * 48;
-      for (int x = from_x; x <= to_x; x++) {
-        const float delta_x = __fdiv_rn((float)x - center_x, p.skip_x);
-        float factor = 1.0f - (delta_x * delta_x) - dy2;
-        factor = factor < 0.0f ? 0.0f : factor;
-        const int c = prow[x % 48];
-        const float v = golevel((float)__ldg(rowp + x), p.black, p.range, p.range_rc, p.exact_rc) * factor;
+    F2 acc[4] = {F2{0.f, 0.f}, F2{0.f, 0.f}, F2{0.f, 0.f}, F2{0.f, 0.f}};  // {sums[c], counts[c]}
+    if (nx <= kMaxCols) {
+      float ax[kMaxCols];  // 1.0 - delta_x*delta_x of window column k
 #pragma unroll
-        for (int k = 0; k < 4; k++)
-          if (c == k) { sums[k] += v; counts[k] += factor; }
+      for (int k = 0; k < kMaxCols; k++) {
+        const float delta_x = __fdiv_rn((float)(from_x + k) - center_x, p.skip_x);
+        ax[k] = 1.0f - (delta_x * delta_x);
+      }
+      const int xm0 = from_x % 48;
+      int ym = from_y % 48;
+      const uint16_t *rowp = p.raw + (long long)(from_y + p.crop_y - p.src_row0) * p.raw_pitch + p.crop_x + from_x;
+      for (int y = from_y; y <= to_y; y++, rowp += p.raw_pitch) {
+        const float delta_y = __fdiv_rn((float)y - center_y, p.skip_y);
+        const float dy2 = delta_y * delta_y;
+        const uint8_t *prow = sm.pat + ym * kPatStride + xm0;
+        ym = ym == 47 ? 0 : ym + 1;
+#pragma unroll
+        for (int k = 0; k < kMaxCols; k++) {
+          if (k < nx) {
+            float factor = ax[k] - dy2;
+            factor = factor < 0.0f ? 0.0f : factor;
+            const int c = prow[k];
+            const float v = golevel((float)__ldg(rowp + k), p.black, p.range, p.range_rc, p.exact_rc);
+            const F2 prod = pk_mul(F2{v, 1.0f}, splat(factor));  // (v*factor, factor)
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+              if (c == j) acc[j] = pk.add(acc[j], prod);
+          }
+        }
+      }
+    } else {
+      // wide windows (scale >= 7): the plain loop
+      for (int y = from_y; y <= to_y; y++) {
+        const float delta_y = __fdiv_rn((float)y - center_y, p.skip_y);
+        const float dy2 = delta_y * delta_y;
+        const uint16_t *rowp = p.raw + (long long)(y + p.crop_y - p.src_row0) * p.raw_pitch + p.crop_x;
+        const uint8_t *prow = sm.pat + (y % 48) * kPatStride;
+        for (int x = from_x; x <= to_x; x++) {
+          const float delta_x = __fdiv_rn((float)x - center_x, p.skip_x);
+          float factor = 1.0f - (delta_x * delta_x) - dy2;
+          factor = factor < 0.0f ? 0.0f : factor;
+          const int c = prow[x % 48];
+          const float v = golevel((float)__ldg(rowp + x), p.black, p.range, p.range_rc, p.exact_rc) * factor;
+#pragma unroll
+          for (int j = 0; j < 4; j++)
+            if (c == j) { acc[j].x += v; acc[j].y += factor; }
+        }
       }
     }
     float px[4];
 #pragma unroll
-    for (int k = 0; k < 4; k++) px[k] = counts[k] > 0.0f ? __fdiv_rn(sums[k], counts[k]) : 0.0f;
+    for (int k = 0; k < 4; k++) px[k] = acc[k].y > 0.0f ? __fdiv_rn(acc[k].x, acc[k].y) : 0.0f;
     float r[4] = {0.f, 0.f, 0.f, 0.f}, g[4] = {0.f, 0.f, 0.f, 0.f}, b[4] = {0.f, 0.f, 0.f, 0.f};
     color_chain<true>(P, lab, gam, px[0], px[1], px[2], px[3], r[0], g[0], b[0]);
     store_px4<OUT>(p.out, (size_t)(idx), 1, r, g, b);
