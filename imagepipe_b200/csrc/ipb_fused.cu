@@ -656,12 +656,64 @@ __device__ __forceinline__ int f2i_sat(float f) {  // Rust `f as usize` for the 
   return (int)min(__float2uint_rz(f), 0x7fffffffu);
 }
 
+// acc += prod when cond, as one predicated packed add (each half rounded like the scalar `+=`; the multiplication by
+// the run-time `one` keeps ptxas from fusing the producer's multiply into it, see PkAdd)
+__device__ __forceinline__ void pk_add_if(F2 &acc, F2 prod, float one, bool cond) {
+  asm("{ .reg .pred q; .reg .b64 ra, rb, rc;\n"
+      "  setp.ne.s32 q, %4, 0; mov.b64 ra, {%0, %1}; mov.b64 rb, {%2, %3}; mov.b64 rc, {%5, %5};\n"
+      "  @q fma.rn.f32x2 ra, rb, rc, ra; mov.b64 {%0, %1}, ra; }"
+      : "+f"(acc.x), "+f"(acc.y) : "f"(prod.x), "f"(prod.y), "r"((int)cond), "f"(one));
+}
+
+// u16 -> f32 without the conversion unit: 0x4B000000 | v is the float 2^23 + v, and subtracting 2^23 is exact
+__device__ __forceinline__ float u16_to_float(uint32_t v) { return __uint_as_float(0x4B000000u | v) - 8388608.0f; }
+
+// The taps of one output pixel whose window is at most NX columns wide (scaling.rs:91-118, CFA mode).  Columns k >= nx
+// of a narrower window (frame edge, or a lane whose window is narrower than its warp's) get weight 0 and re-read the
+// window's last column: they add (+-0, 0) to the accumulators, which changes neither a sum nor a count (neither is
+// ever -0.0: both start at +0.0).
+template <int NX, bool UNIFORM, int NC>
+__device__ __forceinline__ void window_taps(const ScaledParams &p, const uint8_t *pat, float one, int from_x, int nx,
+                                            int from_y, int to_y, float center_x, float center_y, F2 acc[4]) {
+  const float black = p.black, range = p.range, rc = p.range_rc, skip_x = p.skip_x, skip_y = p.skip_y;
+  float ax[NX];  // 1.0 - delta_x*delta_x of window column k
+#pragma unroll
+  for (int k = 0; k < NX; k++) {
+    const float delta_x = __fdiv_rn((float)(from_x + k) - center_x, skip_x);
+    ax[k] = 1.0f - (delta_x * delta_x);
+  }
+  int ym = from_y % 48;
+  const uint8_t *pcol = pat + from_x % 48;
+  const uint16_t *rowp = p.raw + (long long)(from_y + p.crop_y - p.src_row0) * p.raw_pitch + p.crop_x + from_x;
+  for (int y = from_y; y <= to_y; y++, rowp += p.raw_pitch) {
+    const float delta_y = __fdiv_rn((float)y - center_y, skip_y);
+    const float dy2 = delta_y * delta_y;
+    const uint8_t *prow = pcol + ym * kPatStride;
+    ym = ym == 47 ? 0 : ym + 1;
+#pragma unroll
+    for (int k = 0; k < NX; k++) {
+      const bool valid = UNIFORM || k < nx;
+      float factor = ax[k] - dy2;
+      factor = factor < 0.0f ? 0.0f : factor;
+      if (!UNIFORM) factor = valid ? factor : 0.0f;
+      const int kk = UNIFORM ? k : min(k, nx - 1);
+      const int c = prow[kk];
+      const float v = fminf(div_rc(u16_to_float(__ldg(rowp + kk)) - black, range, rc), 1.0f);  // gofloat.rs:127
+      const F2 prod = pk_mul(F2{v, 1.0f}, splat(factor));  // (v*factor, factor)
+#pragma unroll
+      for (int j = 0; j < NC; j++) pk_add_if(acc[j], prod, one, c == j);
+    }
+  }
+}
+
 // k_fused_scaled: one output pixel per thread (scaling.rs:76-127 with the CFA binning of :109-112), then the colour
 // chain.  The reference's per-tap arithmetic is kept expression by expression; what is shared between taps is
 // computed once: delta_x and 1 - delta_x^2 per window column (the reference recomputes them for every row),
 // delta_y^2 per window row.  A colour's weighted sum and weight sum travel as one packed f32x2 accumulator:
-// (v, 1) * (f, f) = (v*f, f) is one FMUL2 and the two additions one packed add, each half rounded exactly like the
-// reference's scalar `sums[c] += v*f; counts[c] += f` — and in the same tap order.
+// (v, 1) * (f, f) = (v*f, f) is one FMUL2 and the two additions one predicated packed add, each half rounded exactly
+// like the reference's scalar `sums[c] += v*f; counts[c] += f` — and in the same tap order.  The window loop is
+// unrolled for the warp's widest window (5 columns at 4x; 6 and 8 as fall-backs), without per-lane predication when
+// every lane has that width.
 template <int OUT>
 __global__ void __launch_bounds__(kNTScaled, 1)
 k_fused_scaled(const __grid_constant__ ScaledParams p, const __grid_constant__ CfaDev cfa,
@@ -669,18 +721,22 @@ k_fused_scaled(const __grid_constant__ ScaledParams p, const __grid_constant__ C
   extern __shared__ __align__(16) unsigned char smem_raw[];
   SmemScaled &sm = *reinterpret_cast<SmemScaled *>(smem_raw);
   load_luts(sm.lut_lab, sm.lut_gamma, p.lut_lab, p.lut_gamma);
+  bool has_e = false;
   for (int i = threadIdx.x; i < 48 * kPatStride; i += blockDim.x) {
     const int r = i / kPatStride, c = i - r * kPatStride;
     sm.pat[i] = cfa.pat[r * 48 + (c % 48)];
+    has_e |= sm.pat[i] >= 3;
   }
-  __syncthreads();
+  const bool four = __syncthreads_or(has_e) != 0;  // a fourth colour somewhere in the pattern
   const LutShared lab{smem_u32(sm.lut_lab)}, gam{smem_u32(sm.lut_gamma)};
-  const PkAdd pk{P.one, P.mone};
 
   const long long npix = (long long)(p.out_row1 - p.out_row0) * p.nwidth;
-  for (long long idx = (long long)blockIdx.x * kNTScaled + threadIdx.x; idx < npix;
+  const long long npix_pad = (npix + 31) / 32 * 32;  // whole warps stay in the loop (warp-wide votes below)
+  for (long long idx = (long long)blockIdx.x * kNTScaled + threadIdx.x; idx < npix_pad;
        idx += (long long)gridDim.x * kNTScaled) {
-    const int row = p.out_row0 + (int)(idx / p.nwidth), col = (int)(idx % p.nwidth);
+    const bool live = idx < npix;
+    const long long id = live ? idx : npix - 1;
+    const int row = p.out_row0 + (int)(id / p.nwidth), col = (int)(id % p.nwidth);
     const float frow = (float)row, frow1 = (float)(row + 1), fcol = (float)col, fcol1 = (float)(col + 1);
     // scaling.rs:77-89 with topleft = (0,0), skip_x_y = skip_y_x = 0
     const float rfrom_x = 0.0f + 0.0f * frow;
@@ -698,37 +754,18 @@ k_fused_scaled(const __grid_constant__ ScaledParams p, const __grid_constant__ C
     const int nx = to_x - from_x + 1;
 
     F2 acc[4] = {F2{0.f, 0.f}, F2{0.f, 0.f}, F2{0.f, 0.f}, F2{0.f, 0.f}};  // {sums[c], counts[c]}
-    if (nx <= kMaxCols) {
-      float ax[kMaxCols];  // 1.0 - delta_x*delta_x of window column k
-#pragma unroll
-      for (int k = 0; k < kMaxCols; k++) {
-        const float delta_x = __fdiv_rn((float)(from_x + k) - center_x, p.skip_x);
-        ax[k] = 1.0f - (delta_x * delta_x);
-      }
-      const int xm0 = from_x % 48;
-      int ym = from_y % 48;
-      const uint16_t *rowp = p.raw + (long long)(from_y + p.crop_y - p.src_row0) * p.raw_pitch + p.crop_x + from_x;
-      for (int y = from_y; y <= to_y; y++, rowp += p.raw_pitch) {
-        const float delta_y = __fdiv_rn((float)y - center_y, p.skip_y);
-        const float dy2 = delta_y * delta_y;
-        const uint8_t *prow = sm.pat + ym * kPatStride + xm0;
-        ym = ym == 47 ? 0 : ym + 1;
-#pragma unroll
-        for (int k = 0; k < kMaxCols; k++) {
-          if (k < nx) {
-            float factor = ax[k] - dy2;
-            factor = factor < 0.0f ? 0.0f : factor;
-            const int c = prow[k];
-            const float v = golevel((float)__ldg(rowp + k), p.black, p.range, p.range_rc, p.exact_rc);
-            const F2 prod = pk_mul(F2{v, 1.0f}, splat(factor));  // (v*factor, factor)
-#pragma unroll
-            for (int j = 0; j < 4; j++)
-              if (c == j) acc[j] = pk.add(acc[j], prod);
-          }
-        }
-      }
+    const int nx_max = __reduce_max_sync(kFull, nx), nx_min = __reduce_min_sync(kFull, nx);
+    if (nx_max <= kMaxCols && p.exact_rc && !four) {
+      if (nx_max == 5 && nx_min == 5)
+        window_taps<5, true, 3>(p, sm.pat, P.one, from_x, nx, from_y, to_y, center_x, center_y, acc);
+      else if (nx_max <= 6)
+        window_taps<6, false, 3>(p, sm.pat, P.one, from_x, nx, from_y, to_y, center_x, center_y, acc);
+      else
+        window_taps<kMaxCols, false, 3>(p, sm.pat, P.one, from_x, nx, from_y, to_y, center_x, center_y, acc);
+    } else if (nx_max <= kMaxCols && p.exact_rc) {
+      window_taps<kMaxCols, false, 4>(p, sm.pat, P.one, from_x, nx, from_y, to_y, center_x, center_y, acc);
     } else {
-      // wide windows (scale >= 7): the plain loop
+      // wide windows (scale >= 7) or a level mapping that needs IEEE division: the plain loop
       for (int y = from_y; y <= to_y; y++) {
         const float delta_y = __fdiv_rn((float)y - center_y, p.skip_y);
         const float dy2 = delta_y * delta_y;
@@ -751,7 +788,7 @@ k_fused_scaled(const __grid_constant__ ScaledParams p, const __grid_constant__ C
     for (int k = 0; k < 4; k++) px[k] = acc[k].y > 0.0f ? __fdiv_rn(acc[k].x, acc[k].y) : 0.0f;
     float r[4] = {0.f, 0.f, 0.f, 0.f}, g[4] = {0.f, 0.f, 0.f, 0.f}, b[4] = {0.f, 0.f, 0.f, 0.f};
     color_chain<true>(P, lab, gam, px[0], px[1], px[2], px[3], r[0], g[0], b[0]);
-    store_px4<OUT>(p.out, (size_t)(idx), 1, r, g, b);
+    if (live) store_px4<OUT>(p.out, (size_t)(idx), 1, r, g, b);
   }
 }
 
