@@ -56,6 +56,8 @@ struct FullParams {
   int pw, ph;                   // CFA period
   int use_tma;
   int gamma8;                   // lut_out is the 8-bit threshold table
+  uint32_t g8_bias;             // 0x4B000000 << 3 (mod 2^32), as a run-time value: ptxas would otherwise split the
+                                // constant off the shift-add that forms a threshold-table address (two instructions)
 };
 
 struct Smem {
@@ -135,6 +137,24 @@ __device__ __forceinline__ float bin_mean(uint32_t m, const float v[9]) {
 #pragma unroll
   for (int i = 0; i < 9; i++) s = s + (((m >> i) & 1u) ? v[i] : 0.0f);
   return __fdiv_rn(s, (float)__popc(m));
+}
+
+// {1/n rounded to nearest, n} for tap counts n = 0..9 (entry 0 divides the empty sum by 1: +0.0)
+__constant__ float2 kTapRcp[10] = {{0.0f, 1.0f}, {1.0f, 1.0f}, {0.5f, 2.0f}, {1.0f / 3.0f, 3.0f}, {0.25f, 4.0f},
+                                   {1.0f / 5.0f, 5.0f}, {1.0f / 6.0f, 6.0f}, {1.0f / 7.0f, 7.0f}, {0.125f, 8.0f},
+                                   {1.0f / 9.0f, 9.0f}};
+
+// The same bin for a pixel whose nine taps are all inside the frame, without the IEEE division: the sum over the
+// selected taps in the reference's order (predicated adds), then s / n through the 3-instruction reciprocal form,
+// which equals IEEE division for every divisor 1..9 (tools/verify_constdiv.c; sums of level-mapped samples are zero
+// or normal numbers).
+__device__ __forceinline__ float bin_mean_rc(uint32_t m, const float v[9]) {
+  float s = 0.0f;
+#pragma unroll
+  for (int i = 0; i < 9; i++)
+    if ((m >> i) & 1u) s = s + v[i];
+  const float2 e = kTapRcp[__popc(m)];
+  return div_rc(s, e.y, e.x);
 }
 
 template <int OUT>
@@ -228,10 +248,12 @@ __device__ __forceinline__ float lerp_fetch(uint32_t lut_base, float tf, float a
 // cubic of the segment that starts there gives y exactly, like the reference's early return.  The fused launch is
 // gated on finite inputs and strictly increasing knots (ipb_host.cu fused_params_bounded), so NaN never gets here.
 __device__ __forceinline__ float spline_eval_smem(const float (*spl)[8], const SplineDev &s, float val) {
-  int idx = (val >= s.x[0] ? 1 : 0) + (val >= s.x[1] ? 1 : 0);
-  if (s.n > 2) {
-    idx += val >= s.x[2] ? 1 : 0;
-    for (int j = 3; j < s.n; j++) idx += val >= s.x[j] ? 1 : 0;
+  int idx;
+  if (s.n == 3) {  // the raw default: one interior knot (curves.rs:14-20)
+    idx = val >= s.x[1] ? (val >= s.x[2] ? 3 : 2) : (val >= s.x[0] ? 1 : 0);
+  } else {
+    idx = (val >= s.x[0] ? 1 : 0) + (val >= s.x[1] ? 1 : 0);
+    for (int j = 2; j < s.n; j++) idx += val >= s.x[j] ? 1 : 0;
   }
   const float4 c = *reinterpret_cast<const float4 *>(spl[idx]);
   const float c3 = spl[idx][4];
@@ -310,7 +332,8 @@ __device__ __forceinline__ int lab_lookup4(const PkAdd &pk, uint32_t lab_base, f
 // Lab from the transfer-function values, basecurve, from_lab (+ gamma) for two pixels
 template <int OUT>
 __device__ __forceinline__ void lab_to_output_pair(const ColorParams &P, const PkAdd &pk, const Smem &sm,
-                                                   uint32_t out_base, bool g8, F2 fx, F2 fy, F2 fz, float orr[2],
+                                                   uint32_t out_base, uint32_t g8_bias, bool g8, F2 fx, F2 fy, F2 fz,
+                                                   float orr[2],
                                                    float og[2], float ob[2], uint32_t q8[6]) {
   F2 l = pk.add(pk_mul(fy, 116.0f), -16.0f);
   F2 a = pk_mul(pk.sub(fx, fy), 500.0f);
@@ -354,7 +377,7 @@ __device__ __forceinline__ void lab_to_output_pair(const ColorParams &P, const P
     const F2 tr = pk.add_rm(pk_mul(vr, kLutMax), 8388608.0f);
     const F2 tg = pk.add_rm(pk_mul(vg, kLutMax), 8388608.0f);
     const F2 tb = pk.add_rm(pk_mul(vb, kLutMax), 8388608.0f);
-    const uint32_t bias = out_base - 0x58000000u;
+    const uint32_t bias = out_base - g8_bias;
     q8[0] = gamma8_fetch(bias, tr.x, vr.x);
     q8[1] = gamma8_fetch(bias, tg.x, vg.x);
     q8[2] = gamma8_fetch(bias, tb.x, vb.x);
@@ -548,23 +571,31 @@ k_fused_full(const __grid_constant__ FullParams p, const __grid_constant__ CfaDe
         // With TMA staging the tile holds whatever lies outside the cropped frame; the masks never select it.
         const int pr = y % p.ph;
         int pc = x0 % p.pw;
+        const bool inside = __all_sync(kFull, !live || interior);  // no tap of the warp's pixels leaves the frame
 #pragma unroll
         for (int j = 0; j < 4; j++) {
           const int x = x0 + j;
-          uint32_t valid = 0x1ffu;
-          if (y <= 0) valid &= ~0x007u;
-          if (y >= p.height - 1) valid &= ~0x1c0u;
-          if (x <= 0) valid &= ~0x049u;
-          if (x >= p.width - 1) valid &= ~0x124u;
           const uint2 mm = sm.taps[pr * p.pw + pc];
           pc = (pc + 1 == p.pw) ? 0 : pc + 1;
           float v[9];
 #pragma unroll
           for (int k = 0; k < 3; k++) { v[k * 3] = w[k][j]; v[k * 3 + 1] = w[k][j + 1]; v[k * 3 + 2] = w[k][j + 2]; }
-          cr[j] = bin_mean(mm.x & 0xffffu & valid, v);
-          cg[j] = bin_mean((mm.x >> 16) & valid, v);
-          cb[j] = bin_mean(mm.y & 0xffffu & valid, v);
-          ce[j] = bin_mean((mm.y >> 16) & valid, v);
+          if (inside) {
+            cr[j] = bin_mean_rc(mm.x & 0xffffu, v);
+            cg[j] = bin_mean_rc(mm.x >> 16, v);
+            cb[j] = bin_mean_rc(mm.y & 0xffffu, v);
+            ce[j] = P.use_e ? bin_mean_rc(mm.y >> 16, v) : 0.0f;
+          } else {
+            uint32_t valid = 0x1ffu;
+            if (y <= 0) valid &= ~0x007u;
+            if (y >= p.height - 1) valid &= ~0x1c0u;
+            if (x <= 0) valid &= ~0x049u;
+            if (x >= p.width - 1) valid &= ~0x124u;
+            cr[j] = bin_mean(mm.x & 0xffffu & valid, v);
+            cg[j] = bin_mean((mm.x >> 16) & valid, v);
+            cb[j] = bin_mean(mm.y & 0xffffu & valid, v);
+            ce[j] = bin_mean((mm.y >> 16) & valid, v);
+          }
         }
       }
 
@@ -595,9 +626,9 @@ k_fused_full(const __grid_constant__ FullParams p, const __grid_constant__ CfaDe
         }
         __syncwarp();
       }
-      lab_to_output_pair<OUT>(P, pk, sm, out_base, g8, F2{fxs[0], fxs[1]}, F2{fys[0], fys[1]}, F2{fzs[0], fzs[1]}, orr, og,
+      lab_to_output_pair<OUT>(P, pk, sm, out_base, p.g8_bias, g8, F2{fxs[0], fxs[1]}, F2{fys[0], fys[1]}, F2{fzs[0], fzs[1]}, orr, og,
                               ob, q8);
-      lab_to_output_pair<OUT>(P, pk, sm, out_base, g8, F2{fxs[2], fxs[3]}, F2{fys[2], fys[3]}, F2{fzs[2], fzs[3]}, orr + 2,
+      lab_to_output_pair<OUT>(P, pk, sm, out_base, p.g8_bias, g8, F2{fxs[2], fxs[3]}, F2{fys[2], fys[3]}, F2{fzs[2], fzs[3]}, orr + 2,
                               og + 2, ob + 2, q8 + 6);
       if (live) {
         const size_t pix = (size_t)(y - p.out_row0) * p.width + x0;
@@ -921,6 +952,7 @@ cudaError_t launch_fused_full(cudaStream_t s, const FusedArgs &a, const CfaDev &
   p.lut_lab = a.lut_lab;
   p.gamma8 = (a.out_kind == kOutU8 && !P.linear && a.lut_gamma8) ? 1 : 0;
   p.lut_out = p.gamma8 ? a.lut_gamma8 : a.lut_gamma;
+  p.g8_bias = 0x58000000u;
   p.tiles_x = (p.width + kTW - 1) / kTW;
   p.tiles_y = (p.out_row1 - p.out_row0 + kTH - 1) / kTH;
   p.pw = cfa.width; p.ph = cfa.height;

@@ -30,6 +30,6 @@ int main(void) {
   bad += check(0.95047f, "white_x"); bad += check(1.08883f, "white_z"); bad += check(100.0f, "100");
   bad += check(255.0f, "255"); bad += check(116.0f, "116"); bad += check(500.0f, "500");
   bad += check(200.0f, "200"); bad += check(k, "k"); bad += check(65535.0f, "65535"); bad += check(12.92f, "12.92");
-  bad += check(3.0f, "3");
+  bad += check(3.0f, "3"); bad += check(5.0f, "5"); bad += check(6.0f, "6"); bad += check(7.0f, "7"); bad += check(9.0f, "9");
   return bad != 0;
 }
