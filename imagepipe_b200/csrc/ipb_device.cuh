@@ -195,27 +195,25 @@ __device__ __forceinline__ void camera_to_lab(const ColorParams &P, const Lut &l
   ob = divc<RC>(bb + 127.0f, 255.0f);
 }
 
-// SplineFunc::interpolate — curves.rs:126-157.  The binary search over points[0..nseg) ends at the last
-// knot strictly below val, or returns y exactly on a knot; the cubic evaluated at diff == 0 gives the
-// same y, so the segment is "last knot <= val".  NaN falls through every comparison of the reference's
-// search and returns y[(nseg-1)/2].
+// SplineFunc::interpolate — curves.rs:126-157, statement by statement, including the binary search over
+// points[0..nseg): for sorted knots it ends at the last knot below val (or returns y exactly on a knot); for unsorted
+// knots and NaN it does whatever the reference's search does (NaN fails every comparison and returns y[(nseg-1)/2]).
+// Used by the per-op kernels; the fused kernels take sorted knots only (ipb_fused.cu spline_eval_smem).
 __device__ __forceinline__ float spline_eval(const SplineDev &s, float val) {
   const int last = s.n - 1;
-  float xi = s.x[0], yi = s.y[0], c1 = s.c1[0], c2 = s.c2[0], c3 = s.c3[0];
-  for (int j = 1; j < s.nseg; j++) {
-    bool ge = val >= s.x[j];
-    xi = ge ? s.x[j] : xi;
-    yi = ge ? s.y[j] : yi;
-    c1 = ge ? s.c1[j] : c1;
-    c2 = ge ? s.c2[j] : c2;
-    c3 = ge ? s.c3[j] : c3;
+  if (val >= s.x[last]) return s.y[last];
+  if (val <= s.x[0]) return s.y[0];
+  int low = 0, high = s.nseg - 1;
+  while (low <= high) {
+    const int mid = (low + high) / 2;
+    const float xhere = s.x[mid];
+    if (xhere < val) low = mid + 1;
+    else if (xhere > val) high = mid - 1;
+    else return s.y[mid];
   }
-  float diff = val - xi;
-  float res = yi + c1 * diff + c2 * diff * diff + c3 * diff * diff * diff;
-  res = (val <= s.x[0]) ? s.y[0] : res;
-  res = (val >= s.x[last]) ? s.y[last] : res;
-  res = (val != val) ? s.y[(s.nseg - 1) / 2] : res;
-  return res;
+  const int i = high > 0 ? high : 0;
+  const float diff = val - s.x[i];
+  return s.y[i] + s.c1[i] * diff + s.c2[i] * diff * diff + s.c3[i] * diff * diff * diff;
 }
 
 // lab_to_xyz + lab_to_rgb — color_conversions.rs:58-65,172-191
