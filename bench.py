@@ -167,25 +167,51 @@ def run_c5(args, ip, common, torch, dist, ctx, stream, barrier, rank, world, loc
         for j in range(F):
             b, o = bufs[j % nsets], outs[j % nsets]
             if world > 1:
-                exchange_halos(b, lays, rank)
+                exchange_halos(b, lays, rank)   # NCCL send/recv of the stencil rows, on the launching stream
             run_stripe_8bit(p, b.data_ptr(), me, DevicePtr(o.data_ptr(), o.numel()))
 
     with torch.cuda.stream(stream):
         for _ in range(Wm):
             step()
     barrier()
+    # One step (F frames: exchange + fused launch each) is captured into a CUDA graph and replayed: at 8 GPUs a stripe
+    # takes ~0.15 ms and the Python / NCCL-group host path per frame (~0.2 ms) would otherwise be the bottleneck.
+    graph, mode = None, "eager"
+    if not args.no_graph:
+        try:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=stream, capture_error_mode="thread_local"):
+                step()
+            graph, mode = g, "cuda graph of one step"
+        except Exception as e:  # noqa: BLE001
+            print(f"bench.py: graph capture failed on rank {rank} ({e}); running eagerly", file=sys.stderr)
+            torch.cuda.synchronize()
+    modes = [None] * world
+    if world > 1:
+        dist.all_gather_object(modes, mode)
+        if any(m != modes[0] for m in modes) or modes[0] == "eager":
+            graph, mode = None, "eager"   # all ranks must agree, or the exchange would not pair up
+
+    def run_step():
+        if graph is not None:
+            graph.replay()
+        else:
+            step()
+
+    with torch.cuda.stream(stream):
+        run_step()
+    barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
-    launches0 = ctx.launch_count
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
     with torch.cuda.stream(stream):
         ev[0].record(stream)
         for _ in range(K):
-            step()
+            run_step()
         ev[1].record(stream)
     barrier()
     clocks = sampler.stop()
-    launches = ctx.launch_count - launches0
+    launches = K * F   # one fused launch per frame (replayed from the graph when mode says so)
     t = torch.tensor([ev[0].elapsed_time(ev[1])], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -223,7 +249,8 @@ def run_c5(args, ip, common, torch, dist, ctx, stream, barrier, rank, world, loc
                        "frames_per_step": F, "buffer_sets": nsets, "stripe_rows": rows_out,
                        "halo_rows": (me.own_row0 - me.src_row0) + (me.src_row1 - me.own_row1),
                        "l2": f"inputs larger than L2: {nsets} rotating sets x {set_bytes / 1e6:.0f} MB per GPU",
-                       "parallelism": f"{world} row stripe(s), send/recv of stencil rows between neighbours"},
+                       "launch": mode,
+                                      "parallelism": f"{world} row stripe(s), send/recv of stencil rows between neighbours"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": None, "kernel": "k_fused_full<u8> (one stripe, exchange included in the time)",
                          "kernel_ms": launch_ms, "peak_kind": peak_kind,
@@ -245,6 +272,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--frames-per-step", type=int, default=None)
+    ap.add_argument("--no-graph", action="store_true", help="c5: launch every frame from Python instead of replaying a CUDA graph")
     ap.add_argument("--workload", default="c2", choices=["c2", "c5"],
                     help="c2 (default, the contract's line): 24 MP frames, replicas; c5: one 101.8 MP frame per step-frame, "
                          "row stripes over the ranks with an NCCL halo exchange (strong scaling)")
