@@ -95,31 +95,30 @@ def plan_stripes(ops, settings, width, height, world, multiple=32):
 def exchange_halos(buf, layouts, rank, group=None):
     """Fill the halo rows of `buf` — a 2-D torch tensor (rows src_row0..src_row1 of the frame, any dtype, one row of
     samples per tensor row) whose own block is already in place — from the neighbouring ranks, and send them theirs.
-    One batched isend/irecv per boundary; returns after the transfers are complete (on the GPU: enqueued on the
-    current stream, which then waits for them — no host synchronisation)."""
+    `buf` may also be a list of such tensors (several frames with the same layout): all their rows travel in ONE
+    batched isend/irecv group, which amortises the NCCL launch latency over the frames (the messages are tiny:
+    one or two rows).  Returns after the transfers are complete (on the GPU: enqueued on the current stream, which
+    then waits for them — no host synchronisation)."""
     import torch
     import torch.distributed as dist
     me = layouts[rank]
+    bufs = list(buf) if isinstance(buf, (list, tuple)) else [buf]
     ops = []
-    if buf.element_size() != 1:  # NCCL has no 16-bit integer type: move the rows as bytes
-        buf = buf.view(torch.uint8)
-
-    def rows(lay_from, a, b):  # view of my buffer for frame rows [a, b)
-        return buf[a - me.src_row0: b - me.src_row0]
-
     for nb in (rank - 1, rank + 1):
         if nb < 0 or nb >= len(layouts):
             continue
         other = layouts[nb]
-        # what the neighbour needs from my own block
-        a, b = (other.halo_down if nb < rank else other.halo_up)
-        a, b = max(a, me.own_row0), min(b, me.own_row1)
-        if b > a:
-            ops.append(dist.P2POp(dist.isend, rows(me, a, b), nb, group))
-        # what I need from the neighbour's own block
-        a, b = (me.halo_up if nb < rank else me.halo_down)
-        if b > a:
-            ops.append(dist.P2POp(dist.irecv, rows(me, a, b), nb, group))
+        # what the neighbour needs from my own block / what I need from the neighbour's own block
+        sa, sb = (other.halo_down if nb < rank else other.halo_up)
+        sa, sb = max(sa, me.own_row0), min(sb, me.own_row1)
+        ra, rb = (me.halo_up if nb < rank else me.halo_down)
+        for b in bufs:
+            if b.element_size() != 1:  # NCCL has no 16-bit integer type: move the rows as bytes
+                b = b.view(torch.uint8)
+            if sb > sa:
+                ops.append(dist.P2POp(dist.isend, b[sa - me.src_row0: sb - me.src_row0], nb, group))
+            if rb > ra:
+                ops.append(dist.P2POp(dist.irecv, b[ra - me.src_row0: rb - me.src_row0], nb, group))
     if ops:
         for w in dist.batch_isend_irecv(ops):
             w.wait()

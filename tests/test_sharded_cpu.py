@@ -116,9 +116,15 @@ def _halo_worker(rank, world, port, case, ret):
         buf = torch.full((me.src_row1 - me.src_row0, w), 0x7FFF, dtype=torch.int16)
         own = torch.from_numpy(frame[me.own_row0:me.own_row1].view(np.int16).copy())
         buf[me.own_row0 - me.src_row0: me.own_row1 - me.src_row0] = own
-        exchange_halos(buf, lays, rank)
+        # a second frame with the same layout travels in the same batched group
+        frame2 = common.synth_cfa(w, h, seed=common.SEED + 9)
+        buf2 = torch.full((me.src_row1 - me.src_row0, w), 0x7FFF, dtype=torch.int16)
+        buf2[me.own_row0 - me.src_row0: me.own_row1 - me.src_row0] = torch.from_numpy(
+            frame2[me.own_row0:me.own_row1].view(np.int16).copy())
+        exchange_halos([buf, buf2], lays, rank)
         got = buf.numpy().view(np.uint16)
-        ok = bool(np.array_equal(got, frame[me.src_row0:me.src_row1]))
+        ok = bool(np.array_equal(got, frame[me.src_row0:me.src_row1])) and \
+            bool(np.array_equal(buf2.numpy().view(np.uint16), frame2[me.src_row0:me.src_row1]))
         halo_rows = (me.own_row0 - me.src_row0) + (me.src_row1 - me.own_row1)
         flags = torch.tensor([int(ok), halo_rows])
         gathered = [torch.zeros_like(flags) for _ in range(world)]
