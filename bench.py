@@ -41,6 +41,16 @@ def workload_params():
     return common.raw_params(cfa=CFA)
 
 
+def measured_traffic(key):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu capture (profiles/traffic.json), or None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            e = json.load(f)[key]
+        return e["dram_read_bytes"] + e["dram_write_bytes"]
+    except Exception:
+        return None
+
+
 def measured_peak():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -420,7 +430,8 @@ def main():
                        "l2": f"inputs larger than L2: {NSETS} rotating sets x 120 MB",
                        "parallelism": f"frames round-robin, {world} replica(s), no collective"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "kernel": "k_fused_full<u8>", "kernel_ms": kernel_ms, "peak_kind": peak_kind,
+                         "traffic": measured_traffic("k_fused_full<u8> C2 6000x4000"), "kernel": "k_fused_full<u8>",
+                         "kernel_ms": kernel_ms, "peak_kind": peak_kind,
                          "algorithmic_bytes_per_launch": ALGO_BYTES_PER_PX * W * H},
             "e2e": {"value": e2e_value, "unit": "MP/s", "h2d_bytes_per_step": e2e_frames * W * H * 2,
                     "d2h_bytes_per_step": e2e_frames * W * H * 3, "steps": e2e_steps, "frames_per_step": e2e_frames,
