@@ -5,7 +5,7 @@ C-ABI library libipb200.so (include/ipb200.h, sources in csrc/).  Nothing here c
 """
 from ._capi import IpbError, LIB_PATH, lib  # noqa: F401
 from .pipeline import (Context, DeviceArray, ImageSource, OpBaseCurve, OpBuffer, OpDemosaic, OpFromLab,  # noqa: F401
-                       OpGamma, OpGoFloat, OpRotateCrop, OpToLab, OpTransform, Pipeline, PipelineGlobals,
+                       OpGamma, OpGoFloat, OpRotateCrop, OpToLab, OpTransform, Pipeline, PipelineCache, PipelineGlobals,
                        PipelineOps, PipelineSettings, Rotation, SplineFunc, SRGBImage, SRGBImage16,
                        calculate_scale, default_context, rotate_buffer, scale_down_srgb, scaling_size,
                        synth_cfa_u16)

@@ -142,6 +142,13 @@ def lib():
         "ipb_pipeline_set_fused": (i, [vp, i]),
         "ipb_pipeline_output_size": (i, [vp, szp, szp]),
         "ipb_pipeline_run": (i, [vp, vpp]),
+        "ipb_cache_create": (i, [vp, sz, vpp]),
+        "ipb_cache_destroy": (None, [vp]),
+        "ipb_cache_clear": (None, [vp]),
+        "ipb_cache_bytes": (sz, [vp]),
+        "ipb_cache_entries": (sz, [vp]),
+        "ipb_pipeline_run_cached": (i, [vp, vp, vpp]),
+        "ipb_pipeline_last_run_info": (None, [vp, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
         "ipb_pipeline_output_8bit": (i, [vp, vp, sz, i, szp, szp]),
         "ipb_pipeline_output_16bit": (i, [vp, vp, sz, i, szp, szp]),
         "ipb_pipeline_stripe_rows": (i, [vp, sz, sz, szp, szp]),

@@ -69,6 +69,23 @@ struct ipb_pipeline {
   size_t stage_in_bytes = 0;
   void *stage_out = nullptr;
   size_t stage_out_bytes = 0;
+  // last run with a cache: first op executed (8 = everything came from the cache) and number of ops executed
+  int last_startpos = 0, last_ops_run = 0;
+};
+
+// Pipeline::new_cache (pipeline.rs:257-260): size-bounded LRU of device OpBuffers keyed by the cumulative hash of
+// the settings and the op parameters up to and including the op that produced the buffer (pipeline.rs:340-361).
+struct ipb_cache {
+  struct Key {
+    uint64_t a = 0, b = 0;
+    bool operator==(const Key &o) const { return a == o.a && b == o.b; }
+  };
+  struct Entry { Key key; ipb_buffer *buf; size_t bytes; };
+  ipb_ctx *ctx = nullptr;
+  size_t max_bytes = 0, bytes = 0;
+  std::vector<Entry> lru;  // front = least recently used
+  std::mutex mu;           // the reference shares one cache between pipelines on different threads
+  unsigned long long hits = 0, misses = 0;
 };
 
 namespace {
@@ -1513,6 +1530,174 @@ int ipb_pipeline_run(ipb_pipeline *p, ipb_buffer **out) {
   if (rc != IPB_OK) return rc;
   *out = t;
   return IPB_OK;
+}
+
+// ---- Pipeline::run(Some(&cache)) — pipeline.rs:340-372
+
+extern "C++" {
+namespace {
+
+// Two independent 64-bit FNV-1a style streams: the keys never leave the process, so the hash only has to be
+// collision-free in practice (the reference uses blake3 over bincode for the same purpose, hasher.rs:12-47).
+struct ChainHash {
+  uint64_t a = 0xcbf29ce484222325ull, b = 0x84222325cbf29ce4ull;
+  void bytes(const void *p, size_t n) {
+    const unsigned char *c = (const unsigned char *)p;
+    for (size_t i = 0; i < n; i++) {
+      a = (a ^ c[i]) * 0x100000001b3ull;
+      b = (b ^ (c[i] + 0x9e)) * 0x9e3779b97f4a7c15ull;
+      b ^= b >> 29;
+    }
+  }
+  template <class T> void pod(const T &v) { bytes(&v, sizeof(v)); }
+  void name(const char *s) { bytes(s, strlen(s)); }  // ImageOp::hash writes the op name first (pipeline.rs:88-92)
+  ipb_cache::Key key() const { ipb_cache::Key k; k.a = a; k.b = b; return k; }
+};
+
+ipb_buffer *cache_get(ipb_cache *c, const ipb_cache::Key &k) {
+  std::lock_guard<std::mutex> g(c->mu);
+  for (size_t i = 0; i < c->lru.size(); i++)
+    if (c->lru[i].key == k) {
+      ipb_cache::Entry e = c->lru[i];
+      c->lru.erase(c->lru.begin() + i);
+      c->lru.push_back(e);  // most recently used
+      c->hits++;
+      ipb_buffer_retain(e.buf);
+      return e.buf;
+    }
+  c->misses++;
+  return nullptr;
+}
+
+void cache_put(ipb_cache *c, const ipb_cache::Key &k, ipb_buffer *buf) {
+  const size_t bytes = buf->width * buf->height * buf->colors * 4;  // pipeline.rs:369
+  std::lock_guard<std::mutex> g(c->mu);
+  for (size_t i = 0; i < c->lru.size(); i++)
+    if (c->lru[i].key == k) {
+      ipb_buffer_release(c->lru[i].buf);
+      c->bytes -= c->lru[i].bytes;
+      c->lru.erase(c->lru.begin() + i);
+      break;
+    }
+  if (bytes > c->max_bytes) return;  // would evict everything and still not fit
+  while (c->bytes + bytes > c->max_bytes && !c->lru.empty()) {
+    ipb_buffer_release(c->lru.front().buf);
+    c->bytes -= c->lru.front().bytes;
+    c->lru.erase(c->lru.begin());
+  }
+  ipb_buffer_retain(buf);
+  ipb_cache::Entry e;
+  e.key = k; e.buf = buf; e.bytes = bytes;
+  c->lru.push_back(e);
+  c->bytes += bytes;
+}
+
+}  // namespace
+}  // extern "C++"
+
+int ipb_cache_create(ipb_ctx *ctx, size_t max_bytes, ipb_cache **out) {
+  if (!ctx || !out) return IPB_ERR_INVALID;
+  ipb_cache *c = new (std::nothrow) ipb_cache();
+  if (!c) return fail(ctx, IPB_ERR_NOMEM, "out of host memory");
+  c->ctx = ctx;
+  c->max_bytes = max_bytes;
+  *out = c;
+  return IPB_OK;
+}
+
+void ipb_cache_clear(ipb_cache *c) {
+  if (!c) return;
+  std::lock_guard<std::mutex> g(c->mu);
+  for (auto &e : c->lru) ipb_buffer_release(e.buf);
+  c->lru.clear();
+  c->bytes = 0;
+}
+
+void ipb_cache_destroy(ipb_cache *c) {
+  if (!c) return;
+  ipb_cache_clear(c);
+  delete c;
+}
+
+size_t ipb_cache_bytes(const ipb_cache *c) { return c ? c->bytes : 0; }
+size_t ipb_cache_entries(const ipb_cache *c) { return c ? c->lru.size() : 0; }
+
+int ipb_pipeline_run_cached(ipb_pipeline *p, ipb_cache *cache, ipb_buffer **out) {
+  if (!p || !out) return IPB_ERR_INVALID;
+  if (!cache) return ipb_pipeline_run(p, out);
+  ipb_ctx *ctx = p->ctx;
+  IPB_TRY(enter(ctx));
+  if (cache->ctx != ctx) return fail(ctx, IPB_ERR_INVALID, "the cache belongs to another context (device buffers are per context)");
+  if (p->image.width < 10 || p->image.height < 10) return fail(ctx, IPB_ERR_INVALID, "source smaller than 10x10");
+  if (p->has_stripe) return fail(ctx, IPB_ERR_UNSUPPORTED, "pipeline_run on a stripe source: use output_8bit_stripe");
+  negotiate(p, nullptr, nullptr);
+  // the hash chain: settings first (pipeline.rs:346), then every op cumulatively (:350-361).  The source's identity
+  // is hashed too (the reference leaves that to the caller: one cache per image).
+  ChainHash h;
+  const ipb_settings &st = p->settings;
+  h.pod(st.maxwidth); h.pod(st.maxheight); h.pod(st.demosaic_width); h.pod(st.demosaic_height);
+  h.pod(st.linear); h.pod(st.use_fastpath);
+  h.pod(p->image.kind); h.pod(p->image.width); h.pod(p->image.height); h.pod(p->image.cpp); h.pod(p->image.data);
+  ipb_cache::Key keys[8];
+  const ipb_ops &o = p->ops;
+  h.name("gofloat");
+  h.pod(o.gofloat.crop_top); h.pod(o.gofloat.crop_right); h.pod(o.gofloat.crop_bottom); h.pod(o.gofloat.crop_left);
+  h.pod(o.gofloat.is_cfa); h.pod(o.gofloat.blacklevels); h.pod(o.gofloat.whitelevels);
+  keys[0] = h.key();
+  h.name("demosaic"); h.bytes(o.demosaic.cfa, strnlen(o.demosaic.cfa, sizeof(o.demosaic.cfa)));
+  keys[1] = h.key();
+  h.name("rotatecrop");
+  h.pod(o.rotatecrop.crop_top); h.pod(o.rotatecrop.crop_right); h.pod(o.rotatecrop.crop_bottom);
+  h.pod(o.rotatecrop.crop_left); h.pod(o.rotatecrop.rotation);
+  keys[2] = h.key();
+  h.name("to_lab");
+  h.pod(o.tolab.cam_to_xyz); h.pod(o.tolab.cam_to_xyz_normalized); h.pod(o.tolab.xyz_to_cam); h.pod(o.tolab.wb_coeffs);
+  keys[3] = h.key();
+  h.name("basecurve"); h.pod(o.basecurve.exposure); h.pod(o.basecurve.npoints);
+  for (size_t i = 0; i < o.basecurve.npoints && i < IPB_MAX_CURVE_POINTS; i++) h.pod(o.basecurve.points[i]);
+  keys[4] = h.key();
+  h.name("from_lab");
+  keys[5] = h.key();
+  h.name("gamma");
+  keys[6] = h.key();
+  h.name("transform"); h.pod(o.transform.rotation); h.pod(o.transform.fliph); h.pod(o.transform.flipv);
+  keys[7] = h.key();
+  // the latest op whose output is cached (pipeline.rs:355-360)
+  ipb_buffer *cur = nullptr;
+  int startpos = 0;
+  for (int i = 7; i >= 0 && !cur; i--) {
+    cur = cache_get(cache, keys[i]);
+    if (cur) startpos = i + 1;
+  }
+  p->last_startpos = startpos;
+  p->last_ops_run = 8 - startpos;
+  // the remaining ops, one kernel each, every result into the cache (pipeline.rs:364-371)
+  for (int i = startpos; i < 8; i++) {
+    ipb_buffer *next = nullptr;
+    int rc;
+    switch (i) {
+      case 0: rc = ipb_gofloat_run(ctx, &p->ops.gofloat, &p->image, &next); break;
+      case 1: rc = ipb_demosaic_run(ctx, &p->ops.demosaic, &p->settings, cur, &next); break;
+      case 2: rc = ipb_rotatecrop_run(ctx, &p->ops.rotatecrop, cur, &next); break;
+      case 3: rc = ipb_tolab_run(ctx, &p->ops.tolab, cur, &next); break;
+      case 4: rc = ipb_basecurve_run(ctx, &p->ops.basecurve, cur, &next); break;
+      case 5: rc = ipb_fromlab_run(ctx, cur, &next); break;
+      case 6: rc = ipb_gamma_run(ctx, &p->settings, cur, &next); break;
+      default: rc = ipb_transform_run(ctx, &p->ops.transform, cur, &next); break;
+    }
+    if (cur) ipb_buffer_release(cur);
+    if (rc != IPB_OK) return rc;
+    cur = next;
+    cache_put(cache, keys[i], cur);
+  }
+  *out = cur;
+  return IPB_OK;
+}
+
+void ipb_pipeline_last_run_info(const ipb_pipeline *p, int *startpos, int *ops_run) {
+  if (!p) return;
+  if (startpos) *startpos = p->last_startpos;
+  if (ops_run) *ops_run = p->last_ops_run;
 }
 
 static bool ops_are_default_other(const ipb_pipeline *p) {  // Pipeline::default_ops (pipeline.rs:286-288)

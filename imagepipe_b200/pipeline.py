@@ -409,6 +409,29 @@ SRGBImage16 = SRGBImage
 
 # --------------------------------------------------------------------------------------------- Pipeline
 
+class PipelineCache:
+    """PipelineCache = MultiCache<BufHash, OpBuffer> (src/pipeline.rs:43), holding device buffers."""
+
+    def __init__(self, size, ctx=None):
+        self.ctx = ctx or default_context()
+        self.handle = C.c_void_p()
+        _capi.check(self.ctx.handle, lib().ipb_cache_create(self.ctx.handle, int(size), C.byref(self.handle)))
+
+    bytes = property(lambda s: int(lib().ipb_cache_bytes(s.handle)))
+    entries = property(lambda s: int(lib().ipb_cache_entries(s.handle)))
+
+    def clear(self):
+        lib().ipb_cache_clear(self.handle)
+
+    def __del__(self):
+        try:
+            if self.handle and self.ctx.handle:
+                lib().ipb_cache_destroy(self.handle)
+        except Exception:
+            pass
+        self.handle = None
+
+
 class Pipeline:
     """src/pipeline.rs:245-470.  `globals.settings` and `ops` are live views of the native pipeline object."""
 
@@ -447,10 +470,34 @@ class Pipeline:
         _capi.check(self.ctx.handle, lib().ipb_pipeline_output_size(self.handle, C.byref(w), C.byref(h)))
         return w.value, h.value
 
+    @staticmethod
+    def new_cache(size, ctx=None):
+        """Pipeline::new_cache(size) (pipeline.rs:257-260): a device-resident LRU of op outputs, `size` bytes."""
+        return PipelineCache(size, ctx)
+
     def run(self, cache=None):
+        """Pipeline::run(cache) (pipeline.rs:311-375).  With a cache the ops run one by one from the first op whose
+        parameters changed since a cached run; without, the fused kernel is used when the chain allows it."""
         out = C.c_void_p()
-        _capi.check(self.ctx.handle, lib().ipb_pipeline_run(self.handle, C.byref(out)))
+        if cache is not None:
+            _capi.check(self.ctx.handle, lib().ipb_pipeline_run_cached(self.handle, cache.handle, C.byref(out)))
+        else:
+            _capi.check(self.ctx.handle, lib().ipb_pipeline_run(self.handle, C.byref(out)))
         return OpBuffer(out, self.ctx)
+
+    def last_run_info(self):
+        """(index of the first op the last cached run executed — 8: none —, number of ops executed)"""
+        a, b = C.c_int(), C.c_int()
+        lib().ipb_pipeline_last_run_info(self.handle, C.byref(a), C.byref(b))
+        return a.value, b.value
+
+    def _output_cached(self, cache, pack, dtype, linear):
+        # pipeline.rs:404-421 / :451-468: set settings.linear, run(cache), pack loop
+        self.globals.settings.linear = int(linear)
+        buf = self.run(cache)
+        host = np.empty(buf.width * buf.height * 3, dtype)
+        _capi.check(self.ctx.handle, pack(self.ctx.handle, buf.handle, host.ctypes.data, 0))
+        return SRGBImage(buf.width, buf.height, host)
 
     def _output(self, fn, dtype, dst):
         w, h = self.output_size()
@@ -471,9 +518,13 @@ class Pipeline:
         return SRGBImage(ow.value, oh.value, host)
 
     def output_8bit(self, cache=None, dst=None):
+        if cache is not None:
+            return self._output_cached(cache, lib().ipb_pack_8bit, np.uint8, False)
         return self._output(lib().ipb_pipeline_output_8bit, np.uint8, dst)
 
     def output_16bit(self, cache=None, dst=None):
+        if cache is not None:
+            return self._output_cached(cache, lib().ipb_pack_16bit, np.uint16, True)
         return self._output(lib().ipb_pipeline_output_16bit, np.uint16, dst)
 
     # ---- row stripes (multi-GPU sharding of one large frame; no reference equivalent)

@@ -45,6 +45,7 @@ typedef enum ipb_status {
 typedef struct ipb_ctx ipb_ctx;           /* device + stream + uploaded LUTs/constants */
 typedef struct ipb_buffer ipb_buffer;     /* device-resident OpBuffer (src/buffer.rs:4-11), ref-counted like Arc<OpBuffer> */
 typedef struct ipb_pipeline ipb_pipeline; /* Pipeline (src/pipeline.rs:245-249) */
+typedef struct ipb_cache ipb_cache;       /* PipelineCache = MultiCache<BufHash, OpBuffer> (src/pipeline.rs:43), device-resident */
 
 /* ------------------------------------------------------------------ parameter PODs
  * 1:1 with the reference's serde structs so the Rust side can fill them field by field. */
@@ -249,6 +250,21 @@ int ipb_pipeline_set_band_mb(ipb_pipeline *p, int megabytes);
 int ipb_pipeline_output_size(ipb_pipeline *p, size_t *width, size_t *height);
 /* Pipeline::run(None) — pipeline.rs:311-375; result is a 3-channel f32 OpBuffer */
 int ipb_pipeline_run(ipb_pipeline *p, ipb_buffer **out);
+/* Pipeline::new_cache(size) — pipeline.rs:257-260: a size-bounded (bytes of f32 data, as the reference counts them,
+ * :369) least-recently-used cache of device OpBuffers.  One cache may serve several pipelines and threads of the same
+ * context. */
+int ipb_cache_create(ipb_ctx *ctx, size_t max_bytes, ipb_cache **out);
+void ipb_cache_destroy(ipb_cache *cache);
+void ipb_cache_clear(ipb_cache *cache);
+size_t ipb_cache_bytes(const ipb_cache *cache);
+size_t ipb_cache_entries(const ipb_cache *cache);
+/* Pipeline::run(Some(&cache)) — pipeline.rs:340-372: the cumulative hash chain over settings and op parameters finds
+ * the latest op whose output is cached; the ops after it run one kernel each and every result goes into the cache, so
+ * that a parameter change re-runs the pipeline from the first op it affects.  cache == NULL: ipb_pipeline_run. */
+int ipb_pipeline_run_cached(ipb_pipeline *p, ipb_cache *cache, ipb_buffer **out);
+/* what the last ipb_pipeline_run_cached did: index of the first op executed (0 = gofloat ... 7 = transform, 8 = the
+ * final buffer came from the cache) and how many ops ran */
+void ipb_pipeline_last_run_info(const ipb_pipeline *p, int *startpos, int *ops_run);
 /* Pipeline::output_8bit / output_16bit — pipeline.rs:377-469 (incl. the non-raw fast path).
  * dst capacity is in elements; *width/*height receive the image size. dst_on_device == 0 synchronises. */
 int ipb_pipeline_output_8bit(ipb_pipeline *p, uint8_t *dst, size_t dst_capacity, int dst_on_device, size_t *width,
