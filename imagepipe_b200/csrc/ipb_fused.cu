@@ -670,6 +670,7 @@ struct ScaledParams {
   int exact_rc;
   const float2 *lut_lab, *lut_gamma;
   float skip_x, skip_y;         // skip_x_x, skip_y_y of scaling.rs:69-72 (skip_x_y == skip_y_x == 0 here)
+  int bayer;                    // 2x2 pattern with green on one diagonal and red / blue on the other
 };
 
 constexpr int kPatStride = 56;   // pattern row: 48 columns + the first 8 again, so that x % 48 + k needs no wrap
@@ -687,13 +688,11 @@ __device__ __forceinline__ int f2i_sat(float f) {  // Rust `f as usize` for the 
   return (int)min(__float2uint_rz(f), 0x7fffffffu);
 }
 
-// acc += prod when cond, as one predicated packed add (each half rounded like the scalar `+=`; the multiplication by
-// the run-time `one` keeps ptxas from fusing the producer's multiply into it, see PkAdd)
-__device__ __forceinline__ void pk_add_if(F2 &acc, F2 prod, float one, bool cond) {
-  asm("{ .reg .pred q; .reg .b64 ra, rb, rc;\n"
-      "  setp.ne.s32 q, %4, 0; mov.b64 ra, {%0, %1}; mov.b64 rb, {%2, %3}; mov.b64 rc, {%5, %5};\n"
-      "  @q fma.rn.f32x2 ra, rb, rc, ra; mov.b64 {%0, %1}, ra; }"
-      : "+f"(acc.x), "+f"(acc.y) : "f"(prod.x), "f"(prod.y), "r"((int)cond), "f"(one));
+// sums[c] += vf; counts[c] += f when cond, as two predicated scalar adds (a predicated packed add is lowered to an
+// unpredicated FFMA2 plus two selects, which costs more issue slots than this)
+__device__ __forceinline__ void add_if(F2 &acc, float vf, float f, bool cond) {
+  asm("{ .reg .pred q; setp.ne.s32 q, %2, 0; @q add.rn.f32 %0, %0, %3; @q add.rn.f32 %1, %1, %4; }"
+      : "+f"(acc.x), "+f"(acc.y) : "r"((int)cond), "f"(vf), "f"(f));
 }
 
 // u16 -> f32 without the conversion unit: 0x4B000000 | v is the float 2^23 + v, and subtracting 2^23 is exact
@@ -730,11 +729,63 @@ __device__ __forceinline__ void window_taps(const ScaledParams &p, const uint8_t
       const int kk = UNIFORM ? k : min(k, nx - 1);
       const int c = prow[kk];
       const float v = fminf(div_rc(u16_to_float(__ldg(rowp + kk)) - black, range, rc), 1.0f);  // gofloat.rs:127
-      const F2 prod = pk_mul(F2{v, 1.0f}, splat(factor));  // (v*factor, factor)
+      const float vf = v * factor;
 #pragma unroll
-      for (int j = 0; j < NC; j++) pk_add_if(acc[j], prod, one, c == j);
+      for (int j = 0; j < NC; j++) add_if(acc[j], vf, factor, c == j);
     }
   }
+}
+
+// One window row of an RGB Bayer frame.  RP = parity of the row relative to the window's first row.  In a Bayer mosaic
+// green sits on one diagonal, so whether window column k of this row is green depends only on (RP + k) & 1 and on
+// one per-lane bit — is the window's top-left sample green (g00) — and the row's other colour is the same for the
+// whole row.  Green taps go to `g`, the others to `xacc` (the caller keeps one per relative row parity and maps the
+// two to red / blue at the end): no colour look-up, no comparisons, four predicated adds per tap.  Each colour still
+// receives its taps in raster order, like the reference's sums[c] / counts[c].
+template <int NX, bool UNIFORM, int RP>
+__device__ __forceinline__ void bayer_row(const uint16_t *rowp, const float ax[NX], float dy2, int nx, bool g00, float black,
+                                          float range, float rc, F2 &g, F2 &xacc) {
+#pragma unroll
+  for (int k = 0; k < NX; k++) {
+    float factor = ax[k] - dy2;
+    factor = factor < 0.0f ? 0.0f : factor;
+    if (!UNIFORM) factor = k < nx ? factor : 0.0f;
+    const int kk = UNIFORM ? k : min(k, nx - 1);
+    const float v = fminf(div_rc(u16_to_float(__ldg(rowp + kk)) - black, range, rc), 1.0f);  // gofloat.rs:127
+    const float vf = v * factor;
+    const bool green = ((RP + k) & 1) ? !g00 : g00;
+    add_if(g, vf, factor, green);
+    add_if(xacc, vf, factor, !green);
+  }
+}
+
+template <int NX, bool UNIFORM>
+__device__ __forceinline__ void window_taps_bayer(const ScaledParams &p, const CfaDev &cfa, int from_x, int nx, int from_y,
+                                                  int to_y, float center_x, float center_y, F2 acc[4]) {
+  const float black = p.black, range = p.range, rc = p.range_rc, skip_x = p.skip_x, skip_y = p.skip_y;
+  float ax[NX];
+#pragma unroll
+  for (int k = 0; k < NX; k++) {
+    const float delta_x = __fdiv_rn((float)(from_x + k) - center_x, skip_x);
+    ax[k] = 1.0f - (delta_x * delta_x);
+  }
+  const int py = from_y & 1, pxb = from_x & 1;
+  const bool g00 = cfa.pat[py * 48 + pxb] == 1;
+  F2 g{0.f, 0.f}, x0{0.f, 0.f}, x1{0.f, 0.f};
+  const uint16_t *rowp = p.raw + (long long)(from_y + p.crop_y - p.src_row0) * p.raw_pitch + p.crop_x + from_x;
+  for (int y = from_y; y <= to_y; y += 2, rowp += 2 * p.raw_pitch) {
+    float delta_y = __fdiv_rn((float)y - center_y, skip_y);
+    bayer_row<NX, UNIFORM, 0>(rowp, ax, delta_y * delta_y, nx, g00, black, range, rc, g, x0);
+    if (y + 1 <= to_y) {
+      delta_y = __fdiv_rn((float)(y + 1) - center_y, skip_y);
+      bayer_row<NX, UNIFORM, 1>(rowp + p.raw_pitch, ax, delta_y * delta_y, nx, g00, black, range, rc, g, x1);
+    }
+  }
+  // the non-green colour of the window's first row (0 = red or 2 = blue); the second row holds the other one
+  const int c0 = g00 ? cfa.pat[py * 48 + (pxb ^ 1)] : cfa.pat[py * 48 + pxb];
+  acc[1] = g;
+  acc[0] = c0 == 0 ? x0 : x1;
+  acc[2] = c0 == 0 ? x1 : x0;
 }
 
 // k_fused_scaled: one output pixel per thread (scaling.rs:76-127 with the CFA binning of :109-112), then the colour
@@ -786,7 +837,14 @@ k_fused_scaled(const __grid_constant__ ScaledParams p, const __grid_constant__ C
 
     F2 acc[4] = {F2{0.f, 0.f}, F2{0.f, 0.f}, F2{0.f, 0.f}, F2{0.f, 0.f}};  // {sums[c], counts[c]}
     const int nx_max = __reduce_max_sync(kFull, nx), nx_min = __reduce_min_sync(kFull, nx);
-    if (nx_max <= kMaxCols && p.exact_rc && !four) {
+    if (nx_max <= kMaxCols && p.exact_rc && p.bayer) {
+      if (nx_max == 5 && nx_min == 5)
+        window_taps_bayer<5, true>(p, cfa, from_x, nx, from_y, to_y, center_x, center_y, acc);
+      else if (nx_max <= 6)
+        window_taps_bayer<6, false>(p, cfa, from_x, nx, from_y, to_y, center_x, center_y, acc);
+      else
+        window_taps_bayer<kMaxCols, false>(p, cfa, from_x, nx, from_y, to_y, center_x, center_y, acc);
+    } else if (nx_max <= kMaxCols && p.exact_rc && !four) {
       if (nx_max == 5 && nx_min == 5)
         window_taps<5, true, 3>(p, sm.pat, P.one, from_x, nx, from_y, to_y, center_x, center_y, acc);
       else if (nx_max <= 6)
@@ -985,6 +1043,7 @@ cudaError_t launch_fused_scaled(cudaStream_t s, const FusedArgs &a, const CfaDev
   // scaling.rs:46,69-72: corners (0,0), (width-1,0), (0,height-1)
   p.skip_x = ((float)((long)a.width - 1) - 0.0f) / (float)(a.out_width - 1);
   p.skip_y = ((float)((long)a.height - 1) - 0.0f) / (float)(a.out_height - 1);
+  p.bayer = is_rgb_bayer(cfa) ? 1 : 0;
   const long long npix = (long long)(p.out_row1 - p.out_row0) * p.nwidth;
   long long blocks = (npix + kNTScaled - 1) / kNTScaled;
   const int grid = (int)(blocks < sm_count ? blocks : sm_count);
