@@ -7,7 +7,7 @@ from ._capi import IpbError, LIB_PATH, lib  # noqa: F401
 from .pipeline import (Context, DeviceArray, ImageSource, OpBaseCurve, OpBuffer, OpDemosaic, OpFromLab,  # noqa: F401
                        OpGamma, OpGoFloat, OpRotateCrop, OpToLab, OpTransform, Pipeline, PipelineCache, PipelineGlobals,
                        PipelineOps, PipelineSettings, Rotation, SplineFunc, SRGBImage, SRGBImage16,
-                       calculate_scale, default_context, rotate_buffer, scale_down_srgb, scaling_size,
+                       calculate_scale, default_context, lanczos_resize, rotate_buffer, scale_down_srgb, scaling_size,
                        synth_cfa_u16)
 
 __version__ = "0.1.0"

@@ -133,6 +133,7 @@ def lib():
         "ipb_pack_16bit": (i, [vp, vp, vp, i]),
         "ipb_scale_down_srgb": (i, [vp, vp, sz, sz, sz, sz, vp, i]),
         "ipb_scale_down_srgb16": (i, [vp, vp, sz, sz, sz, sz, vp, i]),
+        "ipb_lanczos_resize": (i, [vp, vp, sz, sz, i, vpp]),
         "ipb_ops_default": (None, [vp, vp]),
         "ipb_pipeline_create": (i, [vp, vp, vp, vpp]),
         "ipb_pipeline_destroy": (None, [vp]),

@@ -1090,6 +1090,107 @@ int ipb_scale_down_srgb16(ipb_ctx *ctx, const uint16_t *src, size_t w, size_t h,
 
 // ------------------------------------------------------------------------------------------------ Pipeline
 
+// ---- Lanczos-a resampler (extension; the reference only has the FIXME at scaling.rs:101-103)
+
+extern "C++" {
+namespace {
+struct LzAxis {
+  std::vector<int> start, count;
+  std::vector<float> w;
+  int ksize = 0;
+};
+double lz_kernel(double t, int a) {
+  if (t < 0) t = -t;
+  if (t >= (double)a) return 0.0;
+  if (t == 0.0) return 1.0;
+  const double pt = M_PI * t;
+  return (sin(pt) / pt) * (sin(pt / (double)a) / (pt / (double)a));
+}
+// taps of one axis: centre (i + 0.5) * scale, support a * max(scale, 1), weights normalised in double, stored as f32
+void lz_axis(size_t n_in, size_t n_out, int a, LzAxis *ax) {
+  const double scale = (double)n_in / (double)n_out;
+  const double fscale = scale < 1.0 ? 1.0 : scale;
+  const double support = (double)a * fscale;
+  ax->ksize = (int)ceil(support) * 2 + 1;
+  ax->start.assign(n_out, 0);
+  ax->count.assign(n_out, 0);
+  ax->w.assign(n_out * (size_t)ax->ksize, 0.0f);
+  std::vector<double> tmp((size_t)ax->ksize);
+  for (size_t i = 0; i < n_out; i++) {
+    const double centre = ((double)i + 0.5) * scale;
+    long xmin = (long)(centre - support + 0.5);
+    long xmax = (long)(centre + support + 0.5);
+    if (xmin < 0) xmin = 0;
+    if (xmax > (long)n_in) xmax = (long)n_in;
+    const long n = xmax - xmin;
+    double sum = 0.0;
+    for (long k = 0; k < n; k++) {
+      tmp[(size_t)k] = lz_kernel(((double)(xmin + k) - centre + 0.5) / fscale, a);
+      sum += tmp[(size_t)k];
+    }
+    for (long k = 0; k < n; k++)
+      ax->w[i * (size_t)ax->ksize + (size_t)k] = (float)(sum != 0.0 ? tmp[(size_t)k] / sum : tmp[(size_t)k]);
+    ax->start[i] = (int)xmin;
+    ax->count[i] = (int)n;
+  }
+}
+}  // namespace
+}  // extern "C++"
+
+int ipb_lanczos_resize(ipb_ctx *ctx, ipb_buffer *in, size_t nwidth, size_t nheight, int a, ipb_buffer **out) {
+  IPB_TRY(enter(ctx));
+  if (!in || !out) return fail(ctx, IPB_ERR_INVALID, "null pointer");
+  if (nwidth == 0 || nheight == 0 || a < 1 || a > 8 || in->width == 0 || in->height == 0)
+    return fail(ctx, IPB_ERR_INVALID, "lanczos: sizes must be positive and 1 <= a <= 8");
+  if (in->width >= (1u << 30) || in->height >= (1u << 30) || nwidth >= (1u << 30) || nheight >= (1u << 30))
+    return fail(ctx, IPB_ERR_INVALID, "lanczos: frame too large");
+  const size_t W = in->width, H = in->height, Cc = in->colors;
+  LzAxis ax, ay;
+  lz_axis(W, nwidth, a, &ax);
+  lz_axis(H, nheight, a, &ay);
+  // widest input span a 256-column tile of the horizontal pass stages in shared memory
+  size_t max_span = 0;
+  for (size_t x0 = 0; x0 < nwidth; x0 += 256) {
+    const size_t x1 = x0 + 256 < nwidth ? x0 + 256 : nwidth;
+    const size_t span = (size_t)(ax.start[x1 - 1] + ax.count[x1 - 1] - ax.start[x0]) * Cc;
+    if (span > max_span) max_span = span;
+  }
+  if ((max_span + 8) * sizeof(float) > 200 * 1024)
+    return fail(ctx, IPB_ERR_UNSUPPORTED, "lanczos: a 256-column tile spans %zu floats of a source row (scale too large)", max_span);
+  ipb_buffer *o;
+  IPB_TRY(new_buffer(ctx, nwidth, nheight, Cc, in->monochrome, false, &o));
+  const size_t nx = nwidth, ny = nheight;
+  const size_t ibytes = (2 * nx + 2 * ny) * sizeof(int);
+  const size_t wbytes = (nx * (size_t)ax.ksize + ny * (size_t)ay.ksize) * sizeof(float);
+  const size_t midbytes = H * nwidth * Cc * sizeof(float);
+  char *dev = nullptr;
+  cudaError_t e = cudaMallocAsync((void **)&dev, ibytes + wbytes + midbytes + 64, ctx->stream);
+  if (e != cudaSuccess) { ipb_buffer_release(o); return fail(ctx, IPB_ERR_NOMEM, "lanczos: %s", cudaGetErrorString(e)); }
+  // one pageable staging block: [sx cx sy cy | wx wy]
+  std::vector<char> host(ibytes + wbytes);
+  int *hi = (int *)host.data();
+  memcpy(hi, ax.start.data(), nx * sizeof(int));
+  memcpy(hi + nx, ax.count.data(), nx * sizeof(int));
+  memcpy(hi + 2 * nx, ay.start.data(), ny * sizeof(int));
+  memcpy(hi + 2 * nx + ny, ay.count.data(), ny * sizeof(int));
+  float *hw = (float *)(host.data() + ibytes);
+  memcpy(hw, ax.w.data(), ax.w.size() * sizeof(float));
+  memcpy(hw + ax.w.size(), ay.w.data(), ay.w.size() * sizeof(float));
+  e = cudaMemcpyAsync(dev, host.data(), host.size(), cudaMemcpyHostToDevice, ctx->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);  // `host` is pageable and goes out of scope
+  const int *di = (const int *)dev;
+  const float *dw = (const float *)(dev + ibytes);
+  float *mid = (float *)(dev + ((ibytes + wbytes + 63) / 64) * 64);
+  if (e == cudaSuccess)
+    e = launch_lanczos(ctx->stream, in->dptr, W, H, Cc, nwidth, nheight, di, di + nx, dw, ax.ksize, max_span, di + 2 * nx,
+                       di + 2 * nx + ny, dw + ax.w.size(), ay.ksize, mid, o->dptr);
+  cudaFreeAsync(dev, ctx->stream);
+  if (e != cudaSuccess) { ipb_buffer_release(o); return fail(ctx, IPB_ERR_CUDA, "lanczos: %s", cudaGetErrorString(e)); }
+  ctx->launches += 2;
+  *out = o;
+  return IPB_OK;
+}
+
 void ipb_ops_default(ipb_ops *ops, const ipb_source *image) {
   const HostTables &T = tables();
   memset(ops, 0, sizeof(*ops));

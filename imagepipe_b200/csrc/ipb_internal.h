@@ -70,6 +70,11 @@ cudaError_t launch_spline_eval(cudaStream_t s, const SplineDev &sp, const float 
 cudaError_t launch_rgb16_to_8(cudaStream_t s, const uint16_t *in, size_t n, uint8_t *out);
 cudaError_t launch_rgb8_to_16(cudaStream_t s, const uint8_t *in, size_t n, uint16_t *out);
 
+// ---- ipb_lanczos.cu (extension: Lanczos-a separable resampler, horizontal then vertical pass; two launches)
+cudaError_t launch_lanczos(cudaStream_t s, const float *in, size_t W, size_t H, size_t C, size_t nw, size_t nh,
+                           const int *sx, const int *cx, const float *wx, int kx, size_t max_span_floats, const int *sy,
+                           const int *cy, const float *wy, int ky, float *mid, float *out);
+
 // ---- ipb_fused.cu
 // full-resolution CFA -> RGB (gofloat + demosaic::full + colour chain + pack) in one kernel
 cudaError_t launch_fused_full(cudaStream_t s, const FusedArgs &a, const CfaDev &cfa, const ColorParams &P,

@@ -575,6 +575,11 @@ def scale_down_srgb(img, nwidth, nheight, ctx=None):
     return out
 
 
+def lanczos_resize(buf, nwidth, nheight, a=3):
+    """EXTENSION: Lanczos-a separable resample of a device OpBuffer (the reference has none: scaling.rs:101-103)."""
+    return _run_op(buf.ctx, lib().ipb_lanczos_resize, buf.handle, int(nwidth), int(nheight), int(a))
+
+
 def scaling_size(width, height, maxwidth, maxheight):
     ow, oh = C.c_size_t(), C.c_size_t()
     lib().ipb_scaling_size(width, height, maxwidth, maxheight, C.byref(ow), C.byref(oh))

@@ -222,6 +222,12 @@ int ipb_scale_down_srgb(ipb_ctx *ctx, const uint8_t *src, size_t w, size_t h, si
 int ipb_scale_down_srgb16(ipb_ctx *ctx, const uint16_t *src, size_t w, size_t h, size_t nw, size_t nh,
                           uint16_t *dst, int on_device);
 
+/* EXTENSION — Lanczos-a separable resampler of an f32 OpBuffer (any channel count), 1 <= a <= 8 (3 is the usual
+ * choice).  The reference has NO Lanczos resampler: src/scaling.rs:101-103 is a FIXME that names it as a possible
+ * replacement of the paraboloid window.  Never used by the pipeline entry points; parity is against
+ * oracle/lanczos.c, not the reference. */
+int ipb_lanczos_resize(ipb_ctx *ctx, ipb_buffer *in, size_t nwidth, size_t nheight, int a, ipb_buffer **out);
+
 /* ------------------------------------------------------------------ Pipeline — src/pipeline.rs:257-470 */
 
 /* PipelineOps::new for everything that does not need rawloader metadata (pipeline.rs:166-179):

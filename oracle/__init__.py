@@ -19,7 +19,7 @@ ROT_NORMAL, ROT_90, ROT_180, ROT_270 = 0, 1, 2, 3
 
 def build(force=False):
     """Compile oracle/liboracle.so from oracle/*.c (gcc, OpenMP)."""
-    srcs = [os.path.join(_HERE, f) for f in ("oracle.c", "kats.c", "oracle.h", "Makefile")]
+    srcs = [os.path.join(_HERE, f) for f in ("oracle.c", "kats.c", "lanczos.c", "oracle.h", "Makefile")]
     if (not force and os.path.exists(_LIB_PATH)
             and all(os.path.getmtime(_LIB_PATH) >= os.path.getmtime(s) for s in srcs)):
         return _LIB_PATH
@@ -133,6 +133,8 @@ def lib():
                                             C.POINTER(C.c_long), sz, sz, sz, C.POINTER(Cfa), fp]),
         "orc_scaled_demosaic": (BP, [C.POINTER(Cfa), BP, sz, sz]),
         "orc_scale_down_opbuf": (BP, [BP, sz, sz]),
+        "orc_lanczos_resize": (BP, [BP, sz, sz, C.c_int]),
+        "orc_lanczos_weights": (None, [sz, sz, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), fp, C.POINTER(C.c_size_t)]),
         "orc_scale_down_srgb": (None, [C.c_void_p, sz, sz, sz, sz, C.c_void_p]),
         "orc_scale_down_srgb16": (None, [C.c_void_p, sz, sz, sz, sz, C.c_void_p]),
         "orc_spline_new": (None, [C.POINTER(Spline), C.c_void_p, sz]),

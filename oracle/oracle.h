@@ -161,6 +161,9 @@ void orc_transform_buffer_u16(const uint16_t *src, size_t width, size_t height,
                               size_t nwidth, size_t nheight, size_t components, uint16_t *out);
 orc_buffer *orc_scaled_demosaic(const orc_cfa *cfa, const orc_buffer *buf, size_t nw, size_t nh);
 orc_buffer *orc_scale_down_opbuf(const orc_buffer *buf, size_t nw, size_t nh);
+/* lanczos.c — EXTENSION with no reference implementation (scaling.rs:101-103 is a FIXME): parity unpinned */
+orc_buffer *orc_lanczos_resize(const orc_buffer *buf, size_t nw, size_t nh, int a);
+void orc_lanczos_weights(size_t n_in, size_t n_out, int a, int *start, int *count, float *w, size_t *ksize_out);
 void orc_scale_down_srgb(const uint8_t *src, size_t w, size_t h, size_t nw, size_t nh, uint8_t *out);
 void orc_scale_down_srgb16(const uint16_t *src, size_t w, size_t h, size_t nw, size_t nh, uint16_t *out);
 
