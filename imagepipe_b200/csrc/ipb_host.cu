@@ -34,6 +34,10 @@ struct ipb_ctx {
   float2 *lut_gamma8 = nullptr;  // device {threshold, base} table: output8bit(apply_srgb_gamma(v)) per segment
   std::string err;
   unsigned long long launches = 0;
+  // Stream-ordered allocations come from a pool of the context that keeps its memory between frames (the device's
+  // default pool hands everything back to the driver at every synchronisation: a 384 MB OpBuffer then costs
+  // milliseconds to map again).  Like the reference's allocator, it holds on to what a pipeline run needed.
+  cudaMemPool_t pool = nullptr;
   // copy streams + events of the chunk-pipelined host<->device path (created on first use)
   cudaStream_t copy_in = nullptr, copy_out = nullptr;
   std::vector<cudaEvent_t> events;
@@ -113,6 +117,10 @@ int fail(ipb_ctx *ctx, int code, const char *fmt, ...) {
     if (e_ != cudaSuccess) return fail((ctx), IPB_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e_)); \
     (ctx)->launches++;                                                                             \
   } while (0)
+// stream-ordered allocation from the context's pool
+static inline cudaError_t ipb_malloc_async(ipb_ctx *ctx, void **p, size_t bytes) {
+  return ctx->pool ? cudaMallocFromPoolAsync(p, bytes, ctx->pool, ctx->stream) : cudaMallocAsync(p, bytes, ctx->stream);
+}
 #define IPB_TRY(call)            \
   do {                           \
     int rc_ = (call);            \
@@ -476,7 +484,7 @@ int new_buffer(ipb_ctx *ctx, size_t w, size_t h, size_t colors, int mono, bool z
   if (!b) return fail(ctx, IPB_ERR_NOMEM, "out of host memory");
   b->ctx = ctx; b->width = w; b->height = h; b->colors = colors; b->monochrome = mono;
   size_t bytes = w * h * colors * sizeof(float);
-  cudaError_t e = cudaMallocAsync((void **)&b->dptr, bytes ? bytes : 4, ctx->stream);
+  cudaError_t e = ipb_malloc_async(ctx, (void **)&b->dptr, bytes ? bytes : 4);
   if (e == cudaSuccess && zero && bytes) e = cudaMemsetAsync(b->dptr, 0, bytes, ctx->stream);
   if (e != cudaSuccess) {
     delete b;
@@ -512,7 +520,7 @@ int device_source(ipb_ctx *ctx, const ipb_source *img, DevSrc *d) {
   if (!img->data) return fail(ctx, IPB_ERR_INVALID, "source has no data");
   if (img->on_device) { d->ptr = img->data; return IPB_OK; }
   size_t bytes = img->width * img->height * src_cpp(img) * src_elem_size(img->kind);
-  IPB_CUDA(ctx, cudaMallocAsync(&d->tmp, bytes ? bytes : 4, ctx->stream));
+  IPB_CUDA(ctx, ipb_malloc_async(ctx, &d->tmp, bytes ? bytes : 4));
   IPB_CUDA(ctx, cudaMemcpyAsync(d->tmp, img->data, bytes, cudaMemcpyHostToDevice, ctx->stream));
   d->ptr = d->tmp;
   return IPB_OK;
@@ -552,6 +560,21 @@ int ipb_ctx_create(int device, void *stream, ipb_ctx **out) {
       return bail(IPB_ERR_CUDA);
     }
     ctx->own_stream = true;
+  }
+  {
+    cudaMemPoolProps props;
+    memset(&props, 0, sizeof(props));
+    props.allocType = cudaMemAllocationTypePinned;
+    props.handleTypes = cudaMemHandleTypeNone;
+    props.location.type = cudaMemLocationTypeDevice;
+    props.location.id = device;
+    if (cudaMemPoolCreate(&ctx->pool, &props) == cudaSuccess) {
+      unsigned long long keep = ~0ull;
+      cudaMemPoolSetAttribute(ctx->pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    } else {
+      ctx->pool = nullptr;  // fall back to the device's default pool
+      cudaGetLastError();
+    }
   }
   cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
   if (ctx->sm_count <= 0) ctx->sm_count = 148;
@@ -595,6 +618,7 @@ void ipb_ctx_destroy(ipb_ctx *ctx) {
   if (ctx->copy_in) { cudaStreamSynchronize(ctx->copy_in); cudaStreamDestroy(ctx->copy_in); }
   if (ctx->copy_out) { cudaStreamSynchronize(ctx->copy_out); cudaStreamDestroy(ctx->copy_out); }
   for (cudaEvent_t e : ctx->events) cudaEventDestroy(e);
+  if (ctx->pool) cudaMemPoolDestroy(ctx->pool);
   if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -637,7 +661,7 @@ void ipb_host_free(void *p) {
 int ipb_device_alloc(ipb_ctx *ctx, size_t bytes, void **out) {
   IPB_TRY(enter(ctx));
   if (!out) return fail(ctx, IPB_ERR_INVALID, "null out pointer");
-  cudaError_t e = cudaMallocAsync(out, bytes ? bytes : 4, ctx->stream);
+  cudaError_t e = ipb_malloc_async(ctx, out, bytes ? bytes : 4);
   if (e != cudaSuccess)
     return fail(ctx, e == cudaErrorMemoryAllocation ? IPB_ERR_NOMEM : IPB_ERR_CUDA, "device alloc %zu: %s", bytes, cudaGetErrorString(e));
   return IPB_OK;
@@ -750,7 +774,10 @@ int ipb_gofloat_run(ipb_ctx *ctx, const ipb_gofloat *op, const ipb_source *image
     if (image->cpp == 1 && !op->is_cfa) { mode = 0; colors = 4; mono = 1; }
     else if (image->cpp == 3) { mode = 1; colors = 4; }
     else { mode = 2; colors = image->cpp; }
-    rc = new_buffer(ctx, width, height, colors, mono, mode == 2, &b);
+    // the CFA / plain branch leaves elements at 0.0 only if the raster is shorter than its header says (gofloat.rs:126)
+    const bool zero = mode == 2 && !gofloat_rows_cover(image->width * image->height * image->cpp, image->width, x, y, width,
+                                                       height, image->cpp);
+    rc = new_buffer(ctx, width, height, colors, mono, zero, &b);
     if (rc == IPB_OK) {
       cudaError_t e = launch_gofloat_raw(ctx->stream, image->kind == IPB_SRC_RAW_F32, src.ptr,
                                          image->width * image->height * image->cpp, image->width, x, y, width, height,
@@ -1009,7 +1036,7 @@ int ipb_spline_eval(ipb_ctx *ctx, const ipb_basecurve *op, const float *in, floa
     return fail(ctx, IPB_ERR_INVALID, "degenerate curve (the reference panics)");
   }
   float *d;
-  IPB_CUDA(ctx, cudaMallocAsync((void **)&d, 2 * (n ? n : 1) * sizeof(float), ctx->stream));
+  IPB_CUDA(ctx, ipb_malloc_async(ctx, (void **)&d, 2 * (n ? n : 1) * sizeof(float)));
   IPB_CUDA(ctx, cudaMemcpyAsync(d, in, n * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
   IPB_LAUNCH(ctx, launch_spline_eval(ctx->stream, sp, d, n, d + n));
   IPB_CUDA(ctx, cudaMemcpyAsync(out, d + n, n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
@@ -1028,7 +1055,7 @@ static int pack_impl(ipb_ctx *ctx, const ipb_buffer *in, T *dst, int dst_on_devi
   if (in->colors != 3) return fail(ctx, IPB_ERR_BAD_COLORS, "pack: expected 3 channels, got %zu", in->colors);
   const size_t n = in->width * in->height * 3;
   T *d = dst;
-  if (!dst_on_device) IPB_CUDA(ctx, cudaMallocAsync((void **)&d, (n ? n : 1) * sizeof(T), ctx->stream));
+  if (!dst_on_device) IPB_CUDA(ctx, ipb_malloc_async(ctx, (void **)&d, (n ? n : 1) * sizeof(T)));
   cudaError_t e = sizeof(T) == 1 ? launch_pack8(ctx->stream, in->dptr, n, (uint8_t *)d)
                                  : launch_pack16(ctx->stream, in->dptr, n, (uint16_t *)d);
   if (e != cudaSuccess) return fail(ctx, IPB_ERR_CUDA, "pack kernel: %s", cudaGetErrorString(e));
@@ -1059,7 +1086,7 @@ static int scale_srgb_impl(ipb_ctx *ctx, const T *src, size_t w, size_t h, size_
   T *d = dst;
   T *tmp = nullptr;
   if (!on_device) {
-    IPB_CUDA(ctx, cudaMallocAsync((void **)&tmp, (nin + nout) * sizeof(T), ctx->stream));
+    IPB_CUDA(ctx, ipb_malloc_async(ctx, (void **)&tmp, (nin + nout) * sizeof(T)));
     IPB_CUDA(ctx, cudaMemcpyAsync(tmp, src, nin * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
     s = tmp;
     d = tmp + nin;
@@ -1164,7 +1191,7 @@ int ipb_lanczos_resize(ipb_ctx *ctx, ipb_buffer *in, size_t nwidth, size_t nheig
   const size_t wbytes = (nx * (size_t)ax.ksize + ny * (size_t)ay.ksize) * sizeof(float);
   const size_t midbytes = H * nwidth * Cc * sizeof(float);
   char *dev = nullptr;
-  cudaError_t e = cudaMallocAsync((void **)&dev, ibytes + wbytes + midbytes + 64, ctx->stream);
+  cudaError_t e = ipb_malloc_async(ctx, (void **)&dev, ibytes + wbytes + midbytes + 64);
   if (e != cudaSuccess) { ipb_buffer_release(o); return fail(ctx, IPB_ERR_NOMEM, "lanczos: %s", cudaGetErrorString(e)); }
   // one pageable staging block: [sx cx sy cy | wx wy]
   std::vector<char> host(ibytes + wbytes);
@@ -1838,13 +1865,13 @@ static int output_impl(ipb_pipeline *p, T *dst, size_t cap, int dst_on_device, s
     T *conv = nullptr;  // source raster at the output bit depth, on the device
     const T *raster = (const T *)src.ptr;
     if (!same_depth) {
-      IPB_CUDA(ctx, cudaMallocAsync((void **)&conv, (n ? n : 1) * sizeof(T), ctx->stream));
+      IPB_CUDA(ctx, ipb_malloc_async(ctx, (void **)&conv, (n ? n : 1) * sizeof(T)));
       if (want8) IPB_LAUNCH(ctx, launch_rgb16_to_8(ctx->stream, (const uint16_t *)src.ptr, n, (uint8_t *)conv));
       else IPB_LAUNCH(ctx, launch_rgb8_to_16(ctx->stream, (const uint8_t *)src.ptr, n, (uint16_t *)conv));
       raster = conv;
     }
     T *d = dst;
-    if (!dst_on_device) IPB_CUDA(ctx, cudaMallocAsync((void **)&d, nw * nh * 3 * sizeof(T), ctx->stream));
+    if (!dst_on_device) IPB_CUDA(ctx, ipb_malloc_async(ctx, (void **)&d, nw * nh * 3 * sizeof(T)));
     if (scale) {
       XformGeom g;
       g.tl[0] = 0; g.tl[1] = 0; g.tr[0] = (long)w - 1; g.tr[1] = 0; g.bl[0] = 0; g.bl[1] = (long)h - 1;
@@ -2001,7 +2028,7 @@ int ipb_selftest_gamma8(ipb_ctx *ctx, unsigned long long *mismatches) {
   if (!mismatches) return fail(ctx, IPB_ERR_INVALID, "null pointer");
   if (!ctx->lut_gamma8) return fail(ctx, IPB_ERR_UNSUPPORTED, "the 8-bit gamma threshold table failed its build-time checks");
   unsigned long long *d;
-  IPB_CUDA(ctx, cudaMallocAsync((void **)&d, sizeof(*d), ctx->stream));
+  IPB_CUDA(ctx, ipb_malloc_async(ctx, (void **)&d, sizeof(*d)));
   IPB_CUDA(ctx, cudaMemsetAsync(d, 0, sizeof(*d), ctx->stream));
   IPB_LAUNCH(ctx, launch_gamma8_selftest(ctx->stream, ctx->lut_gamma, ctx->lut_gamma8, d));
   IPB_CUDA(ctx, cudaMemcpyAsync(mismatches, d, sizeof(*d), cudaMemcpyDeviceToHost, ctx->stream));
@@ -2015,7 +2042,7 @@ int ipb_gamma_pack_8bit(ipb_ctx *ctx, const float *in, size_t n, uint8_t *out) {
   if (!in || !out) return fail(ctx, IPB_ERR_INVALID, "null pointer");
   if (!ctx->lut_gamma8) return fail(ctx, IPB_ERR_UNSUPPORTED, "the 8-bit gamma threshold table failed its build-time checks");
   float *d;
-  IPB_CUDA(ctx, cudaMallocAsync((void **)&d, (n ? n : 1) * 5, ctx->stream));
+  IPB_CUDA(ctx, ipb_malloc_async(ctx, (void **)&d, (n ? n : 1) * 5));
   uint8_t *o = (uint8_t *)(d + n);
   IPB_CUDA(ctx, cudaMemcpyAsync(d, in, n * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
   IPB_LAUNCH(ctx, launch_gamma8_pack(ctx->stream, ctx->lut_gamma8, d, n, o));

@@ -50,6 +50,7 @@ struct FusedArgs {
 cudaError_t launch_gofloat_raw(cudaStream_t s, int is_f32, const void *src, size_t total_elems, size_t owidth,
                                size_t x, size_t y, size_t width, size_t height, size_t cpp, int mode,
                                const float mins[4], const float ranges[4], float *out);
+bool gofloat_rows_cover(size_t total, size_t owidth, size_t x, size_t y, size_t width, size_t height, size_t cpp);
 cudaError_t launch_gofloat_other(cudaStream_t s, int is16, const void *src, size_t owidth, size_t x, size_t y,
                                  size_t width, size_t height, const float2 *lut_rev, float *out);
 cudaError_t launch_demosaic_full(cudaStream_t s, const CfaDev &cfa, const float *in, size_t w, size_t h, float *out);

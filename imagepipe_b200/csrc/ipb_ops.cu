@@ -14,6 +14,13 @@ static inline unsigned grid_for(size_t n, unsigned block) {
 
 // ------------------------------------------------------------------ K1 gofloat (gofloat.rs:84-201)
 
+// true when every sample the CFA / plain branch reads lies inside the raster (then no output element stays at its
+// initial 0.0 and the buffer needs no zero fill)
+bool gofloat_rows_cover(size_t total, size_t owidth, size_t x, size_t y, size_t width, size_t height, size_t cpp) {
+  if (width == 0 || height == 0) return true;
+  return owidth * (height - 1 + y) + x + width * cpp <= total;
+}
+
 template <typename T>
 __global__ void k_gofloat_raw(const T *__restrict__ src, size_t total, size_t owidth, size_t x, size_t y,
                               size_t width, size_t height, size_t cpp, int mode, float m0, float m1, float m2,
@@ -43,11 +50,36 @@ __global__ void k_gofloat_raw(const T *__restrict__ src, size_t total, size_t ow
   reinterpret_cast<float4 *>(out)[idx] = o;
 }
 
+// mode 2 (CFA / plain, gofloat.rs:122-130) without 64-bit index arithmetic: blockIdx.x = output row, blockIdx.y =
+// 256-element chunk of the row; 2-byte loads and 4-byte stores on consecutive addresses.  The caller has checked that
+// every source offset is inside the raster (otherwise the general kernel runs on a zeroed buffer).
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_gofloat_rows(const T *__restrict__ src, size_t owidth, size_t x, size_t y, unsigned linelen, float m0, float r0,
+               float *__restrict__ out) {
+  const unsigned c = blockIdx.y * 256u + threadIdx.x;
+  if (c >= linelen) return;
+  const size_t row = blockIdx.x;
+  const float v = (float)__ldg(src + owidth * (row + y) + x + c);
+  out[row * linelen + c] = fminf(__fdiv_rn(v - m0, r0), 1.0f);
+}
+
 cudaError_t launch_gofloat_raw(cudaStream_t s, int is_f32, const void *src, size_t total, size_t owidth, size_t x,
                                size_t y, size_t width, size_t height, size_t cpp, int mode, const float mins[4],
                                const float ranges[4], float *out) {
   size_t n = mode == 2 ? width * cpp * height : width * height;
   if (n == 0) return cudaSuccess;
+  const size_t linelen = width * cpp;
+  if (mode == 2 && gofloat_rows_cover(total, owidth, x, y, width, height, cpp) && (linelen + 255) / 256 <= 65535 &&
+      height < (1ull << 31)) {
+    dim3 grid((unsigned)height, (unsigned)((linelen + 255) / 256));
+    if (is_f32)
+      k_gofloat_rows<float><<<grid, 256, 0, s>>>((const float *)src, owidth, x, y, (unsigned)linelen, mins[0], ranges[0], out);
+    else
+      k_gofloat_rows<uint16_t><<<grid, 256, 0, s>>>((const uint16_t *)src, owidth, x, y, (unsigned)linelen, mins[0],
+                                                    ranges[0], out);
+    return cudaGetLastError();
+  }
   if (is_f32)
     k_gofloat_raw<float><<<grid_for(n, 256), 256, 0, s>>>((const float *)src, total, owidth, x, y, width, height, cpp,
                                                           mode, mins[0], mins[1], mins[2], ranges[0], ranges[1],
@@ -97,45 +129,84 @@ cudaError_t launch_gofloat_other(cudaStream_t s, int is16, const void *src, size
 
 // ------------------------------------------------------------------ K2 demosaic::full (demosaic.rs:67-119)
 
-__global__ void k_demosaic_full(const __grid_constant__ CfaDev cfa, const float *__restrict__ in, int w, int h,
-                                float *__restrict__ out) {
-  __shared__ uint8_t pat[48 * 48];
-  for (int i = threadIdx.x; i < 48 * 48; i += blockDim.x) pat[i] = cfa.pat[i];
-  __syncthreads();
-  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= (size_t)w * h) return;
-  int row = (int)(idx / w), col = (int)(idx - (size_t)row * w);
-  int pr = row % 48, pc = col % 48;
-  int pixcolor = pat[pr * 48 + pc];
-  float sums[4] = {0.f, 0.f, 0.f, 0.f}, counts[4] = {0.f, 0.f, 0.f, 0.f};
+// One CTA = a strip of 256 columns x kDemRows rows.  Every thread walks down its column with the 3x3 neighbourhood
+// in registers (three new loads per pixel, consecutive lanes on consecutive addresses) and writes one float4 per pixel.
+// Which taps feed which colour comes from a per-pattern-position mask table built once per CTA (demosaic.rs:77-90);
+// out-of-frame taps are dropped from sum and count (:103-107); a colour without taps stays 0.0 (:110-114).
+constexpr int kDemRows = 64;
+
+__device__ __forceinline__ float dem_bin(uint32_t m, const float v[9]) {
+  if (m == 0u) return 0.0f;
+  float s = 0.0f;
 #pragma unroll
-  for (int dy = -1; dy <= 1; dy++) {
-#pragma unroll
-    for (int dx = -1; dx <= 1; dx++) {
-      int r = row + dy, c = col + dx;
-      int oc = pat[((pr + 48 + dy) % 48) * 48 + (pc + 48 + dx) % 48];
-      // taps of the centre's own colour (other than the centre itself) go to the discarded bin 4 (:87)
-      bool keep = (oc != pixcolor) || (dx == 0 && dy == 0);
-      if (keep && r >= 0 && r < h && c >= 0 && c < w) {
-        float v = in[(size_t)r * w + c];
-#pragma unroll
-        for (int k = 0; k < 4; k++)
-          if (oc == k) { sums[k] += v; counts[k] += 1.0f; }
+  for (int i = 0; i < 9; i++)
+    if ((m >> i) & 1u) s = s + v[i];
+  return __fdiv_rn(s, (float)__popc(m));
+}
+
+__global__ void __launch_bounds__(256)
+k_demosaic_full(const __grid_constant__ CfaDev cfa, const float *__restrict__ in, int w, int h,
+                float *__restrict__ out) {
+  __shared__ uint2 taps[144];
+  const int pw = cfa.width, ph = cfa.height;
+  for (int pos = threadIdx.x; pos < pw * ph; pos += blockDim.x) {
+    const int pr = pos / pw, pc = pos - pr * pw;
+    const int pix = cfa.pat[pr * 48 + pc];
+    uint32_t m[4] = {0u, 0u, 0u, 0u};
+    int i = 0;
+    for (int dy = -1; dy <= 1; dy++)
+      for (int dx = -1; dx <= 1; dx++, i++) {
+        const int oc = cfa.pat[((pr + 48 + dy) % 48) * 48 + (pc + 48 + dx) % 48];
+        if ((oc != pix || (dx == 0 && dy == 0)) && oc < 4) m[oc] |= 1u << i;
       }
-    }
+    taps[pos] = make_uint2(m[0] | (m[1] << 16), m[2] | (m[3] << 16));
   }
-  float4 o;
-  o.x = counts[0] > 0.f ? __fdiv_rn(sums[0], counts[0]) : 0.f;
-  o.y = counts[1] > 0.f ? __fdiv_rn(sums[1], counts[1]) : 0.f;
-  o.z = counts[2] > 0.f ? __fdiv_rn(sums[2], counts[2]) : 0.f;
-  o.w = counts[3] > 0.f ? __fdiv_rn(sums[3], counts[3]) : 0.f;
-  reinterpret_cast<float4 *>(out)[idx] = o;
+  __syncthreads();
+  const int col = blockIdx.x * 256 + threadIdx.x;
+  if (col >= w) return;
+  const int row0 = blockIdx.y * kDemRows, row1 = min(h, row0 + kDemRows);
+  const int pc = col % pw;
+  int pr = row0 % ph;
+  const bool has_l = col > 0, has_r = col < w - 1;
+  uint32_t colmask = 0x1ffu;
+  if (!has_l) colmask &= ~0x049u;
+  if (!has_r) colmask &= ~0x124u;
+  auto load3 = [&](int r, float &a, float &b, float &c) {
+    a = b = c = 0.0f;
+    if (r >= 0 && r < h) {
+      const float *p = in + (size_t)r * w + col;
+      b = __ldg(p);
+      if (has_l) a = __ldg(p - 1);
+      if (has_r) c = __ldg(p + 1);
+    }
+  };
+  float v[9];
+  load3(row0 - 1, v[0], v[1], v[2]);
+  load3(row0, v[3], v[4], v[5]);
+  for (int row = row0; row < row1; row++) {
+    load3(row + 1, v[6], v[7], v[8]);
+    uint32_t valid = colmask;
+    if (row == 0) valid &= ~0x007u;
+    if (row == h - 1) valid &= ~0x1c0u;
+    const uint2 mm = taps[pr * pw + pc];
+    pr = pr + 1 == ph ? 0 : pr + 1;
+    float4 o;
+    o.x = dem_bin(mm.x & 0xffffu & valid, v);
+    o.y = dem_bin((mm.x >> 16) & valid, v);
+    o.z = dem_bin(mm.y & 0xffffu & valid, v);
+    o.w = dem_bin((mm.y >> 16) & valid, v);
+    reinterpret_cast<float4 *>(out)[(size_t)row * w + col] = o;
+#pragma unroll
+    for (int i = 0; i < 6; i++) v[i] = v[i + 3];
+  }
 }
 
 cudaError_t launch_demosaic_full(cudaStream_t s, const CfaDev &cfa, const float *in, size_t w, size_t h, float *out) {
-  size_t n = w * h;
-  if (n == 0) return cudaSuccess;
-  k_demosaic_full<<<grid_for(n, 256), 256, 0, s>>>(cfa, in, (int)w, (int)h, out);
+  if (w == 0 || h == 0) return cudaSuccess;
+  if (cfa.width <= 0 || cfa.height <= 0 || cfa.width * cfa.height > 144) return cudaErrorInvalidValue;
+  if ((h + kDemRows - 1) / kDemRows > 65535) return cudaErrorInvalidValue;  // 4 M rows
+  dim3 grid((unsigned)((w + 255) / 256), (unsigned)((h + kDemRows - 1) / kDemRows));
+  k_demosaic_full<<<grid, 256, 0, s>>>(cfa, in, (int)w, (int)h, out);
   return cudaGetLastError();
 }
 
@@ -253,22 +324,63 @@ cudaError_t launch_transform_u16(cudaStream_t s, const XformGeom &g, const uint1
 
 // ------------------------------------------------------------------ K4 to_lab (colorspaces.rs:89-112)
 
-__global__ void k_tolab(const __grid_constant__ ColorParams P, const float2 *__restrict__ lut_lab,
-                        const float *__restrict__ in, size_t npix, float *__restrict__ out) {
-  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= npix) return;
-  float4 p = reinterpret_cast<const float4 *>(in)[idx];
-  LutGlobal lab{lut_lab};
-  float l, a, b;
-  camera_to_lab<false>(P, lab, p.x, p.y, p.z, p.w, l, a, b);
-  out[idx * 3 + 0] = l;
-  out[idx * 3 + 1] = a;
-  out[idx * 3 + 2] = b;
+// Persistent CTAs (three per SM: 64 KB of shared memory each for the table) walk the buffer grid-stride; the table
+// look-ups hit shared memory instead of gathering from L1/L2.
+constexpr int kLutThreads = 512;
+__device__ __forceinline__ void load_lut_smem(float2 *dst, const float2 *__restrict__ src) {
+  const uint4 *a = reinterpret_cast<const uint4 *>(src);
+  uint4 *d = reinterpret_cast<uint4 *>(dst);
+  for (int i = threadIdx.x; i < kLutEntries / 2; i += blockDim.x) d[i] = __ldg(a + i);
+  __syncthreads();
+}
+struct LutSmemPtr {
+  const float2 *t;
+  __device__ __forceinline__ float2 at(int key) const { return t[key]; }
+};
+
+__global__ void __launch_bounds__(kLutThreads)
+k_tolab(const __grid_constant__ ColorParams P, const float2 *__restrict__ lut_lab, const float *__restrict__ in,
+        size_t npix, float *__restrict__ out) {
+  extern __shared__ __align__(16) unsigned char lut_smem[];
+  float2 *tab = reinterpret_cast<float2 *>(lut_smem);
+  load_lut_smem(tab, lut_lab);
+  const LutSmemPtr lab{tab};
+  // four pixels per thread: four 16-byte loads, three 16-byte stores (12 floats)
+  const size_t ngroups = npix / 4;
+  for (size_t gi = (size_t)blockIdx.x * kLutThreads + threadIdx.x; gi < ngroups; gi += (size_t)gridDim.x * kLutThreads) {
+    const float4 *src = reinterpret_cast<const float4 *>(in) + gi * 4;
+    float o[12];
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const float4 px = __ldg(src + j);
+      camera_to_lab<false>(P, lab, px.x, px.y, px.z, px.w, o[j * 3], o[j * 3 + 1], o[j * 3 + 2]);
+    }
+    float4 *dst = reinterpret_cast<float4 *>(out + gi * 12);
+    dst[0] = make_float4(o[0], o[1], o[2], o[3]);
+    dst[1] = make_float4(o[4], o[5], o[6], o[7]);
+    dst[2] = make_float4(o[8], o[9], o[10], o[11]);
+  }
+  for (size_t idx = ngroups * 4 + (size_t)blockIdx.x * kLutThreads + threadIdx.x; idx < npix;
+       idx += (size_t)gridDim.x * kLutThreads) {
+    const float4 px = reinterpret_cast<const float4 *>(in)[idx];
+    camera_to_lab<false>(P, lab, px.x, px.y, px.z, px.w, out[idx * 3], out[idx * 3 + 1], out[idx * 3 + 2]);
+  }
+}
+static int lut_grid(size_t work_items) {
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  size_t blocks = (work_items + kLutThreads - 1) / kLutThreads;
+  const size_t cap = (size_t)sms * 3;
+  return (int)(blocks < cap ? (blocks ? blocks : 1) : cap);
 }
 cudaError_t launch_tolab(cudaStream_t s, const ColorParams &P, const float2 *lut_lab, const float *in, size_t npix,
                          float *out) {
   if (npix == 0) return cudaSuccess;
-  k_tolab<<<grid_for(npix, 256), 256, 0, s>>>(P, lut_lab, in, npix, out);
+  const size_t smem = kLutEntries * sizeof(float2);
+  cudaError_t e = cudaFuncSetAttribute(k_tolab, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  k_tolab<<<lut_grid(npix / 4 + 1), kLutThreads, smem, s>>>(P, lut_lab, in, npix, out);
   return cudaGetLastError();
 }
 
@@ -319,16 +431,27 @@ cudaError_t launch_fromlab(cudaStream_t s, const ColorParams &P, const float *in
 
 // ------------------------------------------------------------------ K7 gamma (gamma.rs:16-26)
 
-__global__ void k_gamma(const float2 *__restrict__ lut_gamma, const float *__restrict__ in, size_t nelem,
-                        float *__restrict__ out) {
-  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= nelem) return;
-  LutGlobal gam{lut_gamma};
-  out[idx] = gamma_elem(gam, in[idx]);
+__global__ void __launch_bounds__(kLutThreads)
+k_gamma(const float2 *__restrict__ lut_gamma, const float *__restrict__ in, size_t nelem, float *__restrict__ out) {
+  extern __shared__ __align__(16) unsigned char lut_smem[];
+  float2 *tab = reinterpret_cast<float2 *>(lut_smem);
+  load_lut_smem(tab, lut_gamma);
+  const LutSmemPtr gam{tab};
+  const size_t nvec = nelem / 4;
+  for (size_t i = (size_t)blockIdx.x * kLutThreads + threadIdx.x; i < nvec; i += (size_t)gridDim.x * kLutThreads) {
+    const float4 v = __ldg(reinterpret_cast<const float4 *>(in) + i);
+    reinterpret_cast<float4 *>(out)[i] =
+        make_float4(gamma_elem(gam, v.x), gamma_elem(gam, v.y), gamma_elem(gam, v.z), gamma_elem(gam, v.w));
+  }
+  for (size_t i = nvec * 4 + (size_t)blockIdx.x * kLutThreads + threadIdx.x; i < nelem; i += (size_t)gridDim.x * kLutThreads)
+    out[i] = gamma_elem(gam, in[i]);
 }
 cudaError_t launch_gamma(cudaStream_t s, const float2 *lut_gamma, const float *in, size_t nelem, float *out) {
   if (nelem == 0) return cudaSuccess;
-  k_gamma<<<grid_for(nelem, 256), 256, 0, s>>>(lut_gamma, in, nelem, out);
+  const size_t smem = kLutEntries * sizeof(float2);
+  cudaError_t e = cudaFuncSetAttribute(k_gamma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  k_gamma<<<lut_grid(nelem / 4 + 1), kLutThreads, smem, s>>>(lut_gamma, in, nelem, out);
   return cudaGetLastError();
 }
 
