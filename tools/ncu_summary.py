@@ -49,8 +49,10 @@ def main():
                 us = float(vals["gpu__time_duration.sum"])
                 print(f"  -> {wi / (mp * 1e6):.2f} warp-instructions/px = {32 * wi / (mp * 1e6):.0f} thread-instruction slots/px; "
                       f"{mp / us:.3f} MP/us")
-                rd, wr = float(vals["dram__bytes_read.sum"]), float(vals["dram__bytes_write.sum"])
-                print(f"  -> dram traffic {rd + wr:.2f} (units as above) vs algorithmic bytes (see DESIGN.md)")
+                scale = {"byte": 1e-6, "Kbyte": 1e-3, "Mbyte": 1.0, "Gbyte": 1e3}
+                rd = float(vals["dram__bytes_read.sum"]) * scale[units[hdr.index("dram__bytes_read.sum")]]
+                wr = float(vals["dram__bytes_write.sum"]) * scale[units[hdr.index("dram__bytes_write.sum")]]
+                print(f"  -> dram traffic {rd + wr:.2f} MB per launch vs algorithmic bytes (see DESIGN.md)")
             except Exception as e:  # noqa: BLE001
                 print("  (derived figures unavailable:", e, ")")
     src = list(csv.reader(io.StringIO(ncu(rep, "--page", "source", "--csv", "--print-source", "cuda,sass"))))
