@@ -1586,8 +1586,7 @@ static int run_fused_banded(ipb_pipeline *p, const FusedPlan &plan, int out_kind
     mark(ctx->copy_in);
     uint8_t *band_out = out_dev + (b0 - r0) * row_out_bytes;
     mark(ctx->stream);
-    static const bool nokernel = getenv("IPB_NOKERNEL") != nullptr;  // transfer-only timing experiment
-    if (!nokernel) IPB_TRY(launch_fused_rows(p, plan, P, out_kind, b0, b1, band_out, raw_dev, dev0, dev_rows));
+    IPB_TRY(launch_fused_rows(p, plan, P, out_kind, b0, b1, band_out, raw_dev, dev0, dev_rows));
     mark(ctx->stream);
     if (dst_host) {
       IPB_CUDA(ctx, cudaEventRecord(ctx->events[2 * b + 1], ctx->stream));
