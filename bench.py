@@ -163,7 +163,7 @@ def run_c5(args, ip, common, torch, dist, ctx, stream, barrier, rank, world, loc
     me = lays[rank]
     rows_out = me.out_row1 - me.out_row0
     set_bytes = (me.src_row1 - me.src_row0) * W5 * 2 + rows_out * W5 * 3
-    nsets = max(2, -(-300_000_000 // set_bytes))  # rotating working set of >= 300 MB per GPU (L2 is 126 MB)
+    nsets = max(2, -(-600_000_000 // set_bytes))  # rotating working set of >= 600 MB per GPU (L2 is 126 MB)
     bufs, outs = [], []
     with torch.cuda.stream(stream):
         for i in range(nsets):
