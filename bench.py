@@ -29,10 +29,34 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 W, H = 6000, 4000
 MP = W * H / 1e6
 CFA = "RGGB"
+SETTINGS = {}          # PipelineSettings overrides of the workload (c4: maxwidth / maxheight)
+OUT_W, OUT_H = W, H    # size of the result
+WORKLOAD_NAME = "C2: 6000x4000 RGGB Bayer -> 8-bit sRGB, fused demosaic->gamma kernel"
+KERNEL_NAME, TRAFFIC_KEY = "k_fused_full<u8>", "k_fused_full<u8> C2 6000x4000"
 NSETS = 8
 FRAMES_PER_STEP = 32
 E2E_THREADS = 2
 ALGO_BYTES_PER_PX = 5  # 2 B in (u16 CFA sample) + 3 B out (u8 sRGB) — SURVEY.md §8d
+
+
+def select_workload(name):
+    """c2 is the contract's line; c3 / c4 are the other single-GPU BASELINE configurations, run the same way."""
+    global W, H, MP, CFA, SETTINGS, OUT_W, OUT_H, WORKLOAD_NAME, KERNEL_NAME, TRAFFIC_KEY, ALGO_BYTES_PER_PX
+    if name == "c3":
+        import common
+        W, H, CFA = 8256, 5504, common.XTRANS
+        OUT_W, OUT_H = W, H
+        WORKLOAD_NAME = "C3: 8256x5504 Fuji X-Trans 6x6 -> 8-bit sRGB, fused demosaic->gamma kernel (generic CFA path)"
+        KERNEL_NAME, TRAFFIC_KEY = "k_fused_full<u8, generic CFA>", "k_fused_full<u8,generic> C3 8256x5504"
+    elif name == "c4":
+        SETTINGS = {"maxwidth": 1500, "maxheight": 1000}
+        OUT_W, OUT_H = 1500, 1000
+        WORKLOAD_NAME = ("C4: 6000x4000 RGGB Bayer -> 1500x1000 8-bit sRGB (4x down-scale inside the demosaic op, "
+                         "scaled_demosaic), frames round-robin over the GPUs")
+        KERNEL_NAME, TRAFFIC_KEY = "k_fused_scaled<u8>", "k_fused_scaled<u8> C4 6000x4000->1500x1000"
+        ALGO_BYTES_PER_PX = 2 + 3.0 * OUT_W * OUT_H / (W * H)  # per INPUT pixel: 2.1875
+    MP = W * H / 1e6
+
 METRIC = "megapixels/sec raw->sRGB full pipe"
 
 
@@ -120,7 +144,7 @@ def cpu_reference_leg(steps, warmup, frames_note=True):
     L.orc_set_threads(0)
     cores = L.orc_get_threads()
     data = common.synth_cfa(W, H)
-    p = oracle.make_pipeline(data, "raw", workload_params())
+    p = oracle.make_pipeline(data, "raw", workload_params(), SETTINGS or None)
     for _ in range(warmup):
         oracle.pipeline_output_8bit(p)
     times = []
@@ -130,7 +154,7 @@ def cpu_reference_leg(steps, warmup, frames_note=True):
         times.append(time.perf_counter() - t0)
     per = float(np.mean(times))
     return {"value": MP / per, "unit": "MP/s", "cores": int(cores), "kind": "port",
-            "sample": f"{steps} x one 6000x4000 RGGB frame, output_8bit, OpenMP row-parallel C port of the reference "
+            "sample": f"{steps} x one {W}x{H} frame of the workload, output_8bit, OpenMP row-parallel C port of the reference "
                       f"CPU path (Rust toolchain absent)", "ms_per_frame": per * 1e3}
 
 
@@ -142,8 +166,7 @@ def run_reference(args, rank, world):
     line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "MP/s", "n_gpus": args.gpus,
             "steps": steps, "warmup": warmup, "ms_per_step": cb["ms_per_frame"], "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "C2: 6000x4000 RGGB Bayer -> 8-bit sRGB, one frame per step on host cores",
-                       "frames_per_step": 1},
+            "config": {"workload": WORKLOAD_NAME + " — one frame per step on host cores", "frames_per_step": 1},
             "cpu_baseline": cb,
             "e2e": {"value": cb["value"], "unit": "MP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
@@ -290,12 +313,15 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--frames-per-step", type=int, default=None)
     ap.add_argument("--no-graph", action="store_true", help="c5: launch every frame from Python instead of replaying a CUDA graph")
-    ap.add_argument("--workload", default="c2", choices=["c2", "c5"],
-                    help="c2 (default, the contract's line): 24 MP frames, replicas; c5: one 101.8 MP frame per step-frame, "
-                         "row stripes over the ranks with an NCCL halo exchange (strong scaling)")
+    ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c4", "c5"],
+                    help="c2 (default, the contract's line): 24 MP frames, replicas; c3: 45 MP X-Trans frames; c4: 24 MP frames "
+                         "with the 4x down-scale; c5: one 101.8 MP frame per step-frame, row stripes over the ranks with an "
+                         "NCCL halo exchange (strong scaling)")
     args = ap.parse_args()
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    select_workload(args.workload)
     if args.frames_per_step is None:
-        args.frames_per_step = FRAMES_PER_STEP if args.workload == "c2" else 8
+        args.frames_per_step = 8 if args.workload == "c5" else FRAMES_PER_STEP
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -331,12 +357,15 @@ def main():
         return
     # NSETS distinct synthetic frames, generated on the device, and NSETS output buffers
     frames = [ip.synth_cfa_u16(common.SEED + rank * 1000 + i, W, 0, H, ctx=ctx) for i in range(NSETS)]
-    outs = [ip.DeviceArray(W * H * 3, ctx) for _ in range(NSETS)]
+    outs = [ip.DeviceArray(OUT_W * OUT_H * 3, ctx) for _ in range(NSETS)]
     pipes = []
     for i in range(NSETS):
         src = ip.ImageSource.Raw(frames[i], width=W, height=H, cpp=1)
         p = ip.Pipeline.new_from_source(src, ctx=ctx)
         common.fill_ipb_ops(p.ops, params)
+        for k, v in SETTINGS.items():
+            setattr(p.globals.settings, k, v)
+        assert p.output_size() == (OUT_W, OUT_H)
         pipes.append(p)
 
     def step():
@@ -377,10 +406,12 @@ def main():
     for t in range(E2E_THREADS):
         wctx = ctx if t == 0 else ip.Context(local_rank)
         host_in, _hp_in = pinned_array(ip, W * H * 2, np.uint16, (H, W))
-        host_out, _hp_out = pinned_array(ip, W * H * 3, np.uint8, (H, W, 3))
+        host_out, _hp_out = pinned_array(ip, OUT_W * OUT_H * 3, np.uint8, (OUT_H, OUT_W, 3))
         host_in[:] = frame0
         pe = ip.Pipeline.new_from_source(ip.ImageSource.Raw(host_in), ctx=wctx)
         common.fill_ipb_ops(pe.ops, params)
+        for k, v in SETTINGS.items():
+            setattr(pe.globals.settings, k, v)
         workers.append((wctx, pe, host_in, host_out))
     pe, host_out = workers[0][1], workers[0][3]
     for _ in range(2):
@@ -415,7 +446,7 @@ def main():
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = world * per_thread * E2E_THREADS * MP / float(te.item())
     # result check on the last e2e frame: the device-resident path produced the same bytes
-    same = all(bool(np.array_equal(w[3], outs[0].to_numpy(np.uint8, (H, W, 3)))) for w in workers)
+    same = all(bool(np.array_equal(w[3], outs[0].to_numpy(np.uint8, (OUT_H, OUT_W, 3)))) for w in workers)
 
     if rank == 0:
         peak, peak_kind = measured_peak()
@@ -425,16 +456,16 @@ def main():
             "metric": METRIC, "value": value, "unit": "MP/s", "n_gpus": world, "steps": K, "warmup": Wm,
             "ms_per_step": total_ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "C2: 6000x4000 RGGB Bayer -> 8-bit sRGB, fused demosaic->gamma kernel",
+            "config": {"workload": WORKLOAD_NAME,
                        "frames_per_step": F, "buffer_sets": NSETS,
-                       "l2": f"inputs larger than L2: {NSETS} rotating sets x 120 MB",
+                       "l2": f"inputs larger than L2: {NSETS} rotating sets x {(W * H * 2 + OUT_W * OUT_H * 3) / 1e6:.0f} MB",
                        "parallelism": f"frames round-robin, {world} replica(s), no collective"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": measured_traffic("k_fused_full<u8> C2 6000x4000"), "kernel": "k_fused_full<u8>",
+                         "traffic": measured_traffic(TRAFFIC_KEY), "kernel": KERNEL_NAME,
                          "kernel_ms": kernel_ms, "peak_kind": peak_kind,
                          "algorithmic_bytes_per_launch": ALGO_BYTES_PER_PX * W * H},
             "e2e": {"value": e2e_value, "unit": "MP/s", "h2d_bytes_per_step": e2e_frames * W * H * 2,
-                    "d2h_bytes_per_step": e2e_frames * W * H * 3, "steps": e2e_steps, "frames_per_step": e2e_frames,
+                    "d2h_bytes_per_step": e2e_frames * OUT_W * OUT_H * 3, "steps": e2e_steps, "frames_per_step": e2e_frames,
                     "host_threads": E2E_THREADS, "frames_timed": per_thread * E2E_THREADS,
                     "single_call_ms": single_call_ms, "matches_device_path": same},
             "gpu_launches": int(launches),
