@@ -447,7 +447,10 @@ k_fused_full(const __grid_constant__ FullParams p, const __grid_constant__ CfaDe
 #pragma unroll
     for (int k = 0; k < 5; k++) sm.spl[i][k] = e[k];
   }
-  const uint32_t lab_base = smem_u32(sm.lut_lab), out_base = smem_u32(sm.lut_out);
+  // shared-window addresses of the tables, made opaque so that they stay in registers: the compiler otherwise
+  // re-derives them from the CTA id (three uniform-pipe instructions) in front of every group of look-ups
+  uint32_t lab_base = smem_u32(sm.lut_lab), out_base = smem_u32(sm.lut_out);
+  asm volatile("" : "+r"(lab_base), "+r"(out_base));
   const int lane = tid & 31, warp = tid >> 5;
   float *queue = sm.queue[warp];
   const bool g8 = OUT == kOutU8 && p.gamma8 != 0;
