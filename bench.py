@@ -10,7 +10,15 @@ over a batch of FRAMES_PER_STEP frames that rotate through NSETS distinct input/
 (NSETS * 120 MB > the 126 MB L2, so no frame is served from cache).  At N > 1 every rank runs the same batch on
 its own GPU (frames are independent: no data-path collective, scaling "weak"); value = total MP/s.
 
-One JSON line on stdout (rank 0).  See DESIGN.md "Measurement" for the roofline arithmetic.
+  --workload c3 | c4   BASELINE configurations 3 (8256x5504 X-Trans) and 4 (24 MP frames with the 4x down-scale)
+                       through the same harness
+  --workload c5        BASELINE configuration 5: one 11648x8736 frame cut into row stripes, one per rank, NCCL halo
+                       exchange of the stencil rows + one fused launch per rank per frame (scaling "strong")
+
+One JSON line on stdout (rank 0): value (device-resident, CUDA events on the launching stream, max over ranks),
+roofline (algorithmic bytes / measured launch time against MEASURED_PEAKS.json), e2e (pinned host buffers through
+the synchronous API, copies inside the timed region), cpu_baseline (the oracle's port of the reference CPU path on
+the host cores, N = 1 only), gpu_launches, clocks.  See DESIGN.md "Measurement" for the arithmetic.
 """
 import argparse
 import ctypes as C
