@@ -54,6 +54,7 @@ struct FullParams {
   const float2 *lut_lab, *lut_out;
   int tiles_x, tiles_y;
   int pw, ph;                   // CFA period
+  uint32_t rcp_pw, rcp_ph;      // floor(2^32 / period) + 1 for the multiply-high remainder, 0: use the % operator
   int use_tma;
   int gamma8;                   // lut_out is the 8-bit threshold table
   uint32_t g8_bias;             // 0x4B000000 << 3 (mod 2^32), as a run-time value: ptxas would otherwise split the
@@ -572,8 +573,9 @@ k_fused_full(const __grid_constant__ FullParams p, const __grid_constant__ CfaDe
       } else {
         // generic CFA / frame border: per-position tap masks, out-of-frame taps dropped from sum and count.
         // With TMA staging the tile holds whatever lies outside the cropped frame; the masks never select it.
-        const int pr = y % p.ph;
-        int pc = x0 % p.pw;
+        // position inside the CFA period: n % d as n - mulhi(n, ceil(2^32 / d)) * d (exact while n * d < 2^32)
+        const int pr = p.rcp_ph ? y - (int)__umulhi((uint32_t)y, p.rcp_ph) * p.ph : y % p.ph;
+        int pc = p.rcp_pw ? x0 - (int)__umulhi((uint32_t)x0, p.rcp_pw) * p.pw : x0 % p.pw;
         const bool inside = __all_sync(kFull, !live || interior);  // no tap of the warp's pixels leaves the frame
 #pragma unroll
         for (int j = 0; j < 4; j++) {
@@ -1017,6 +1019,9 @@ cudaError_t launch_fused_full(cudaStream_t s, const FusedArgs &a, const CfaDev &
   p.tiles_x = (p.width + kTW - 1) / kTW;
   p.tiles_y = (p.out_row1 - p.out_row0 + kTH - 1) / kTH;
   p.pw = cfa.width; p.ph = cfa.height;
+  const bool small = a.width < (1u << 26) && a.height < (1u << 26);  // n * period < 2^32 for every coordinate
+  p.rcp_pw = small && p.pw > 1 ? (uint32_t)(0x100000000ull / (uint64_t)p.pw) + 1u : 0u;
+  p.rcp_ph = small && p.ph > 1 ? (uint32_t)(0x100000000ull / (uint64_t)p.ph) + 1u : 0u;
   CUtensorMap tmap;
   memset(&tmap, 0, sizeof(tmap));
   p.use_tma = (a.use_tma && (a.crop_x % 8) == 0 && make_raw_tmap(&tmap, a.raw, a.raw_pitch, a.raw_pitch, a.src_rows)) ? 1 : 0;
