@@ -52,6 +52,7 @@ struct FullParams {
   float black, range, range_rc;
   int exact_rc;
   const float2 *lut_lab, *lut_out;
+  const float *cbrt_tab;        // cbrtf of every float in (1.0, 1.5], indexed by bit pattern - 0x3f800001
   int tiles_x, tiles_y;
   int pw, ph;                   // CFA period
   uint32_t rcp_pw, rcp_ph;      // floor(2^32 / period) + 1 for the multiply-high remainder, 0: use the % operator
@@ -300,34 +301,77 @@ __device__ __forceinline__ void xyz_ratios_pair(const ColorParams &P, const PkAd
   zr = IPB_PK_DIVC(z, 1.08883f);
 }
 
-// XYZ_LAB_TRANSFORM.lookup of the four values of one channel (pixels 0..3 of the task): table lerp for every value,
-// then the out-of-table ones (the reference's analytic branch) join the warp queue.  Returns the new queue length.
-// slot[j] is where value j was queued (only meaningful when oor bit j is set).
-__device__ __forceinline__ int lab_lookup4(const PkAdd &pk, uint32_t lab_base, float *queue, uint32_t lt, int n, F2 va,
-                                           F2 vb, float f[4], int slot[4], uint32_t &oormask, int shift) {
+// XYZ_LAB_TRANSFORM.lookup, table branch, of the four values of one channel (pixels 0..3 of the task).  Values
+// outside the table read some valid entry (masked key) and are replaced afterwards (lab_outside_table).
+__device__ __forceinline__ void lab_lookup4(const PkAdd &pk, uint32_t lab_base, F2 va, F2 vb, float f[4]) {
   const LerpIdx ia = lerp_index(pk, va), ib = lerp_index(pk, vb);
   f[0] = lerp_fetch(lab_base, ia.tf.x, ia.a.x);
   f[1] = lerp_fetch(lab_base, ia.tf.y, ia.a.y);
   f[2] = lerp_fetch(lab_base, ib.tf.x, ib.a.x);
   f[3] = lerp_fetch(lab_base, ib.tf.y, ib.a.y);
-  const float v[4] = {va.x, va.y, vb.x, vb.y};
-  bool oor[4];
+}
+
+constexpr uint32_t kCbrtTabFirst = 0x3f800001u;  // bit pattern of the first tabulated value: the float after 1.0
+constexpr uint32_t kCbrtTabSize = 1u << 22;      // ... up to and including 1.5 (0x3fc00000)
+
+// The reference's analytic branch of XYZ_LAB_TRANSFORM.lookup (color_conversions.rs:102-104,120-124) for the task's
+// twelve XYZ ratios v (x of pixels 0..3, y, z), entered when some lane of the warp holds a ratio outside [+0, 1]:
+//   1 < v <= 1.5   v.cbrt(): read from a table of the host libm's cbrtf over every float of that range (16 MB, built
+//                  once per context, L2-resident) — ratios a little above 1 are what clipped highlights produce;
+//   v < 0          (k*v + 16) / 116, computed for every value in packed arithmetic and selected;
+//   anything else  (v > 1.5, -0.0, NaN): compacted into the warp's queue and evaluated by lab_f_slow (glibc's cbrtf
+//                  restated in double precision); practically never taken, the fused launch is gated on finite inputs.
+__device__ __forceinline__ void lab_outside_table(const PkAdd &pk, const float *__restrict__ cbrt_tab, float *queue, int lane,
+                                                  const F2 vp[6], float f[12]) {
+  const float kk = 24389.0f / 27.0f;
+  float neg[12];
 #pragma unroll
-  for (int j = 0; j < 4; j++) oor[j] = !in_table(v[j]);
-#pragma unroll
-  for (int j = 0; j < 4; j++) slot[j] = 0;
-  if (__any_sync(kFull, oor[0] | oor[1] | oor[2] | oor[3])) {  // whole channel in table across the warp: common
-#pragma unroll
-    for (int j = 0; j < 4; j++) {
-      const uint32_t bal = __ballot_sync(kFull, oor[j]);
-      if (bal != 0u) {
-        slot[j] = n + __popc(bal & lt);
-        if (oor[j]) { queue[slot[j]] = v[j]; oormask |= 1u << (shift + j); }
-        n += __popc(bal);
-      }
-    }
+  for (int h = 0; h < 6; h++) {
+    const F2 n = IPB_PK_DIVC(pk.add(pk_mul(vp[h], kk), 16.0f), 116.0f);
+    neg[2 * h] = n.x;
+    neg[2 * h + 1] = n.y;
   }
-  return n;
+  uint32_t wmin = 0xffffffffu, umax = 0u;
+#pragma unroll
+  for (int i = 0; i < 12; i++) {
+    const float v = (i & 1) ? vp[i >> 1].y : vp[i >> 1].x;
+    const uint32_t u = __float_as_uint(v);
+    const uint32_t idx = u - kCbrtTabFirst;
+    if (idx < kCbrtTabSize) f[i] = __ldg(cbrt_tab + idx);
+    if (v < 0.0f) f[i] = neg[i];
+    wmin = min(wmin, u - (kCbrtTabFirst + kCbrtTabSize));  // 0 .. 0x403fffff for 1.5 < v, +inf, +NaN and -0.0
+    umax = max(umax, u);
+  }
+  const bool rest = wmin <= 0x80000000u - (kCbrtTabFirst + kCbrtTabSize) || umax > 0xff800000u;  // or a negative NaN
+  if (__any_sync(kFull, rest)) {
+    int cnt = 0;
+    bool mine[12];
+#pragma unroll
+    for (int i = 0; i < 12; i++) {
+      const uint32_t u = __float_as_uint((i & 1) ? vp[i >> 1].y : vp[i >> 1].x);
+      mine[i] = u - (kCbrtTabFirst + kCbrtTabSize) <= 0x80000000u - (kCbrtTabFirst + kCbrtTabSize) || u > 0xff800000u;
+      cnt += mine[i] ? 1 : 0;
+    }
+    int incl = cnt;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int t = __shfl_up_sync(kFull, incl, d);
+      incl += lane >= d ? t : 0;
+    }
+    const int total = __shfl_sync(kFull, incl, 31);
+    int q = incl - cnt;
+#pragma unroll
+    for (int i = 0; i < 12; i++)
+      if (mine[i]) queue[q++] = (i & 1) ? vp[i >> 1].y : vp[i >> 1].x;
+    __syncwarp();
+    for (int i = lane; i < total; i += 32) queue[i] = lab_f_slow(queue[i]);
+    __syncwarp();
+    q = incl - cnt;
+#pragma unroll
+    for (int i = 0; i < 12; i++)
+      if (mine[i]) f[i] = queue[q++];
+    __syncwarp();
+  }
 }
 
 // Lab from the transfer-function values, basecurve, from_lab (+ gamma) for two pixels
@@ -611,26 +655,20 @@ k_fused_full(const __grid_constant__ FullParams p, const __grid_constant__ CfaDe
       F2 xa, ya, za, xb, yb, zb;
       xyz_ratios_pair(P, pk, cr, cg, cb, ce, xa, ya, za);
       xyz_ratios_pair(P, pk, cr + 2, cg + 2, cb + 2, ce + 2, xb, yb, zb);
-      float fxs[4], fys[4], fzs[4];
-      int sx[4], sy[4], sz[4];
-      uint32_t oormask = 0u;
-      const uint32_t lt = (1u << lane) - 1u;
-      int nq = 0;
-      nq = lab_lookup4(pk, lab_base, queue, lt, nq, xa, xb, fxs, sx, oormask, 0);
-      nq = lab_lookup4(pk, lab_base, queue, lt, nq, ya, yb, fys, sy, oormask, 4);
-      nq = lab_lookup4(pk, lab_base, queue, lt, nq, za, zb, fzs, sz, oormask, 8);
-      if (nq > 0) {  // warp-uniform
-        __syncwarp();
-        for (int i = lane; i < nq; i += 32) queue[i] = lab_f_slow(queue[i]);
-        __syncwarp();
+      float fl[12];  // transfer-function values in the order x0 x1 x2 x3 y0 .. z3
+      lab_lookup4(pk, lab_base, xa, xb, fl);
+      lab_lookup4(pk, lab_base, ya, yb, fl + 4);
+      lab_lookup4(pk, lab_base, za, zb, fl + 8);
+      {
+        // any ratio of the warp outside [+0, 1]?  As unsigned bit patterns, negative values, values above 1.0 and NaN
+        // all compare above 1.0f.
+        const F2 vp[6] = {xa, xb, ya, yb, za, zb};
+        uint32_t mx = 0u;
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
-          if (oormask & (1u << j)) fxs[j] = queue[sx[j]];
-          if (oormask & (1u << (4 + j))) fys[j] = queue[sy[j]];
-          if (oormask & (1u << (8 + j))) fzs[j] = queue[sz[j]];
-        }
-        __syncwarp();
+        for (int h = 0; h < 6; h++) mx = max(mx, max(__float_as_uint(vp[h].x), __float_as_uint(vp[h].y)));
+        if (__any_sync(kFull, mx > 0x3f800000u)) lab_outside_table(pk, p.cbrt_tab, queue, lane, vp, fl);
       }
+      const float *fxs = fl, *fys = fl + 4, *fzs = fl + 8;
       lab_to_output_pair<OUT>(P, pk, sm, out_base, p.g8_bias, g8, F2{fxs[0], fxs[1]}, F2{fys[0], fys[1]}, F2{fzs[0], fzs[1]}, orr, og,
                               ob, q8);
       lab_to_output_pair<OUT>(P, pk, sm, out_base, p.g8_bias, g8, F2{fxs[2], fxs[3]}, F2{fys[2], fys[3]}, F2{fzs[2], fzs[3]}, orr + 2,
@@ -1013,6 +1051,7 @@ cudaError_t launch_fused_full(cudaStream_t s, const FusedArgs &a, const CfaDev &
   p.out = a.out;
   p.black = a.black; p.range = a.range; p.range_rc = a.range_rc; p.exact_rc = a.exact_rc;
   p.lut_lab = a.lut_lab;
+  p.cbrt_tab = a.cbrt_tab;
   p.gamma8 = (a.out_kind == kOutU8 && !P.linear && a.lut_gamma8) ? 1 : 0;
   p.lut_out = p.gamma8 ? a.lut_gamma8 : a.lut_gamma;
   p.g8_bias = 0x58000000u;

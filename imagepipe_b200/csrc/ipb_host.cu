@@ -32,6 +32,7 @@ struct ipb_ctx {
   int sm_count = 0;
   float2 *lut_lab = nullptr, *lut_gamma = nullptr, *lut_rev = nullptr;  // device {v, dv} tables
   float2 *lut_gamma8 = nullptr;  // device {threshold, base} table: output8bit(apply_srgb_gamma(v)) per segment
+  float *cbrt_tab = nullptr;     // device table of cbrtf(v) for every float v in (1.0, 1.5], built on first fused launch
   std::string err;
   unsigned long long launches = 0;
   // Stream-ordered allocations come from a pool of the context that keeps its memory between frames (the device's
@@ -615,6 +616,7 @@ void ipb_ctx_destroy(ipb_ctx *ctx) {
   if (ctx->lut_gamma) cudaFree(ctx->lut_gamma);
   if (ctx->lut_rev) cudaFree(ctx->lut_rev);
   if (ctx->lut_gamma8) cudaFree(ctx->lut_gamma8);
+  if (ctx->cbrt_tab) cudaFree(ctx->cbrt_tab);
   if (ctx->copy_in) { cudaStreamSynchronize(ctx->copy_in); cudaStreamDestroy(ctx->copy_in); }
   if (ctx->copy_out) { cudaStreamSynchronize(ctx->copy_out); cudaStreamDestroy(ctx->copy_out); }
   for (cudaEvent_t e : ctx->events) cudaEventDestroy(e);
@@ -1421,6 +1423,32 @@ static int ensure_stage(ipb_ctx *ctx, void **buf, size_t *have, size_t need) {
   return IPB_OK;
 }
 
+// XYZ_LAB_TRANSFORM's analytic branch above 1.0 is v.cbrt() (color_conversions.rs:123): the host libm's cbrtf, like
+// the 8193-entry tables.  The fused full-resolution kernel reads it from a table of every float in (1.0, 1.5] —
+// 2^22 entries, 16 MB, built once per context with the same libm call (about 60 ms) — instead of restating glibc's
+// double-precision algorithm per value; ratios beyond 1.5 still take that restatement (lab_f_slow).
+static int ensure_cbrt_table(ipb_ctx *ctx) {
+  if (ctx->cbrt_tab) return IPB_OK;
+  const size_t n = (size_t)1 << 22;
+  std::vector<float> host(n);
+  for (size_t i = 0; i < n; i++) {
+    const uint32_t bits = 0x3f800001u + (uint32_t)i;
+    float v;
+    memcpy(&v, &bits, 4);
+    host[i] = cbrtf(v);
+  }
+  float *d = nullptr;
+  IPB_CUDA(ctx, cudaMalloc((void **)&d, n * sizeof(float)));
+  cudaError_t e = cudaMemcpyAsync(d, host.data(), n * sizeof(float), cudaMemcpyHostToDevice, ctx->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  if (e != cudaSuccess) {
+    cudaFree(d);
+    return fail(ctx, IPB_ERR_CUDA, "cube-root table upload: %s", cudaGetErrorString(e));
+  }
+  ctx->cbrt_tab = d;
+  return IPB_OK;
+}
+
 // Launch the fused kernel for output rows [r0, r1) into `out` (device, row r0 first).  `raw_dev` holds the
 // un-cropped source rows [have0, have0 + have_rows) on the device.
 static int launch_fused_rows(ipb_pipeline *p, const FusedPlan &plan, const ColorParams &P, int out_kind, size_t r0,
@@ -1457,6 +1485,8 @@ static int launch_fused_rows(ipb_pipeline *p, const FusedPlan &plan, const Color
   a.lut_lab = ctx->lut_lab;
   a.lut_gamma = ctx->lut_gamma;
   a.lut_gamma8 = ctx->lut_gamma8;
+  if (plan.mode == kFusedFull) IPB_TRY(ensure_cbrt_table(ctx));
+  a.cbrt_tab = ctx->cbrt_tab;
   a.use_tma = p->use_tma;
   cudaError_t e = plan.mode == kFusedFull ? launch_fused_full(ctx->stream, a, plan.cfa, P, ctx->sm_count)
                                           : launch_fused_scaled(ctx->stream, a, plan.cfa, P, ctx->sm_count);

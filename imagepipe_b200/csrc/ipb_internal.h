@@ -43,6 +43,7 @@ struct FusedArgs {
   const float2 *lut_lab;   // device tables {v, dv}
   const float2 *lut_gamma;
   const float2 *lut_gamma8;  // 8-bit output: {threshold, base} per table segment (ipb_host.cu build_gamma8)
+  const float *cbrt_tab;     // full-res kernel: host cbrtf of every float in (1.0, 1.5] (ipb_host.cu ensure_cbrt_table)
   int use_tma;             // full-res kernel: stage tiles with TMA (needs 16B-aligned base and pitch)
 };
 
