@@ -539,6 +539,8 @@ extern "C" {
 
 int ipb_version(void) { return IPB_VERSION; }
 
+static int ensure_cbrt_table(ipb_ctx *ctx);
+
 int ipb_ctx_create(int device, void *stream, ipb_ctx **out) {
   if (!out) return fail(nullptr, IPB_ERR_INVALID, "null out pointer");
   *out = nullptr;
@@ -603,6 +605,12 @@ int ipb_ctx_create(int device, void *stream, ipb_ctx **out) {
         return bail(IPB_ERR_CUDA);
       }
     }
+  }
+  // built here rather than at the first fused launch, so that a first launch may sit inside a stream capture
+  if (ensure_cbrt_table(ctx) != IPB_OK) {
+    g_create_err = ctx->err;
+    ipb_ctx_destroy(ctx);
+    return IPB_ERR_CUDA;
   }
   *out = ctx;
   return IPB_OK;
