@@ -9,17 +9,23 @@
 // k_fused_full is a persistent kernel: one 1024-thread CTA per SM walks 128x32-pixel tiles round-robin, one
 // __syncthreads per tile.
 //   * the raw u16 tile (+1 px halo, 144x34 box) of the NEXT tile is fetched by TMA (cp.async.bulk.tensor.2d,
-//     completion on an mbarrier) into a two-stage ring while the current tile is computed;
-//   * a conversion phase applies gofloat once per sensor pixel (smem u16 -> smem f32);
-//   * the compute phase gives every thread four consecutive pixels: 3x6 window from shared memory, demosaic,
-//     then the colour chain on two pixel pairs;
+//     completion on an mbarrier) while the current tile is computed;
+//   * a conversion phase applies gofloat once per sensor pixel (smem u16 -> smem f32, double buffered; warps take
+//     256-sample chunks from a counter, so the warps that finish their pixels first convert the next tile);
+//   * the compute phase gives every thread four consecutive pixels: 3x6 window from shared memory, demosaic
+//     (fixed-count means for RGB Bayer interiors, per-position tap masks for every other pattern and the borders),
+//     then the colour chain on two pixel pairs in packed f32x2 arithmetic;
 //   * both 8192-entry tables stay in shared memory for the whole launch.  For 8-bit output the gamma table is
 //     replaced by a threshold table that yields output8bit(gamma(v)) directly (see build in ipb_host.cu);
-//   * XYZ ratios outside [0,1] (the reference's analytic branch: glibc cbrtf in double precision, or the linear
-//     segment) are rare per lane but common per warp, so they are compacted into a per-warp queue and evaluated
-//     by a dense pass instead of twelve divergent calls.
+//   * XYZ ratios outside [0,1] (the reference's analytic branch): cube roots of ratios in (1, 1.5] come from a table
+//     of the host libm's cbrtf over every float of that range, negative ratios are evaluated inline, and whatever is
+//     left (beyond 1.5, -0.0, NaN) is compacted into a per-warp queue and evaluated by the double-precision
+//     restatement of glibc's cbrtf.
+// k_fused_scaled gives every thread one output pixel: its window of raw samples is read from global memory
+// (L1/L2 serve the overlap), weights per column / row are computed once, colours accumulate in the reference's tap
+// order; RGB Bayer frames use a loop without colour look-ups.
 // Arithmetic is the per-pixel code of ipb_device.cuh, compiled -fmad=false: results are bit-identical to the
-// reference's f32 arithmetic (tests/test_gpu_fused.py compares against the CPU oracle bit for bit).
+// reference's f32 arithmetic (tests/test_gpu_fused*.py compare against the CPU oracle bit for bit).
 #include <cuda.h>  // CUtensorMap (types only; cuTensorMapEncodeTiled is resolved at run time, no libcuda link)
 
 #include "ipb_internal.h"
