@@ -101,3 +101,14 @@ def test_full_size_c5_frame_striped(ip, orc, ctx):
         run_stripe_8bit(p, rows.ptr, lay, dst)
         assert_bit_exact(dst.to_numpy(np.uint8, (lay.out_row1 - lay.out_row0, w, 3)), want[lay.out_row0:lay.out_row1],
                          f"C5 stripe {lay.rank}")
+
+
+@pytest.mark.parametrize("scale", [1.45, 2.5, 40.0])
+def test_ratios_beyond_the_cube_root_table(ip, orc, ctx, scale):
+    """XYZ ratios above 1.0 come from the cube-root table up to 1.5 and from the double-precision restatement of
+    glibc's cbrtf beyond (the per-warp queue); a scaled camera matrix puts ratios on both sides of that border, and
+    negative off-diagonals make some ratios negative.  Still one fused launch, still the oracle's bits."""
+    data = common.synth_cfa(517, 203, seed=141)
+    matrix = common.CAM_TO_XYZ * np.float32(scale)
+    matrix[2, 1] = np.float32(-1.3 * scale)          # strongly negative: Z ratios below zero
+    check(ip, orc, ctx, data, common.raw_params(matrix=matrix), None, True, f"matrix x{scale}")
