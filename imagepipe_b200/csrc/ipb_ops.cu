@@ -345,25 +345,13 @@ k_tolab(const __grid_constant__ ColorParams P, const float2 *__restrict__ lut_la
   float2 *tab = reinterpret_cast<float2 *>(lut_smem);
   load_lut_smem(tab, lut_lab);
   const LutSmemPtr lab{tab};
-  // four pixels per thread: four 16-byte loads, three 16-byte stores (12 floats)
-  const size_t ngroups = npix / 4;
-  for (size_t gi = (size_t)blockIdx.x * kLutThreads + threadIdx.x; gi < ngroups; gi += (size_t)gridDim.x * kLutThreads) {
-    const float4 *src = reinterpret_cast<const float4 *>(in) + gi * 4;
-    float o[12];
-#pragma unroll
-    for (int j = 0; j < 4; j++) {
-      const float4 px = __ldg(src + j);
-      camera_to_lab<false>(P, lab, px.x, px.y, px.z, px.w, o[j * 3], o[j * 3 + 1], o[j * 3 + 2]);
-    }
-    float4 *dst = reinterpret_cast<float4 *>(out + gi * 12);
-    dst[0] = make_float4(o[0], o[1], o[2], o[3]);
-    dst[1] = make_float4(o[4], o[5], o[6], o[7]);
-    dst[2] = make_float4(o[8], o[9], o[10], o[11]);
-  }
-  for (size_t idx = ngroups * 4 + (size_t)blockIdx.x * kLutThreads + threadIdx.x; idx < npix;
-       idx += (size_t)gridDim.x * kLutThreads) {
-    const float4 px = reinterpret_cast<const float4 *>(in)[idx];
-    camera_to_lab<false>(P, lab, px.x, px.y, px.z, px.w, out[idx * 3], out[idx * 3 + 1], out[idx * 3 + 2]);
+  for (size_t idx = (size_t)blockIdx.x * kLutThreads + threadIdx.x; idx < npix; idx += (size_t)gridDim.x * kLutThreads) {
+    const float4 px = __ldg(reinterpret_cast<const float4 *>(in) + idx);
+    float l, a, b;
+    camera_to_lab<false>(P, lab, px.x, px.y, px.z, px.w, l, a, b);
+    out[idx * 3 + 0] = l;
+    out[idx * 3 + 1] = a;
+    out[idx * 3 + 2] = b;
   }
 }
 static int lut_grid(size_t work_items) {
@@ -380,7 +368,7 @@ cudaError_t launch_tolab(cudaStream_t s, const ColorParams &P, const float2 *lut
   const size_t smem = kLutEntries * sizeof(float2);
   cudaError_t e = cudaFuncSetAttribute(k_tolab, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  k_tolab<<<lut_grid(npix / 4 + 1), kLutThreads, smem, s>>>(P, lut_lab, in, npix, out);
+  k_tolab<<<lut_grid(npix), kLutThreads, smem, s>>>(P, lut_lab, in, npix, out);
   return cudaGetLastError();
 }
 
