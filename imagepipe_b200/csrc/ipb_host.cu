@@ -32,7 +32,10 @@ struct ipb_ctx {
   int sm_count = 0;
   float2 *lut_lab = nullptr, *lut_gamma = nullptr, *lut_rev = nullptr;  // device {v, dv} tables
   float2 *lut_gamma8 = nullptr;  // device {threshold, base} table: output8bit(apply_srgb_gamma(v)) per segment
-  float *cbrt_tab = nullptr;     // device table of cbrtf(v) for every float v in (1.0, 1.5], built on first fused launch
+  float *cbrt_tab = nullptr;     // device table of cbrtf(v) for every float v in (1.0, 1.5]
+  // Lanczos tap tables already on the device, most recently used last (ipb_lanczos_resize)
+  struct LzTab { size_t n_in, n_out; int a, ksize; int *start, *count; float *w; std::vector<int> hstart, hcount; };
+  std::vector<LzTab> lz_tabs;
   std::string err;
   unsigned long long launches = 0;
   // Stream-ordered allocations come from a pool of the context that keeps its memory between frames (the device's
@@ -625,6 +628,7 @@ void ipb_ctx_destroy(ipb_ctx *ctx) {
   if (ctx->lut_rev) cudaFree(ctx->lut_rev);
   if (ctx->lut_gamma8) cudaFree(ctx->lut_gamma8);
   if (ctx->cbrt_tab) cudaFree(ctx->cbrt_tab);
+  for (auto &t : ctx->lz_tabs) cudaFree(t.start);
   if (ctx->copy_in) { cudaStreamSynchronize(ctx->copy_in); cudaStreamDestroy(ctx->copy_in); }
   if (ctx->copy_out) { cudaStreamSynchronize(ctx->copy_out); cudaStreamDestroy(ctx->copy_out); }
   for (cudaEvent_t e : ctx->events) cudaEventDestroy(e);
@@ -1174,6 +1178,45 @@ void lz_axis(size_t n_in, size_t n_out, int a, LzAxis *ax) {
 }  // namespace
 }  // extern "C++"
 
+// device-resident tap table of one axis, built once per (n_in, n_out, a) and context and kept (eight most recent)
+static int lz_table(ipb_ctx *ctx, size_t n_in, size_t n_out, int a, const ipb_ctx::LzTab **out) {
+  for (size_t i = 0; i < ctx->lz_tabs.size(); i++)
+    if (ctx->lz_tabs[i].n_in == n_in && ctx->lz_tabs[i].n_out == n_out && ctx->lz_tabs[i].a == a) {
+      ipb_ctx::LzTab t = std::move(ctx->lz_tabs[i]);
+      ctx->lz_tabs.erase(ctx->lz_tabs.begin() + (long)i);
+      ctx->lz_tabs.push_back(std::move(t));
+      *out = &ctx->lz_tabs.back();
+      return IPB_OK;
+    }
+  LzAxis ax;
+  lz_axis(n_in, n_out, a, &ax);
+  const size_t ibytes = ((2 * n_out * sizeof(int) + 15) / 16) * 16, wbytes = ax.w.size() * sizeof(float);
+  char *dev = nullptr;
+  IPB_CUDA(ctx, cudaMalloc((void **)&dev, ibytes + wbytes));
+  std::vector<char> host(ibytes + wbytes);
+  memcpy(host.data(), ax.start.data(), n_out * sizeof(int));
+  memcpy(host.data() + n_out * sizeof(int), ax.count.data(), n_out * sizeof(int));
+  memcpy(host.data() + ibytes, ax.w.data(), wbytes);
+  cudaError_t e = cudaMemcpyAsync(dev, host.data(), host.size(), cudaMemcpyHostToDevice, ctx->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);  // `host` is pageable and goes out of scope
+  if (e != cudaSuccess) {
+    cudaFree(dev);
+    return fail(ctx, IPB_ERR_CUDA, "lanczos tables: %s", cudaGetErrorString(e));
+  }
+  if (ctx->lz_tabs.size() >= 8) {
+    IPB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // a launch may still read the table we drop
+    cudaFree(ctx->lz_tabs.front().start);
+    ctx->lz_tabs.erase(ctx->lz_tabs.begin());
+  }
+  ipb_ctx::LzTab t;
+  t.n_in = n_in; t.n_out = n_out; t.a = a; t.ksize = ax.ksize;
+  t.start = (int *)dev; t.count = (int *)dev + n_out; t.w = (float *)(dev + ibytes);
+  t.hstart = std::move(ax.start); t.hcount = std::move(ax.count);
+  ctx->lz_tabs.push_back(std::move(t));
+  *out = &ctx->lz_tabs.back();
+  return IPB_OK;
+}
+
 int ipb_lanczos_resize(ipb_ctx *ctx, ipb_buffer *in, size_t nwidth, size_t nheight, int a, ipb_buffer **out) {
   IPB_TRY(enter(ctx));
   if (!in || !out) return fail(ctx, IPB_ERR_INVALID, "null pointer");
@@ -1182,46 +1225,30 @@ int ipb_lanczos_resize(ipb_ctx *ctx, ipb_buffer *in, size_t nwidth, size_t nheig
   if (in->width >= (1u << 30) || in->height >= (1u << 30) || nwidth >= (1u << 30) || nheight >= (1u << 30))
     return fail(ctx, IPB_ERR_INVALID, "lanczos: frame too large");
   const size_t W = in->width, H = in->height, Cc = in->colors;
-  LzAxis ax, ay;
-  lz_axis(W, nwidth, a, &ax);
-  lz_axis(H, nheight, a, &ay);
+  const ipb_ctx::LzTab *tx = nullptr, *ty = nullptr;
+  IPB_TRY(lz_table(ctx, W, nwidth, a, &tx));
+  // copy what we need of the x table: fetching the y table may reorder / evict entries of the small cache
+  const int *sx = tx->start, *cx = tx->count;
+  const float *wx = tx->w;
+  const int kx = tx->ksize;
   // widest input span a 256-column tile of the horizontal pass stages in shared memory
   size_t max_span = 0;
   for (size_t x0 = 0; x0 < nwidth; x0 += 256) {
     const size_t x1 = x0 + 256 < nwidth ? x0 + 256 : nwidth;
-    const size_t span = (size_t)(ax.start[x1 - 1] + ax.count[x1 - 1] - ax.start[x0]) * Cc;
+    const size_t span = (size_t)(tx->hstart[x1 - 1] + tx->hcount[x1 - 1] - tx->hstart[x0]) * Cc;
     if (span > max_span) max_span = span;
   }
   if ((max_span + 8) * sizeof(float) > 200 * 1024)
     return fail(ctx, IPB_ERR_UNSUPPORTED, "lanczos: a 256-column tile spans %zu floats of a source row (scale too large)", max_span);
+  IPB_TRY(lz_table(ctx, H, nheight, a, &ty));
   ipb_buffer *o;
   IPB_TRY(new_buffer(ctx, nwidth, nheight, Cc, in->monochrome, false, &o));
-  const size_t nx = nwidth, ny = nheight;
-  const size_t ibytes = (2 * nx + 2 * ny) * sizeof(int);
-  const size_t wbytes = (nx * (size_t)ax.ksize + ny * (size_t)ay.ksize) * sizeof(float);
-  const size_t midbytes = H * nwidth * Cc * sizeof(float);
-  char *dev = nullptr;
-  cudaError_t e = ipb_malloc_async(ctx, (void **)&dev, ibytes + wbytes + midbytes + 64);
+  float *mid = nullptr;
+  cudaError_t e = ipb_malloc_async(ctx, (void **)&mid, H * nwidth * Cc * sizeof(float));
   if (e != cudaSuccess) { ipb_buffer_release(o); return fail(ctx, IPB_ERR_NOMEM, "lanczos: %s", cudaGetErrorString(e)); }
-  // one pageable staging block: [sx cx sy cy | wx wy]
-  std::vector<char> host(ibytes + wbytes);
-  int *hi = (int *)host.data();
-  memcpy(hi, ax.start.data(), nx * sizeof(int));
-  memcpy(hi + nx, ax.count.data(), nx * sizeof(int));
-  memcpy(hi + 2 * nx, ay.start.data(), ny * sizeof(int));
-  memcpy(hi + 2 * nx + ny, ay.count.data(), ny * sizeof(int));
-  float *hw = (float *)(host.data() + ibytes);
-  memcpy(hw, ax.w.data(), ax.w.size() * sizeof(float));
-  memcpy(hw + ax.w.size(), ay.w.data(), ay.w.size() * sizeof(float));
-  e = cudaMemcpyAsync(dev, host.data(), host.size(), cudaMemcpyHostToDevice, ctx->stream);
-  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);  // `host` is pageable and goes out of scope
-  const int *di = (const int *)dev;
-  const float *dw = (const float *)(dev + ibytes);
-  float *mid = (float *)(dev + ((ibytes + wbytes + 63) / 64) * 64);
-  if (e == cudaSuccess)
-    e = launch_lanczos(ctx->stream, in->dptr, W, H, Cc, nwidth, nheight, di, di + nx, dw, ax.ksize, max_span, di + 2 * nx,
-                       di + 2 * nx + ny, dw + ax.w.size(), ay.ksize, mid, o->dptr);
-  cudaFreeAsync(dev, ctx->stream);
+  e = launch_lanczos(ctx->stream, in->dptr, W, H, Cc, nwidth, nheight, sx, cx, wx, kx, max_span, ty->start, ty->count, ty->w,
+                     ty->ksize, mid, o->dptr);
+  cudaFreeAsync(mid, ctx->stream);
   if (e != cudaSuccess) { ipb_buffer_release(o); return fail(ctx, IPB_ERR_CUDA, "lanczos: %s", cudaGetErrorString(e)); }
   ctx->launches += 2;
   *out = o;
