@@ -592,8 +592,8 @@ k_fused_full(const __grid_constant__ FullParams p, const __grid_constant__ CfaDe
         const float4 mid = *reinterpret_cast<const float4 *>(tp + k * kTileStride + 1);
         w[k][0] = tp[k * kTileStride];
         w[k][1] = mid.x; w[k][2] = mid.y; w[k][3] = mid.z; w[k][4] = mid.w;
-        w[k][5] = tp[k * kTileStride + 5];
-      }
+        w[k][5] = tp[k * kTileStride + 5];  // (fetching the two halo columns from the neighbouring lanes by shuffle
+      }                                     //  instead was measured slower: 252 vs 246 us per C2 frame)
 
       float cr[4], cg[4], cb[4], ce[4];
       if (fast) {
