@@ -130,3 +130,23 @@ def test_cuda_fused_matches_golden_through_the_chain(ip, orc, ctx, name):
     cur = p.ops.basecurve.run(p.globals, p.ops.tolab.run(p.globals, buf))
     want = p.ops.gamma.run(p.globals, p.ops.fromlab.run(p.globals, cur)).to_numpy()
     assert_bit_exact(fused, want, f"{name}: fused vs golden demosaic + per-op chain")
+
+
+def test_committed_fixtures_are_what_the_generator_writes(tmp_path, monkeypatch):
+    """tests/golden/*.npz are exactly the output of tests/golden/make_golden.py (the independent numpy restatement)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_golden", os.path.join(GOLD, "make_golden.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    monkeypatch.setattr(mod, "HERE", str(tmp_path))
+    mod.main()
+    names = sorted(os.path.basename(p) for p in glob.glob(os.path.join(GOLD, "*.npz")))
+    assert names == sorted(os.listdir(tmp_path))
+    for n in names:
+        a, b = np.load(os.path.join(GOLD, n)), np.load(os.path.join(tmp_path, n))
+        assert sorted(a.files) == sorted(b.files)
+        for k in a.files:
+            if a[k].dtype.kind == "f":
+                assert np.array_equal(a[k].view(np.uint32) if a[k].dtype == np.float32 else a[k], b[k].view(np.uint32) if b[k].dtype == np.float32 else b[k], equal_nan=False) or np.array_equal(a[k], b[k], equal_nan=True), (n, k)
+            else:
+                assert np.array_equal(a[k], b[k]), (n, k)
