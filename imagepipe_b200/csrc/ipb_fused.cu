@@ -77,6 +77,7 @@ struct Smem {
   float spl[kMaxSplinePts + 2][8];  // [0] below the first knot, [1 + i] segment i, [n] at/above the last: x, y, c1, c2, c3
   uint2 taps[kMaxPatPos];       // per pattern position: 9-bit tap masks of colours 0..3, 16 bits each
   alignas(8) unsigned long long mbar;
+  alignas(8) unsigned long long mbar_lut;      // completion of the two bulk copies that bring the tables in
   int conv_ctr[2];              // dynamic chunk counters of the conversion phase (alternating per tile)
 };
 static_assert(sizeof(Smem) <= 232448, "Smem exceeds the 227 KB a CTA can opt in to");
@@ -478,17 +479,25 @@ k_fused_full(const __grid_constant__ FullParams p, const __grid_constant__ CfaDe
     if (tx >= p.tiles_x) { tx -= p.tiles_x; ty++; }
   };
 
+  // Both 64 KB tables come in by bulk asynchronous copy (the TMA engine, no tensor map), issued by one thread and
+  // overlapped with the first tile's copy, the tap / spline tables and the first conversion; everybody waits for them
+  // just before the first look-up.
+  const uint32_t bar_lut = smem_u32(&sm.mbar_lut);
   if (tid == 0) {
     sm.conv_ctr[0] = 0;
     sm.conv_ctr[1] = 0;
-    if (p.use_tma) {
-      mbar_init(bar, 1);
-      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      if ((int)blockIdx.x < ntiles) issue_tile(p, &tmap, raw_addr, bar, txi, tyi);
-    }
+    mbar_init(bar, 1);
+    mbar_init(bar_lut, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    if (p.use_tma && (int)blockIdx.x < ntiles) issue_tile(p, &tmap, raw_addr, bar, txi, tyi);
+    constexpr uint32_t kLutBytes = kLutEntries * (uint32_t)sizeof(float2);
+    mbar_expect_tx(bar_lut, 2 * kLutBytes);
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(sm.lut_lab)), "l"(p.lut_lab), "r"(kLutBytes), "r"(bar_lut) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(sm.lut_out)), "l"(p.lut_out), "r"(kLutBytes), "r"(bar_lut) : "memory");
   }
-  load_luts(sm.lut_lab, sm.lut_out, p.lut_lab, p.lut_out);
   build_taps(sm, cfa, p.pw, p.ph);
   for (int i = tid; i < kMaxSplinePts + 2; i += kNT) {
     float e[5] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
@@ -569,6 +578,7 @@ k_fused_full(const __grid_constant__ FullParams p, const __grid_constant__ CfaDe
     if (tid == 0 && p.use_tma && (int)(blockIdx.x + gridDim.x) < ntiles) issue_tile(p, &tmap, raw_addr, bar, ntx, nty);
   }
 
+  mbar_wait(bar_lut, 0);  // the tables are in
   int it = 0;
   for (int t = blockIdx.x; t < ntiles; t += gridDim.x, it++) {
     const int ty0 = p.out_row0 + tyi * kTH, tx0 = txi * kTW;
