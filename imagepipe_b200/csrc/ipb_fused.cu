@@ -109,17 +109,6 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map
       : "memory");
 }
 
-__device__ __forceinline__ void load_luts(float2 *s_lab, float2 *s_out, const float2 *lab, const float2 *outl) {
-  const uint4 *a = reinterpret_cast<const uint4 *>(lab);
-  const uint4 *b = reinterpret_cast<const uint4 *>(outl);
-  uint4 *da = reinterpret_cast<uint4 *>(s_lab);
-  uint4 *db = reinterpret_cast<uint4 *>(s_out);
-  for (int i = threadIdx.x; i < kLutEntries / 2; i += blockDim.x) {
-    da[i] = __ldg(a + i);
-    db[i] = __ldg(b + i);
-  }
-}
-
 // demosaic.rs:77-90 for every position of the CFA period: which of the nine 3x3 taps feed which colour bin.
 // Taps of the centre's own colour other than the centre itself go to the discarded fifth bin.
 template <class S>
@@ -739,6 +728,7 @@ struct SmemScaled {
   float2 lut_lab[kLutEntries];
   float2 lut_gamma[kLutEntries];
   uint8_t pat[48 * kPatStride];
+  alignas(8) unsigned long long mbar_lut;  // completion of the bulk copies that bring the two tables in
 };
 
 constexpr int kNTScaled = 1024;
@@ -861,7 +851,21 @@ k_fused_scaled(const __grid_constant__ ScaledParams p, const __grid_constant__ C
                const __grid_constant__ ColorParams P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   SmemScaled &sm = *reinterpret_cast<SmemScaled *>(smem_raw);
-  load_luts(sm.lut_lab, sm.lut_gamma, p.lut_lab, p.lut_gamma);
+  // the tables come in by bulk asynchronous copy while the first windows are accumulated (they are first needed by
+  // the colour chain)
+  const uint32_t bar_lut = smem_u32(&sm.mbar_lut);
+  if (threadIdx.x == 0) {
+    mbar_init(bar_lut, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    constexpr uint32_t kLutBytes = kLutEntries * (uint32_t)sizeof(float2);
+    mbar_expect_tx(bar_lut, 2 * kLutBytes);
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(sm.lut_lab)), "l"(p.lut_lab), "r"(kLutBytes), "r"(bar_lut) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(sm.lut_gamma)), "l"(p.lut_gamma), "r"(kLutBytes), "r"(bar_lut) : "memory");
+  }
+  bool luts_in = false;
   bool has_e = false;
   for (int i = threadIdx.x; i < 48 * kPatStride; i += blockDim.x) {
     const int r = i / kPatStride, c = i - r * kPatStride;
@@ -935,6 +939,10 @@ k_fused_scaled(const __grid_constant__ ScaledParams p, const __grid_constant__ C
 #pragma unroll
     for (int k = 0; k < 4; k++) px[k] = acc[k].y > 0.0f ? __fdiv_rn(acc[k].x, acc[k].y) : 0.0f;
     float r[4] = {0.f, 0.f, 0.f, 0.f}, g[4] = {0.f, 0.f, 0.f, 0.f}, b[4] = {0.f, 0.f, 0.f, 0.f};
+    if (!luts_in) {
+      mbar_wait(bar_lut, 0);
+      luts_in = true;
+    }
     color_chain<true>(P, lab, gam, px[0], px[1], px[2], px[3], r[0], g[0], b[0]);
     if (live) store_px4<OUT>(p.out, (size_t)(idx), 1, r, g, b);
   }
