@@ -272,7 +272,7 @@ int ipb_pipeline_run_cached(ipb_pipeline *p, ipb_cache *cache, ipb_buffer **out)
  * final buffer came from the cache) and how many ops ran */
 void ipb_pipeline_last_run_info(const ipb_pipeline *p, int *startpos, int *ops_run);
 /* Pipeline::output_8bit / output_16bit — pipeline.rs:377-469 (incl. the non-raw fast path).
- * dst capacity is in elements; *width/*height receive the image size. dst_on_device == 0 synchronises. */
+ * dst capacity is in elements; *width and *height receive the image size. dst_on_device == 0 synchronises. */
 int ipb_pipeline_output_8bit(ipb_pipeline *p, uint8_t *dst, size_t dst_capacity, int dst_on_device, size_t *width,
                              size_t *height);
 int ipb_pipeline_output_16bit(ipb_pipeline *p, uint16_t *dst, size_t dst_capacity, int dst_on_device,

@@ -62,3 +62,14 @@ def test_no_cpu_fallback_without_a_device(ip):
     with pytest.raises(ip.IpbError) as e:
         ip.Context(0)
     assert "CUDA" in str(e.value)
+
+
+def test_header_is_plain_c_and_cxx(tmp_path):
+    """include/ipb200.h compiles as C11 and as C++17 on its own (no CUDA / torch types in the ABI)."""
+    import subprocess
+    hdr = os.path.join(ROOT, "include", "ipb200.h")
+    src = tmp_path / "t.c"
+    src.write_text('#include "ipb200.h"\nint main(void) { ipb_settings s = {0}; ipb_ops o; (void)o; return (int)s.maxwidth + (IPB_VERSION == 0); }\n')
+    for cmd in (["gcc", "-std=c11", "-Wall", "-Werror", "-pedantic", "-fsyntax-only"], ["g++", "-x", "c++", "-std=c++17", "-Wall", "-fsyntax-only"]):
+        r = subprocess.run(cmd + ["-I", os.path.dirname(hdr), str(src)], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
