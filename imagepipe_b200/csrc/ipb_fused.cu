@@ -619,6 +619,44 @@ k_fused_full(const __grid_constant__ FullParams p, const __grid_constant__ CfaDe
           cb[j] = a_col == 0 ? vo : va;
           ce[j] = 0.0f;
         }
+      } else if (BAYER) {
+        // RGB Bayer warp with pixels on the frame border: the same neighbourhoods, but a tap outside the frame is
+        // dropped from sum and count (demosaic.rs:103-107).  Sums start at 0.0 and take the taps in the reference's
+        // order with +0.0 for a dropped one (a no-op on a partial sum, which is never -0.0); the mean is s / count
+        // through the exact reciprocal form for counts 1..4.  Pixels beyond the frame (partial tiles) compute on
+        // whatever the tile holds and are not stored.
+        const int cfirst = (y & 1) ? c10 : c00;
+        const bool green_first = cfirst == 1;
+        const int a_col = green_first ? ((y & 1) ? cfa.pat[49] : cfa.pat[1]) : cfirst;
+        const bool has_n = y > 0, has_s = y < p.height - 1;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          const int x = x0 + j;
+          const bool has_w = x > 0, has_e = x < p.width - 1;
+          const bool is_green = green_first ? ((j & 1) == 0) : ((j & 1) == 1);
+          const float c = w[1][j + 1];
+          const float n = has_n ? w[0][j + 1] : 0.0f, s = has_s ? w[2][j + 1] : 0.0f;
+          const float wv = has_w ? w[1][j] : 0.0f, e = has_e ? w[1][j + 2] : 0.0f;
+          float va, vg, vo;
+          if (is_green) {
+            const float2 ra = kTapRcp[max((int)has_w + (int)has_e, 1)], ro = kTapRcp[max((int)has_n + (int)has_s, 1)];
+            va = div_rc((0.0f + wv) + e, ra.y, ra.x);
+            vg = c;
+            vo = div_rc((0.0f + n) + s, ro.y, ro.x);
+          } else {
+            const float nw = (has_n && has_w) ? w[0][j] : 0.0f, ne = (has_n && has_e) ? w[0][j + 2] : 0.0f;
+            const float sw = (has_s && has_w) ? w[2][j] : 0.0f, se = (has_s && has_e) ? w[2][j + 2] : 0.0f;
+            const float2 rg = kTapRcp[max((int)has_n + (int)has_w + (int)has_e + (int)has_s, 1)];
+            const float2 ro = kTapRcp[max(((int)has_n + (int)has_s) * ((int)has_w + (int)has_e), 1)];
+            va = c;
+            vg = div_rc((((0.0f + n) + wv) + e) + s, rg.y, rg.x);
+            vo = div_rc((((0.0f + nw) + ne) + sw) + se, ro.y, ro.x);
+          }
+          cr[j] = a_col == 0 ? va : vo;
+          cg[j] = vg;
+          cb[j] = a_col == 0 ? vo : va;
+          ce[j] = 0.0f;
+        }
       } else {
         // generic CFA / frame border: per-position tap masks, out-of-frame taps dropped from sum and count.
         // With TMA staging the tile holds whatever lies outside the cropped frame; the masks never select it.

@@ -1355,8 +1355,9 @@ struct FusedPlan {
 static bool fused_params_bounded(const ipb_pipeline *p) {
   const ipb_gofloat &g = p->ops.gofloat;
   const float black = g.blacklevels[0], range = g.whitelevels[0] - g.blacklevels[0];
-  if (!std::isfinite(black) || !std::isfinite(range) || fabsf(black) > 65535.0f || !(fabsf(range) >= 1.0f) ||
-      fabsf(range) > 131072.0f)
+  // (a negative range — white below black — would turn exact zeros into -0.0, which the kernels' "+0.0 is a no-op"
+  // sums do not reproduce; such metadata runs op by op)
+  if (!std::isfinite(black) || !std::isfinite(range) || fabsf(black) > 65535.0f || !(range >= 1.0f) || range > 131072.0f)
     return false;
   float mul[4];
   normalize_wbs(p->ops.tolab.wb_coeffs, mul);
