@@ -16,7 +16,9 @@
  * tests/maxsize_test.rs).  Functions the reference does not test itself
  * (gofloat::run_raw, demosaic::full, scaled_demosaic numerics, CFA::color_at from the
  * absent rawloader 0.37 crate) are "parity unpinned" by the reference and are pinned
- * only by hand-derived vectors in tests/golden/.
+ * only by tests/golden/: vectors from a second, independent restatement (scalar numpy-f32
+ * loops written from the reference source, tests/golden/make_golden.py) that this oracle
+ * reproduces bit for bit (tests/test_golden.py).
  *
  * Arithmetic: f32 everywhere, compiled -ffp-contract=off (Rust never contracts to FMA),
  * glibc cbrtf/powf/exp2f/sinf/cosf stand in for Rust std (which calls the same libm).
