@@ -158,6 +158,11 @@ def lib():
         "ipb_pipeline_output_8bit_stripe": (i, [vp, vp, sz, i, szp, szp]),
         "ipb_pipeline_set_tma": (i, [vp, i]),
         "ipb_pipeline_set_band_mb": (i, [vp, i]),
+        "ipb_pipeline_set_speculative": (i, [vp, i]),
+        "ipb_ctx_set_spec": (i, [vp, C.c_float, i]),
+        "ipb_spec_bound": (i, [vp, C.c_float, C.POINTER(C.c_float)]),
+        "ipb_ctx_spec_stats": (i, [vp, C.POINTER(C.c_ulonglong), i]),
+        "ipb_pipeline_spec_probe": (i, [vp, C.POINTER(C.c_float), C.POINTER(C.c_double), C.POINTER(C.c_float)]),
         "ipb_selftest_gamma8": (i, [vp, C.POINTER(C.c_ulonglong)]),
         "ipb_gamma_pack_8bit": (i, [vp, vp, sz, vp]),
         "ipb_synth_cfa_u16": (i, [vp, C.c_uint64, sz, sz, sz, vp]),

@@ -20,6 +20,7 @@
 #include <vector>
 
 #include "ipb_internal.h"
+#include "ipb_spec.h"
 
 using namespace ipb;
 
@@ -42,6 +43,18 @@ struct ipb_ctx {
   // default pool hands everything back to the driver at every synchronisation: a 384 MB OpBuffer then costs
   // milliseconds to map again).  Like the reference's allocator, it holds on to what a pipeline run needed.
   cudaMemPool_t pool = nullptr;
+  // speculative 8-bit kernel (ipb_spec.cu): self-test results, device tables, the parameter set they were built for
+  int spec_ok = 0;                  // the shared window starts where the gamma table's addressing assumes it does
+  float mufu_cbrt_err = 1.0f;       // measured max relative error of the XU-pipe cube root (every float in [2^-8, 4])
+  int spec_threads = 512;           // CTA size of k_spec8 (512: two CTAs per SM, 1024: one)
+  float spec_delta_override = 0.0f; // tests: force the bound (0 = the certified one)
+  uint32_t *spec_g8a = nullptr;
+  float2 *spec_stab = nullptr;
+  unsigned long long *spec_stats = nullptr;   // 8 counters, see SpecParams::stats
+  void *spec_stage = nullptr;       // pinned staging for table uploads (capturable copies)
+  SpecTables spec_tab{};
+  int spec_tab_state = 0;           // 0: none, 1: valid for spec_key, -1: spec_key cannot take the speculative path
+  std::vector<unsigned char> spec_key;
   // copy streams + events of the chunk-pipelined host<->device path (created on first use)
   cudaStream_t copy_in = nullptr, copy_out = nullptr;
   std::vector<cudaEvent_t> events;
@@ -63,6 +76,7 @@ struct ipb_pipeline {
   ipb_settings settings{};
   int fused = 1;
   int use_tma = 1;
+  int spec = 1;      // 8-bit output of RGB Bayer frames through the speculative kernel (results identical; 0: k_fused_full)
   int band_mb = 16;  // host<->device paths: band size of the overlapped H2D / kernel / D2H schedule (0 = no bands)
   // golevel_rc_exact() result for the last (black, range) pair: the check walks all 65536 samples
   bool rc_cached = false;
@@ -475,6 +489,9 @@ bool build_gamma8(const float *t, std::vector<Gamma8Entry> *out) {
   return true;
 }
 
+std::vector<Gamma8Entry> g_gamma8;  // built once per process by the first context
+bool g_gamma8_ok = false;
+
 int upload_lut(ipb_ctx *ctx, const float *t, float2 **out) {
   std::vector<float2> host(kLutEntries);
   for (int i = 0; i < kLutEntries; i++) host[i] = make_float2(t[i], t[i + 1] - t[i]);
@@ -596,10 +613,10 @@ int ipb_ctx_create(int device, void *stream, ipb_ctx **out) {
   if ((rc = upload_lut(ctx, T.fwd, &ctx->lut_gamma)) != IPB_OK) return bail(rc);
   if ((rc = upload_lut(ctx, T.rev, &ctx->lut_rev)) != IPB_OK) return bail(rc);
   {
-    static std::vector<Gamma8Entry> g8;
-    static bool g8_ok = false;
+    static std::vector<Gamma8Entry> &g8 = g_gamma8;
+    static bool &g8_ok = g_gamma8_ok;
     static std::once_flag once;
-    std::call_once(once, [&] { g8_ok = build_gamma8(T.fwd, &g8); });
+    std::call_once(once, [&] { if (g8.empty()) g8_ok = build_gamma8(T.fwd, &g8); });
     if (g8_ok) {
       static_assert(sizeof(Gamma8Entry) == sizeof(float2), "table entry layout");
       if ((e = cudaMalloc((void **)&ctx->lut_gamma8, kLutEntries * sizeof(float2))) != cudaSuccess ||
@@ -615,6 +632,27 @@ int ipb_ctx_create(int device, void *stream, ipb_ctx **out) {
     ipb_ctx_destroy(ctx);
     return IPB_ERR_CUDA;
   }
+  // speculative kernel: buffers for its tables, and its self-test (shared window base, XU-pipe cube root accuracy)
+  {
+    unsigned int *d_st = nullptr, h_st[2] = {0, 0};
+    if ((e = cudaMalloc((void **)&ctx->spec_g8a, kSpecG8Entries * sizeof(uint32_t))) != cudaSuccess ||
+        (e = cudaMalloc((void **)&ctx->spec_stab, kSpecSTabEntries * sizeof(float2))) != cudaSuccess ||
+        (e = cudaMalloc((void **)&ctx->spec_stats, 8 * sizeof(unsigned long long))) != cudaSuccess ||
+        (e = cudaMemset(ctx->spec_stats, 0, 8 * sizeof(unsigned long long))) != cudaSuccess ||
+        (e = cudaHostAlloc(&ctx->spec_stage, kSpecG8Entries * sizeof(uint32_t) + kSpecSTabEntries * sizeof(float2), cudaHostAllocDefault)) != cudaSuccess ||
+        (e = cudaMalloc((void **)&d_st, sizeof(h_st))) != cudaSuccess ||
+        (e = cudaMemset(d_st, 0, sizeof(h_st))) != cudaSuccess ||
+        (e = launch_spec_selftest(ctx->stream, d_st)) != cudaSuccess ||
+        (e = cudaMemcpyAsync(h_st, d_st, sizeof(h_st), cudaMemcpyDeviceToHost, ctx->stream)) != cudaSuccess ||
+        (e = cudaStreamSynchronize(ctx->stream)) != cudaSuccess) {
+      ctx->err = std::string("speculative kernel self-test: ") + cudaGetErrorString(e);
+      if (d_st) cudaFree(d_st);
+      return bail(IPB_ERR_CUDA);
+    }
+    cudaFree(d_st);
+    memcpy(&ctx->mufu_cbrt_err, &h_st[1], 4);
+    ctx->spec_ok = (h_st[0] == kSpecSmemBase && g_gamma8_ok && ctx->mufu_cbrt_err < 4.0e-6f) ? 1 : 0;
+  }
   *out = ctx;
   return IPB_OK;
 }
@@ -628,6 +666,10 @@ void ipb_ctx_destroy(ipb_ctx *ctx) {
   if (ctx->lut_rev) cudaFree(ctx->lut_rev);
   if (ctx->lut_gamma8) cudaFree(ctx->lut_gamma8);
   if (ctx->cbrt_tab) cudaFree(ctx->cbrt_tab);
+  if (ctx->spec_g8a) cudaFree(ctx->spec_g8a);
+  if (ctx->spec_stab) cudaFree(ctx->spec_stab);
+  if (ctx->spec_stats) cudaFree(ctx->spec_stats);
+  if (ctx->spec_stage) cudaFreeHost(ctx->spec_stage);
   for (auto &t : ctx->lz_tabs) cudaFree(t.start);
   if (ctx->copy_in) { cudaStreamSynchronize(ctx->copy_in); cudaStreamDestroy(ctx->copy_in); }
   if (ctx->copy_out) { cudaStreamSynchronize(ctx->copy_out); cudaStreamDestroy(ctx->copy_out); }
@@ -1485,6 +1527,48 @@ static int ensure_cbrt_table(ipb_ctx *ctx) {
   return IPB_OK;
 }
 
+// Tables and constants of the speculative kernel for this parameter set, rebuilt (and uploaded in stream order) only
+// when the colour parameters, the level mapping or the forced bound change.  *use = false: these parameters stay on
+// k_fused_full.
+static int ensure_spec_tables(ipb_ctx *ctx, const ColorParams &P, float black, float range, bool *use) {
+  *use = false;
+  if (!ctx->spec_ok) return IPB_OK;
+  std::vector<unsigned char> key(sizeof(ColorParams) + 3 * sizeof(float));
+  memcpy(key.data(), &P, sizeof(ColorParams));
+  memcpy(key.data() + sizeof(ColorParams), &black, 4);
+  memcpy(key.data() + sizeof(ColorParams) + 4, &range, 4);
+  memcpy(key.data() + sizeof(ColorParams) + 8, &ctx->spec_delta_override, 4);
+  if (ctx->spec_tab_state != 0 && key == ctx->spec_key) {
+    *use = ctx->spec_tab_state > 0;
+    return IPB_OK;
+  }
+  ctx->spec_key = key;
+  ctx->spec_tab_state = -1;
+  std::vector<float> thr;
+  for (const Gamma8Entry &g : g_gamma8)
+    if (g.thr <= 1.0f) thr.push_back(g.thr);
+  std::vector<uint32_t> g8a;
+  std::vector<float2> stab;
+  SpecTables T{};
+  if (!spec_build(P, black, range, ctx->mufu_cbrt_err, ctx->spec_delta_override, thr, &g8a, &stab, &T.consts, &T.delta))
+    return IPB_OK;
+  // the previous upload may still be in flight from the pinned staging buffer
+  IPB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  unsigned char *st = (unsigned char *)ctx->spec_stage;
+  memcpy(st, g8a.data(), kSpecG8Entries * sizeof(uint32_t));
+  memcpy(st + kSpecG8Entries * sizeof(uint32_t), stab.data(), kSpecSTabEntries * sizeof(float2));
+  IPB_CUDA(ctx, cudaMemcpyAsync(ctx->spec_g8a, st, kSpecG8Entries * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+  IPB_CUDA(ctx, cudaMemcpyAsync(ctx->spec_stab, st + kSpecG8Entries * sizeof(uint32_t), kSpecSTabEntries * sizeof(float2),
+                                cudaMemcpyHostToDevice, ctx->stream));
+  T.g8a = ctx->spec_g8a;
+  T.stab = ctx->spec_stab;
+  T.stats = ctx->spec_stats;
+  ctx->spec_tab = T;
+  ctx->spec_tab_state = 1;
+  *use = true;
+  return IPB_OK;
+}
+
 // Launch the fused kernel for output rows [r0, r1) into `out` (device, row r0 first).  `raw_dev` holds the
 // un-cropped source rows [have0, have0 + have_rows) on the device.
 static int launch_fused_rows(ipb_pipeline *p, const FusedPlan &plan, const ColorParams &P, int out_kind, size_t r0,
@@ -1524,6 +1608,18 @@ static int launch_fused_rows(ipb_pipeline *p, const FusedPlan &plan, const Color
   if (plan.mode == kFusedFull) IPB_TRY(ensure_cbrt_table(ctx));
   a.cbrt_tab = ctx->cbrt_tab;
   a.use_tma = p->use_tma;
+  // 8-bit output of a full-resolution RGB Bayer frame: the speculative kernel (byte-identical, about a third of the
+  // instructions), when its preconditions hold
+  if (plan.mode == kFusedFull && p->spec && a.exact_rc && spec_supported(a, plan.cfa, P)) {
+    bool use = false;
+    IPB_TRY(ensure_spec_tables(ctx, P, a.black, a.range, &use));
+    if (use) {
+      cudaError_t es = launch_fused_spec8(ctx->stream, a, plan.cfa, P, ctx->spec_tab, ctx->sm_count, ctx->spec_threads);
+      if (es != cudaSuccess) return fail(ctx, IPB_ERR_CUDA, "speculative kernel: %s %s", cudaGetErrorString(es), spec_last_error());
+      ctx->launches++;
+      return IPB_OK;
+    }
+  }
   cudaError_t e = plan.mode == kFusedFull ? launch_fused_full(ctx->stream, a, plan.cfa, P, ctx->sm_count)
                                           : launch_fused_scaled(ctx->stream, a, plan.cfa, P, ctx->sm_count);
   if (e != cudaSuccess) return fail(ctx, IPB_ERR_CUDA, "fused kernel: %s %s", cudaGetErrorString(e), fused_last_error());
@@ -2079,6 +2175,103 @@ int ipb_pipeline_output_8bit_stripe(ipb_pipeline *p, uint8_t *dst, size_t dst_ca
 int ipb_pipeline_set_band_mb(ipb_pipeline *p, int megabytes) {
   if (!p || megabytes < 0) return IPB_ERR_INVALID;
   p->band_mb = megabytes;
+  return IPB_OK;
+}
+
+int ipb_pipeline_set_speculative(ipb_pipeline *p, int on) {
+  if (!p) return IPB_ERR_INVALID;
+  p->spec = on ? 1 : 0;
+  return IPB_OK;
+}
+
+int ipb_ctx_set_spec(ipb_ctx *ctx, float delta, int threads) {
+  IPB_TRY(enter(ctx));
+  if (!(delta >= 0.0f) || (threads != 512 && threads != 1024)) return fail(ctx, IPB_ERR_INVALID, "set_spec: delta >= 0, threads 512 or 1024");
+  ctx->spec_delta_override = delta;
+  ctx->spec_threads = threads;
+  return IPB_OK;
+}
+
+int ipb_ctx_spec_stats(ipb_ctx *ctx, unsigned long long out[4], int reset) {
+  IPB_TRY(enter(ctx));
+  if (!out) return IPB_ERR_INVALID;
+  unsigned long long h[8] = {0};
+  IPB_CUDA(ctx, cudaMemcpyAsync(h, ctx->spec_stats, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+  if (reset) IPB_CUDA(ctx, cudaMemsetAsync(ctx->spec_stats, 0, sizeof(h), ctx->stream));
+  IPB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  uint32_t db = 0, mb = 0;
+  const float d = ctx->spec_tab_state > 0 ? ctx->spec_tab.delta : 0.0f;
+  memcpy(&db, &d, 4);
+  memcpy(&mb, &ctx->mufu_cbrt_err, 4);
+  out[0] = h[0]; out[1] = h[4]; out[2] = db; out[3] = mb;
+  return IPB_OK;
+}
+
+int ipb_spec_bound(const ipb_ops *ops, float mufu_rel_err, float *delta) {
+  if (!ops || !delta) return IPB_ERR_INVALID;
+  static std::once_flag once;
+  std::call_once(once, [] { if (!g_gamma8_ok && g_gamma8.empty()) g_gamma8_ok = build_gamma8(tables().fwd, &g_gamma8); });
+  if (!g_gamma8_ok) return IPB_ERR_UNSUPPORTED;
+  ColorParams P;
+  memset(&P, 0, sizeof(P));
+  fill_tolab(&P, &ops->tolab, 0);
+  P.use_e = 0;
+  if (!build_spline(&ops->basecurve, &P.sp)) return IPB_ERR_INVALID;
+  std::vector<float> thr;
+  for (const Gamma8Entry &g : g_gamma8)
+    if (g.thr <= 1.0f) thr.push_back(g.thr);
+  std::vector<uint32_t> g8a;
+  std::vector<float2> stab;
+  SpecParams c;
+  const float black = ops->gofloat.blacklevels[0], range = ops->gofloat.whitelevels[0] - black;
+  return spec_build(P, black, range, mufu_rel_err, 0.0f, thr, &g8a, &stab, &c, delta) ? IPB_OK : IPB_ERR_UNSUPPORTED;
+}
+
+int ipb_pipeline_spec_probe(ipb_pipeline *p, float *max_dev, double *mean_dev, float *delta) {
+  if (!p || !max_dev || !mean_dev || !delta) return IPB_ERR_INVALID;
+  ipb_ctx *ctx = p->ctx;
+  IPB_TRY(enter(ctx));
+  if (p->has_stripe) return fail(ctx, IPB_ERR_UNSUPPORTED, "spec_probe: whole-frame sources only");
+  const int keep_linear = p->settings.linear;
+  p->settings.linear = 0;
+  negotiate(p, nullptr, nullptr);
+  FusedPlan plan;
+  int rc = plan_fused(p, &plan);
+  ColorParams P;
+  if (rc == IPB_OK) rc = plan.mode == kFusedFull ? fill_color_params(p, plan, &P) : fail(ctx, IPB_ERR_UNSUPPORTED, "spec_probe: not the full-resolution fused path");
+  p->settings.linear = keep_linear;
+  IPB_TRY(rc);
+  const uint16_t *raw = (const uint16_t *)p->image.data;
+  const size_t bytes = p->image.width * p->image.height * sizeof(uint16_t);
+  if (!p->image.on_device) {
+    IPB_TRY(ensure_stage(ctx, &p->stage_in, &p->stage_in_bytes, bytes));
+    IPB_CUDA(ctx, cudaMemcpyAsync(p->stage_in, raw, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    raw = (const uint16_t *)p->stage_in;
+  }
+  FusedArgs a;
+  memset(&a, 0, sizeof(a));
+  a.raw = raw; a.raw_pitch = p->image.width; a.src_row0 = 0; a.src_rows = p->image.height;
+  a.crop_x = plan.crop_x; a.crop_y = plan.crop_y; a.width = plan.width; a.height = plan.height;
+  a.out_row0 = 0; a.out_row1 = plan.height; a.out_width = plan.width; a.out_height = plan.height;
+  a.out_kind = kOutU8;
+  a.black = p->ops.gofloat.blacklevels[0];
+  a.range = p->ops.gofloat.whitelevels[0] - a.black;
+  a.range_rc = 1.0f / a.range;
+  a.exact_rc = golevel_rc_exact(a.black, a.range, a.range_rc) ? 1 : 0;
+  a.lut_lab = ctx->lut_lab; a.lut_gamma = ctx->lut_gamma; a.lut_gamma8 = ctx->lut_gamma8;
+  a.use_tma = 1;
+  bool use = false;
+  if (a.exact_rc && spec_supported(a, plan.cfa, P)) IPB_TRY(ensure_spec_tables(ctx, P, a.black, a.range, &use));
+  if (!use) return fail(ctx, IPB_ERR_UNSUPPORTED, "spec_probe: these parameters do not take the speculative path");
+  IPB_CUDA(ctx, cudaMemsetAsync(ctx->spec_stats + 1, 0, 3 * sizeof(unsigned long long), ctx->stream));
+  IPB_LAUNCH(ctx, launch_spec_probe(ctx->stream, a, plan.cfa, P, ctx->spec_tab, ctx->sm_count));
+  unsigned long long h[4] = {0};
+  IPB_CUDA(ctx, cudaMemcpyAsync(h, ctx->spec_stats, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+  IPB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  const uint32_t mb = (uint32_t)h[1];
+  memcpy(max_dev, &mb, 4);
+  *mean_dev = h[2] ? (double)h[3] / 1099511627776.0 / (double)h[2] : 0.0;
+  *delta = ctx->spec_tab.delta;
   return IPB_OK;
 }
 

@@ -1,0 +1,713 @@
+// ipb_spec.cu — the speculative 8-bit raw -> sRGB kernel (the roofline kernel of BASELINE config 2 / 5).
+//
+// output_8bit of a full-resolution RGB Bayer frame is a function  u16 CFA samples -> 3 bytes per pixel.  The bytes
+// are decided by which of the 255 thresholds of  v -> output8bit(apply_srgb_gamma(clamp(v)))  (gamma.rs:21,
+// color_conversions.rs:323-325; monotone in v, ipb_host.cu build_gamma8) the linear value v of a channel lies above.
+// So the reference's f32 arithmetic has to be reproduced bit for bit only where v is close to a threshold:
+//
+//   cheap pass   every interior pixel goes through a restatement of the chain in contracted arithmetic: level
+//                mapping by a reciprocal multiply, Bayer demosaic on pixel pairs (packed f32x2), white balance and both
+//                matrices folded into FFMA2 chains, the Lab transfer function on the XU pipe (ex2(lg2(v)/3), no table),
+//                to_lab -> basecurve -> from_lab collapsed to   t = f(v) + (S(f(Y)) - f(Y)),  v' = t^3   with S the
+//                basecurve in f-space read from a slope/intercept table, and the 8-bit gamma through a 32-bit
+//                {byte, threshold} table in fixed point.  Its linear value differs from the reference's by at most
+//                delta (derivation: DESIGN.md "speculative pass"; bound computed per launch on the host from the
+//                actual matrices and curve, ipb_host.cu spec_error_bound; measured by ipb_spec_probe).
+//   certificate  a channel whose cheap value is farther than delta from every threshold has, by monotonicity, exactly
+//                the reference's byte.  One add and one mask per channel produce byte and distance together.
+//   fix-up       pixels with a channel inside +-delta of a threshold (about 1 %), and the frame's border pixels, are
+//                queued in shared memory and recomputed by the bit-exact code of ipb_device.cuh (same arithmetic as
+//                the per-op kernels and k_fused_full) from the raw frame, all threads of the CTA working on queue
+//                entries, then their bytes are stored over the cheap ones.
+//
+// Result: byte-identical to k_fused_full / the oracle by construction, at about a third of the instructions.
+// Tile pipeline as in k_fused_full: persistent CTAs, raw u16 boxes by TMA (cp.async.bulk.tensor.2d + mbarrier) one
+// tile ahead, conversion into a double-buffered f32 tile whose even and odd columns live in separate planes (so that
+// the two same-kind pixels of a four-pixel task sit in one aligned register pair and no window load has a bank
+// conflict), one __syncthreads per tile.
+#include <cuda.h>
+
+#include "ipb_internal.h"
+#include "ipb_spec.h"
+
+namespace ipb {
+
+namespace {
+
+constexpr int kTW = 128, kTH = 32;
+constexpr int kTileStride = kTW + 16;  // TMA box columns: frame col tx0-8 .. tx0+kTW+7
+constexpr int kTileRows = kTH + 2;
+constexpr int kTileElems = kTileRows * kTileStride;
+constexpr int kStageElems = (kTileElems * 2 + 127) / 128 * 64;
+constexpr int kPS = kTileStride / 2;   // plane stride (floats): 72
+constexpr uint32_t kFull = 0xffffffffu;
+constexpr int kG8Offset = 32768 - (int)kSpecSmemBase;  // the gamma table starts on a 32 KB boundary of the shared window
+constexpr int kQueueCap = (kG8Offset - kSpecSTabEntries * 8 - 32) / 4;
+constexpr int kFlushAt = kQueueCap / 2;
+
+struct SmemSpec {
+  float2 stab[kSpecSTabEntries];                // basecurve in f-space: {intercept, slope} per segment
+  uint32_t queue[kQueueCap];                    // fix-up queue: pixel index inside the launch's output rows
+  alignas(8) unsigned long long mbar;
+  alignas(8) unsigned long long mbar_tab;
+  int conv_ctr[2];
+  int qn, pad;
+  uint32_t g8a[kSpecG8Entries];                 // {byte, threshold} fixed-point gamma table; 32 KB aligned: its
+                                                // entries are addressed by (bits & 0x7ffc) | base, one LOP3
+  float plane[2][kTileRows][2][kPS];            // [buffer][tile row][even / odd columns][column / 2]
+  alignas(128) uint16_t raw[kStageElems];       // TMA destination
+};
+static_assert(offsetof(SmemSpec, g8a) == kG8Offset, "gamma table must sit on a 32 KB boundary of the shared window");
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "SPEC_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra SPEC_DONE;\n"
+      "bra SPEC_WAIT;\n"
+      "SPEC_DONE:\n"
+      "}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, int x, int y, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+      "l"(map), "r"(x), "r"(y), "r"(bar)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_load(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+// ---------------------------------------------------------------- contracted packed arithmetic (cheap pass only)
+__device__ __forceinline__ F2 a2(F2 a, F2 b) {
+  F2 d;
+  asm("{.reg .b64 ra, rb, rd; mov.b64 ra, {%2, %3}; mov.b64 rb, {%4, %5}; add.rn.f32x2 rd, ra, rb; mov.b64 {%0, %1}, rd;}"
+      : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return d;
+}
+__device__ __forceinline__ F2 m2(F2 a, F2 b) { return pk_mul(a, b); }
+__device__ __forceinline__ F2 f2(F2 a, F2 b, F2 c) { return pk_fma(a, b, c); }
+__device__ __forceinline__ float lg2a(float v) {
+  float r;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
+  return r;
+}
+__device__ __forceinline__ float ex2a(float v) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
+  return r;
+}
+__device__ __forceinline__ float lds32f(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ F2 lds64f(uint32_t addr) {
+  F2 v;
+  asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ uint32_t lds32u(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
+
+constexpr float kLabE = 216.0f / 24389.0f;   // color_conversions.rs:121
+constexpr float kLabK = 24389.0f / 27.0f;    // :122
+
+// Lab transfer function (color_conversions.rs:120-124) of both halves: cube root on the XU pipe above e, the line below
+__device__ __forceinline__ F2 lab_f_cheap(F2 v) {
+  const F2 lg = m2(F2{lg2a(v.x), lg2a(v.y)}, splat(1.0f / 3.0f));
+  const F2 lin = f2(v, splat(kLabK / 116.0f), splat(16.0f / 116.0f));
+  return F2{v.x > kLabE ? ex2a(lg.x) : lin.x, v.y > kLabE ? ex2a(lg.y) : lin.y};
+}
+// its inverse (color_conversions.rs:172-191): t^3 above cbrt(e) = 6/29, the line below
+__device__ __forceinline__ F2 lab_g_cheap(F2 t) {
+  const F2 t2 = m2(t, t);
+  const F2 lin = f2(t, splat(116.0f / kLabK), splat(-16.0f / kLabK));
+  const float t0 = 6.0f / 29.0f;
+  return F2{t.x > t0 ? t2.x * t.x : lin.x, t.y > t0 ? t2.y * t.y : lin.y};
+}
+// basecurve in f-space, S(fy) = (100*spline((116*fy - 16)/100) + 16)/116, from the slope/intercept table
+__device__ __forceinline__ float s_cheap(uint32_t stab_bias, float fy, float tf) {
+  const F2 e = lds64f((__float_as_uint(tf) << 3) + stab_bias);
+  return fmaf(fy, e.y, e.x);
+}
+
+// The colour chain of two pixels in the cheap arithmetic.  In: demosaiced camera RGB (white balance not applied).
+// Out: per channel the sum  table entry + fixed-point value  whose top byte is the 8-bit result and whose low 24
+// bits are the distance to the threshold (+ delta), and with PROBE the clamped linear values themselves.
+template <bool PROBE>
+__device__ __forceinline__ float chain_pair(const SpecParams &p, uint32_t g8_base, uint32_t stab_bias, F2 cr, F2 cg, F2 cb,
+                                            uint32_t s[6], float lin[6]) {
+  // white balance + clip (colorspaces.rs:97-101, color_conversions.rs:43-46) as a clip against 1/mul; the gains are
+  // folded into the matrix.  mul[1] is 1 by construction and demosaiced values never exceed 1: green needs no clip.
+  cr = F2{fminf(cr.x, p.lim_r), fminf(cr.y, p.lim_r)};
+  cb = F2{fminf(cb.x, p.lim_b), fminf(cb.y, p.lim_b)};
+  // camera -> XYZ ratios (matrix rows divided by the white point)
+  const F2 xr = f2(cb, splat(p.m[0][2]), f2(cg, splat(p.m[0][1]), m2(cr, splat(p.m[0][0]))));
+  const F2 yr = f2(cb, splat(p.m[1][2]), f2(cg, splat(p.m[1][1]), m2(cr, splat(p.m[1][0]))));
+  const F2 zr = f2(cb, splat(p.m[2][2]), f2(cg, splat(p.m[2][1]), m2(cr, splat(p.m[2][0]))));
+  const F2 fx = lab_f_cheap(xr), fy = lab_f_cheap(yr), fz = lab_f_cheap(zr);
+  // basecurve: fy' = S(fy); a and b are untouched, so fx' = fx + (fy' - fy), fz' = fz + (fy' - fy)
+  const float ux = __saturatef(fmaf(fy.x, p.s_scale, p.s_off)), uy = __saturatef(fmaf(fy.y, p.s_scale, p.s_off));
+  const F2 tf = pk_fma_rm(F2{ux, uy}, splat((float)(kSpecSTabN + 2)), splat(8388608.0f));
+  const F2 fyp{s_cheap(stab_bias, fy.x, tf.x), s_cheap(stab_bias, fy.y, tf.y)};
+  const F2 d = f2(fy, splat(-1.0f), fyp);
+  const F2 X = lab_g_cheap(a2(fx, d)), Y = lab_g_cheap(fyp), Z = lab_g_cheap(a2(fz, d));
+  // XYZ ratios -> linear sRGB (matrix columns multiplied by the white point), clamp to [0, 1] in the last FMA
+  const F2 r0 = f2(Y, splat(p.ro[0][1]), m2(X, splat(p.ro[0][0])));
+  const F2 g0 = f2(Y, splat(p.ro[1][1]), m2(X, splat(p.ro[1][0])));
+  const F2 b0 = f2(Y, splat(p.ro[2][1]), m2(X, splat(p.ro[2][0])));
+  const F2 r{__saturatef(fmaf(Z.x, p.ro[0][2], r0.x)), __saturatef(fmaf(Z.y, p.ro[0][2], r0.y))};
+  const F2 g{__saturatef(fmaf(Z.x, p.ro[1][2], g0.x)), __saturatef(fmaf(Z.y, p.ro[1][2], g0.y))};
+  const F2 b{__saturatef(fmaf(Z.x, p.ro[2][2], b0.x)), __saturatef(fmaf(Z.y, p.ro[2][2], b0.y))};
+  if (PROBE) { lin[0] = r.x; lin[1] = r.y; lin[2] = g.x; lin[3] = g.y; lin[4] = b.x; lin[5] = b.y; }
+  // fixed point: u = 1 + v*(1 - 2^-13) has the bit pattern 0x3F800000 + F, F = round(v * (2^23 - 2^10)); table
+  // segment = floor(v * 8191), taken from a second float whose mantissa is floor(v * 32764): bits 2..14 = the segment
+  const float c = 1.0f - 1.0f / 8192.0f, c1 = 32764.0f / 8388608.0f;
+  const F2 ur = f2(r, splat(c), splat(1.0f)), ug = f2(g, splat(c), splat(1.0f)), ub = f2(b, splat(c), splat(1.0f));
+  const F2 kr = pk_fma_rm(r, splat(c1), splat(1.0f)), kg = pk_fma_rm(g, splat(c1), splat(1.0f)), kb = pk_fma_rm(b, splat(c1), splat(1.0f));
+  const float uu[6] = {ur.x, ur.y, ug.x, ug.y, ub.x, ub.y}, kk[6] = {kr.x, kr.y, kg.x, kg.y, kb.x, kb.y};
+#pragma unroll
+  for (int i = 0; i < 6; i++) s[i] = lds32u((__float_as_uint(kk[i]) & 0x7ffcu) | g8_base) + __float_as_uint(uu[i]);
+  return fminf(yr.x, yr.y);  // the caller checks the certified domain (Y ratio >= kSpecYMin)
+}
+
+struct Window {
+  F2 En, Ec, Es, On, Oc, Os;  // columns (x0, x0+2) and (x0+1, x0+3) of rows y-1, y, y+1
+  float e2n, e2c, e2s;        // column x0+4
+  float omn, omc, oms;        // column x0-1
+};
+
+// demosaic::full for an interior four-pixel task of an RGB Bayer frame (demosaic.rs:67-119: bilinear means, the
+// centre's own colour passed through).  GF: the row starts with green (x0 is even).  Pixels (0,2) and (1,3) are of the
+// same kind and travel as packed pairs.  Out: (row colour a, green, other colour o) of both pairs.
+template <bool GF>
+__device__ __forceinline__ void demosaic_pairs(const Window &w, F2 &a02, F2 &g02, F2 &o02, F2 &a13, F2 &g13, F2 &o13) {
+  const F2 q{0.25f, 0.25f}, h{0.5f, 0.5f};
+  if (!GF) {
+    // pixels 0, 2 on the row's colour
+    const F2 W{w.omc, w.Oc.x}, NW{w.omn, w.On.x}, SW{w.oms, w.Os.x};
+    a02 = w.Ec;
+    g02 = m2(a2(a2(a2(w.En, W), w.Oc), w.Es), q);
+    o02 = m2(a2(a2(a2(NW, w.On), SW), w.Os), q);
+    // pixels 1, 3 on green
+    const F2 E{w.Ec.y, w.e2c};
+    g13 = w.Oc;
+    a13 = m2(a2(w.Ec, E), h);
+    o13 = m2(a2(w.On, w.Os), h);
+  } else {
+    const F2 W{w.omc, w.Oc.x};
+    g02 = w.Ec;
+    a02 = m2(a2(W, w.Oc), h);
+    o02 = m2(a2(w.En, w.Es), h);
+    const F2 E{w.Ec.y, w.e2c}, NE{w.En.y, w.e2n}, SE{w.Es.y, w.e2s};
+    a13 = w.Oc;
+    g13 = m2(a2(a2(a2(w.On, w.Ec), E), w.Os), q);
+    o13 = m2(a2(a2(a2(w.En, NE), w.Es), SE), q);
+  }
+}
+
+// ---------------------------------------------------------------- exact pixel (fix-up)
+// gofloat (gofloat.rs:127) + demosaic::full (demosaic.rs:67-119) + to_lab + basecurve + from_lab + gamma for ONE
+// pixel straight from the raw frame, in the bit-exact arithmetic of ipb_device.cuh; any CFA, any position.
+// `gamma`: apply OpGamma (false: the clamped linear value, for the probe).
+__device__ __noinline__ void exact_pixel(const SpecParams &p, const CfaDev &cfa, const ColorParams &P, int x, int y,
+                                         bool gamma, float out[3]) {
+  const int pix = cfa.pat[(y % 48) * 48 + x % 48];
+  float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;
+  int n0 = 0, n1 = 0, n2 = 0, n3 = 0;
+#pragma unroll
+  for (int dy = -1; dy <= 1; dy++)
+#pragma unroll
+    for (int dx = -1; dx <= 1; dx++) {
+      const int yy = y + dy, xx = x + dx;
+      if (yy < 0 || yy >= p.height || xx < 0 || xx >= p.width) continue;  // demosaic.rs:103-104
+      const int oc = cfa.pat[(yy % 48) * 48 + xx % 48];
+      if (oc == pix && (dx != 0 || dy != 0)) continue;                    // :87 the discarded fifth bin
+      const float v = golevel((float)__ldg(p.raw + (long long)(yy + p.crop_y - p.src_row0) * p.raw_pitch + p.crop_x + xx),
+                              p.black, p.range, p.range_rc, p.exact_rc);
+      if (oc == 0) { s0 = s0 + v; n0++; }
+      else if (oc == 1) { s1 = s1 + v; n1++; }
+      else if (oc == 2) { s2 = s2 + v; n2++; }
+      else if (oc == 3) { s3 = s3 + v; n3++; }
+    }
+  const float r = n0 ? __fdiv_rn(s0, (float)n0) : 0.0f, g = n1 ? __fdiv_rn(s1, (float)n1) : 0.0f;
+  const float b = n2 ? __fdiv_rn(s2, (float)n2) : 0.0f, e = n3 ? __fdiv_rn(s3, (float)n3) : 0.0f;
+  const LutGlobal lab{p.lut_lab}, gam{p.lut_gamma};
+  float l, a, bb;
+  camera_to_lab<true>(P, lab, r, g, b, e, l, a, bb);
+  if (P.sp.n > 0) l = spline_eval(P.sp, l);
+  lab_to_rgb<true>(P, l, a, bb, out[0], out[1], out[2]);
+#pragma unroll
+  for (int c = 0; c < 3; c++) out[c] = gamma ? gamma_elem(gam, out[c]) : fminf(fmaxf(out[c], 0.0f), 1.0f);
+}
+
+__device__ __forceinline__ void fixup_pixel(const SpecParams &p, const CfaDev &cfa, const ColorParams &P, uint32_t idx) {
+  const int row = (int)(idx / (uint32_t)p.width), x = (int)(idx - (uint32_t)row * (uint32_t)p.width);
+  float v[3];
+  exact_pixel(p, cfa, P, x, p.out_row0 + row, true, v);
+  uint8_t *o = p.out + (size_t)idx * 3;
+  o[0] = (uint8_t)output8bit(v[0]);
+  o[1] = (uint8_t)output8bit(v[1]);
+  o[2] = (uint8_t)output8bit(v[2]);
+}
+
+__device__ __forceinline__ void issue_tile(const SpecParams &p, const CUtensorMap *tmap, uint32_t raw_stage, uint32_t bar,
+                                           int txi, int tyi) {
+  const int x = txi * kTW - 8 + p.crop_x;
+  const int y = p.out_row0 + tyi * kTH - 1 + p.crop_y - p.src_row0;
+  mbar_expect_tx(bar, kTileElems * (uint32_t)sizeof(uint16_t));
+  tma_load_2d(raw_stage, tmap, x, y, bar);
+}
+
+// one four-pixel task of the cheap pass; returns the three output words and the flag mask of pixels to recompute
+template <bool GF, bool AR>
+__device__ __forceinline__ uint32_t cheap_task(const SpecParams &p, uint32_t g8_base, uint32_t stab_bias, const Window &w,
+                                               uint32_t words[3]) {
+  F2 a02, g02, o02, a13, g13, o13;
+  demosaic_pairs<GF>(w, a02, g02, o02, a13, g13, o13);
+  uint32_t s02[6], s13[6];
+  const float y02 = chain_pair<false>(p, g8_base, stab_bias, AR ? a02 : o02, g02, AR ? o02 : a02, s02, nullptr);
+  const float y13 = chain_pair<false>(p, g8_base, stab_bias, AR ? a13 : o13, g13, AR ? o13 : a13, s13, nullptr);
+  // s[2c + h]: channel c of the pair's pixel h.  Bytes: px0 = s02[*][0], px1 = s13[*][0], px2 = s02[*][1], px3 = s13[*][1]
+  const uint32_t r0 = s02[0], g0 = s02[2], b0 = s02[4], r2 = s02[1], g2 = s02[3], b2 = s02[5];
+  const uint32_t r1 = s13[0], g1 = s13[2], b1 = s13[4], r3 = s13[1], g3 = s13[3], b3 = s13[5];
+  words[0] = __byte_perm(__byte_perm(r0, g0, 0x0073), __byte_perm(b0, r1, 0x0073), 0x5410);
+  words[1] = __byte_perm(__byte_perm(g1, b1, 0x0073), __byte_perm(r2, g2, 0x0073), 0x5410);
+  words[2] = __byte_perm(__byte_perm(b2, r3, 0x0073), __byte_perm(g3, b3, 0x0073), 0x5410);
+  const uint32_t M = 0x00ffffffu;
+  const uint32_t d0 = min(min(r0 & M, g0 & M), b0 & M), d1 = min(min(r1 & M, g1 & M), b1 & M);
+  const uint32_t d2 = min(min(r2 & M, g2 & M), b2 & M), d3 = min(min(r3 & M, g3 & M), b3 & M);
+  uint32_t flags = 0;
+  if (min(min(d0, d1), min(d2, d3)) <= p.amb2) {
+    flags = (d0 <= p.amb2 ? 1u : 0u) | (d1 <= p.amb2 ? 2u : 0u) | (d2 <= p.amb2 ? 4u : 0u) | (d3 <= p.amb2 ? 8u : 0u);
+  }
+  if (fminf(y02, y13) < p.y_min) flags = 0xfu;  // outside the certified domain (far below black): all four exactly
+  return flags;
+}
+
+__device__ __forceinline__ int atoms_add(uint32_t addr, int v) {  // plain shared-memory atomic (no warp aggregation)
+  int old;
+  asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(addr), "r"(v) : "memory");
+  return old;
+}
+
+// GF0 / AR0: Bayer phase of even rows of the cropped frame — the row starts with green / its other colour is red.
+// Odd rows are the opposite on both counts (green sits on one diagonal, red and blue on the other).
+template <int NT, bool GF0, bool AR0>
+__global__ void __launch_bounds__(NT, NT == 512 ? 2 : 1)
+k_spec8(const __grid_constant__ SpecParams p, const __grid_constant__ CfaDev cfa, const __grid_constant__ ColorParams P,
+        const __grid_constant__ CUtensorMap tmap) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  SmemSpec &sm = *reinterpret_cast<SmemSpec *>(smem_raw);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int ntiles = p.tiles_x * p.tiles_y;
+  const uint32_t bar = smem_u32(&sm.mbar), bar_tab = smem_u32(&sm.mbar_tab), raw_addr = smem_u32(sm.raw);
+  const uint32_t qn_addr = smem_u32(&sm.qn);
+
+  int tyi = (int)blockIdx.x / p.tiles_x, txi = (int)blockIdx.x - tyi * p.tiles_x;
+  const int step_y = (int)gridDim.x / p.tiles_x, step_x = (int)gridDim.x - step_y * p.tiles_x;
+  auto next_tile = [&](int &tx, int &ty) {
+    tx += step_x; ty += step_y;
+    if (tx >= p.tiles_x) { tx -= p.tiles_x; ty++; }
+  };
+
+  if (tid == 0) {
+    sm.conv_ctr[0] = 0;
+    sm.conv_ctr[1] = 0;
+    sm.qn = 0;
+    mbar_init(bar, 1);
+    mbar_init(bar_tab, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    issue_tile(p, &tmap, raw_addr, bar, txi, tyi);
+    constexpr uint32_t kG8Bytes = kSpecG8Entries * 4u, kSTabBytes = kSpecSTabEntries * 8u;
+    mbar_expect_tx(bar_tab, kG8Bytes + kSTabBytes);
+    bulk_load(smem_u32(sm.g8a), p.g8a, kG8Bytes, bar_tab);
+    bulk_load(smem_u32(sm.stab), p.stab, kSTabBytes, bar_tab);
+  }
+  const uint32_t g8_base = smem_u32(sm.g8a);
+  if ((g8_base & 0x7fffu) != 0u) {  // cannot happen: ipb_ctx_create probed the shared window base (kSpecSmemBase)
+    if (tid == 0 && p.stats) p.stats[4] = 1ull;
+    return;
+  }
+  const uint32_t stab_bias = smem_u32(sm.stab) - p.bias58;  // (0x4B000000 << 3) mod 2^32: tf = 2^23 + key
+
+  // gofloat (gofloat.rs:127) of the staged raw box into tile buffer `buf`, exactly as the reference rounds it (the
+  // cheap pass and the reference then start from identical samples).  Even / odd columns go to separate planes.
+  // Warps pull chunks from a counter, so whichever warps finish their pixels first convert the next tile.
+  auto convert_tile = [&](int buf, int ctr) {
+    constexpr int kGroups = kTileElems / 8;          // 8 samples per thread per chunk
+    constexpr int kChunks = (kGroups + 31) / 32;
+    const F2 rc = splat(p.range_rc), nrange = splat(-p.range), sub_a = splat(p.sub_a), sub_b = splat(p.sub_b);
+    const bool two_subs = p.sub_b != 0.0f;
+    for (;;) {
+      int chunk = 0;
+      if (lane == 0) chunk = atomicAdd(&sm.conv_ctr[ctr], 1);
+      chunk = __shfl_sync(kFull, chunk, 0);
+      if (chunk >= kChunks) break;
+      const int gi = chunk * 32 + lane;
+      if (gi < kGroups) {
+        const uint4 pkd = *reinterpret_cast<const uint4 *>(sm.raw + gi * 8);
+        const uint32_t w4[4] = {pkd.x, pkd.y, pkd.z, pkd.w};
+        float ev[4], od[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          // {0x4B00 | lo16, 0x4B00 | hi16} as floats 2^23 + sample
+          F2 t{__uint_as_float(__byte_perm(w4[k], 0x4B00u, 0x5410)), __uint_as_float(__byte_perm(w4[k], 0x4B00u, 0x5432))};
+          // gofloat.rs:127, bit for bit: (v - black) is exact for an integral black level (one subtraction from
+          // 2^23 + v), otherwise 2^23 comes off first; the division is the verified three-instruction form
+          F2 num = a2(t, sub_a);
+          if (two_subs) num = a2(num, sub_b);
+          const F2 q = m2(num, rc);
+          const F2 res = f2(f2(q, nrange, num), rc, q);
+          ev[k] = fminf(res.x, 1.0f);
+          od[k] = fminf(res.y, 1.0f);
+        }
+        const int r = gi / (kTileStride / 8), g = gi - r * (kTileStride / 8);
+        float *row = &sm.plane[buf][r][0][0];
+        *reinterpret_cast<float4 *>(row + 4 * g) = make_float4(ev[0], ev[1], ev[2], ev[3]);
+        *reinterpret_cast<float4 *>(row + kPS + 4 * g) = make_float4(od[0], od[1], od[2], od[3]);
+      }
+    }
+  };
+
+  __syncthreads();
+  mbar_wait(bar, 0);
+  convert_tile(0, 0);
+  __syncthreads();
+  {
+    int ntx = txi, nty = tyi;
+    next_tile(ntx, nty);
+    if (tid == 0 && (int)(blockIdx.x + gridDim.x) < ntiles) issue_tile(p, &tmap, raw_addr, bar, ntx, nty);
+  }
+  mbar_wait(bar_tab, 0);
+
+  // queue the flagged pixels of a task (pix = index of its first pixel); a full queue recomputes right away — the
+  // cheap bytes are already stored by this very thread, so the exact ones land on top
+  auto push = [&](uint32_t flags, uint32_t pix) {
+    int pos = atoms_add(qn_addr, __popc(flags));
+    while (flags) {
+      const int j = __ffs(flags) - 1;
+      flags &= flags - 1u;
+      if (pos < kQueueCap) sm.queue[pos] = pix + j;
+      else fixup_pixel(p, cfa, P, pix + j);
+      pos++;
+    }
+  };
+  // whole words can be stored when every row starts on a 4-byte boundary
+  const bool rows_aligned = ((reinterpret_cast<uintptr_t>(p.out) & 3) == 0) && ((p.width & 3) == 0);
+
+  int it = 0;
+  for (int t = blockIdx.x; t < ntiles; t += gridDim.x, it++) {
+    const int ty0 = p.out_row0 + tyi * kTH, tx0 = txi * kTW;
+    next_tile(txi, tyi);
+    const uint32_t tile_base = smem_u32(&sm.plane[it & 1][0][0][0]);
+    // a tile is "inner" when all its pixels exist, are wanted, and have their nine taps inside the frame
+    const bool inner = rows_aligned && ty0 >= 1 && ty0 + kTH <= p.height - 1 && ty0 + kTH <= p.out_row1 && tx0 >= 1 &&
+                       tx0 + kTW <= p.width - 1;
+    const uint32_t pix0 = (uint32_t)(ty0 - p.out_row0) * (uint32_t)p.width + (uint32_t)(tx0 + 4 * lane);
+
+#pragma unroll 1
+    for (int r = warp; r < kTH; r += NT / 32) {
+      const int y = ty0 + r;
+      // window: tile row r is frame row y-1; plane index of column x0 is 4 + 2 * lane
+      Window w;
+      const uint32_t a0 = tile_base + (uint32_t)(r * (2 * kPS) + 4 + 2 * lane) * 4u;
+      constexpr uint32_t RS = 2 * kPS * 4, OP = kPS * 4;
+      w.En = lds64f(a0); w.On = lds64f(a0 + OP);
+      w.Ec = lds64f(a0 + RS); w.Oc = lds64f(a0 + RS + OP);
+      w.Es = lds64f(a0 + 2 * RS); w.Os = lds64f(a0 + 2 * RS + OP);
+      w.e2c = lds32f(a0 + RS + 8); w.omc = lds32f(a0 + RS + OP - 4);
+      w.e2n = w.e2s = w.omn = w.oms = 0.0f;
+      const bool gf = ((y & 1) != 0) != GF0;  // rows alternate
+      if (gf) { w.e2n = lds32f(a0 + 8); w.e2s = lds32f(a0 + 2 * RS + 8); }
+      else { w.omn = lds32f(a0 + OP - 4); w.oms = lds32f(a0 + 2 * RS + OP - 4); }
+      uint32_t words[3], flags;
+      if ((y & 1) == 0) flags = cheap_task<GF0, AR0>(p, g8_base, stab_bias, w, words);
+      else flags = cheap_task<!GF0, !AR0>(p, g8_base, stab_bias, w, words);
+      const uint32_t pix = pix0 + (uint32_t)r * (uint32_t)p.width;
+      if (inner) {
+        uint32_t *o4 = reinterpret_cast<uint32_t *>(p.out + (size_t)pix * 3);
+        o4[0] = words[0]; o4[1] = words[1]; o4[2] = words[2];
+        if (flags) push(flags, pix);
+      } else {
+        const int x0 = tx0 + 4 * lane;
+        const bool live = y < p.out_row1 && x0 < p.width;
+        if (live) {
+          const int npx = min(4, p.width - x0);
+          uint8_t *o = p.out + (size_t)pix * 3;
+          if (npx == 4 && ((reinterpret_cast<uintptr_t>(o) & 3) == 0)) {
+            uint32_t *o4 = reinterpret_cast<uint32_t *>(o);
+            o4[0] = words[0]; o4[1] = words[1]; o4[2] = words[2];
+          } else {
+#pragma unroll
+            for (int j = 0; j < 12; j++)
+              if (j < npx * 3) o[j] = (uint8_t)(words[j >> 2] >> ((j & 3) * 8));
+          }
+          // frame border: the cheap demosaic assumed all nine taps (demosaic.rs:103-107 drops the missing ones)
+          if (y < 1 || y > p.height - 2) flags = 0xfu;
+          if (x0 < 1) flags |= 1u;
+          if (x0 + 3 > p.width - 2) flags |= 0xfu & ~((1u << max(p.width - 1 - x0, 0)) - 1u);
+          flags &= (1u << npx) - 1u;
+          if (flags) push(flags, pix);
+        }
+      }
+    }
+
+    const bool have_next = t + (int)gridDim.x < ntiles;
+    if (have_next) {
+      mbar_wait(bar, (it + 1) & 1);
+      convert_tile((it + 1) & 1, (it + 1) & 1);
+    }
+    if (tid == 0) sm.conv_ctr[it & 1] = 0;
+    __syncthreads();
+    if (tid == 0 && t + 2 * (int)gridDim.x < ntiles) {
+      int ntx = txi, nty = tyi;
+      next_tile(ntx, nty);
+      issue_tile(p, &tmap, raw_addr, bar, ntx, nty);
+    }
+    // fix-up queue: recompute when it is half full (dense: every thread takes entries)
+    const int qn = min(sm.qn, kQueueCap);
+    if (qn >= kFlushAt) {
+      for (int i = tid; i < qn; i += NT) fixup_pixel(p, cfa, P, sm.queue[i]);
+      __syncthreads();
+      if (tid == 0) {
+        if (p.stats) atomicAdd(p.stats, (unsigned long long)sm.qn);
+        sm.qn = 0;
+      }
+      __syncthreads();
+    }
+  }
+  // the last barrier of the loop ordered every push before this read
+  const int qn = min(sm.qn, kQueueCap);
+  for (int i = tid; i < qn; i += NT) fixup_pixel(p, cfa, P, sm.queue[i]);
+  if (tid == 0 && p.stats && sm.qn) atomicAdd(p.stats, (unsigned long long)sm.qn);
+}
+
+// ---------------------------------------------------------------- probe: cheap vs exact linear values
+// One thread per interior four-pixel task straight from global memory; stats[1] = max |cheap - exact| over the
+// clamped linear channel values (as float bits), stats[2] = number of values compared, stats[3] = sum of |diff| * 2^40.
+__global__ void k_spec_probe(const __grid_constant__ SpecParams p, const __grid_constant__ CfaDev cfa,
+                             const __grid_constant__ ColorParams P) {
+  extern __shared__ __align__(16) unsigned char probe_smem[];
+  uint32_t *g8a = reinterpret_cast<uint32_t *>(probe_smem + kG8Offset);
+  float2 *stab = reinterpret_cast<float2 *>(probe_smem);
+  for (int i = threadIdx.x; i < kSpecG8Entries; i += blockDim.x) g8a[i] = p.g8a[i];
+  for (int i = threadIdx.x; i < kSpecSTabEntries; i += blockDim.x) stab[i] = p.stab[i];
+  __syncthreads();
+  const uint32_t g8_base = smem_u32(g8a), stab_bias = smem_u32(stab) - p.bias58;
+  if ((g8_base & 0x7fffu) != 0u) return;
+  const int tasks_x = (p.width - 2) / 4;  // tasks start at x0 = 4, 8, ... (aligned like the kernel's), interior only
+  const long long ntasks = (long long)tasks_x * (p.height - 2);
+  float worst = 0.0f;
+  unsigned long long cnt = 0, sum = 0;
+  for (long long id = (long long)blockIdx.x * blockDim.x + threadIdx.x; id < ntasks; id += (long long)gridDim.x * blockDim.x) {
+    const int y = 1 + (int)(id / tasks_x), x0 = 4 * (1 + (int)(id % tasks_x));
+    if (x0 + 4 > p.width - 1) continue;
+    auto ld = [&](int yy, int xx) {
+      const float v = (float)__ldg(p.raw + (long long)(yy + p.crop_y - p.src_row0) * p.raw_pitch + p.crop_x + xx);
+      return golevel(v, p.black, p.range, p.range_rc, p.exact_rc);
+    };
+    Window w;
+    w.En = F2{ld(y - 1, x0), ld(y - 1, x0 + 2)}; w.On = F2{ld(y - 1, x0 + 1), ld(y - 1, x0 + 3)};
+    w.Ec = F2{ld(y, x0), ld(y, x0 + 2)}; w.Oc = F2{ld(y, x0 + 1), ld(y, x0 + 3)};
+    w.Es = F2{ld(y + 1, x0), ld(y + 1, x0 + 2)}; w.Os = F2{ld(y + 1, x0 + 1), ld(y + 1, x0 + 3)};
+    w.e2n = ld(y - 1, x0 + 4); w.e2c = ld(y, x0 + 4); w.e2s = ld(y + 1, x0 + 4);
+    w.omn = ld(y - 1, x0 - 1); w.omc = ld(y, x0 - 1); w.oms = ld(y + 1, x0 - 1);
+    const bool odd = (y & 1) != 0;
+    const bool gf = cfa.pat[(odd ? 48 : 0)] == 1;
+    const bool ar = (gf ? cfa.pat[(odd ? 48 : 0) + 1] : cfa.pat[odd ? 48 : 0]) == 0;
+    F2 a02, g02, o02, a13, g13, o13;
+    if (gf) demosaic_pairs<true>(w, a02, g02, o02, a13, g13, o13);
+    else demosaic_pairs<false>(w, a02, g02, o02, a13, g13, o13);
+    uint32_t s02[6], s13[6];
+    float l02[6], l13[6];
+    const float y02 = chain_pair<true>(p, g8_base, stab_bias, ar ? a02 : o02, g02, ar ? o02 : a02, s02, l02);
+    const float y13 = chain_pair<true>(p, g8_base, stab_bias, ar ? a13 : o13, g13, ar ? o13 : a13, s13, l13);
+    if (fminf(y02, y13) < p.y_min) continue;  // outside the certified domain: the kernel recomputes these
+    for (int j = 0; j < 4; j++) {
+      float ex[3];
+      exact_pixel(p, cfa, P, x0 + j, y, false, ex);
+      const float *l = (j & 1) ? l13 : l02;
+      const int h = j >> 1;
+      for (int c = 0; c < 3; c++) {
+        const float d = fabsf(l[2 * c + h] - ex[c]);
+        worst = fmaxf(worst, d);
+        sum += (unsigned long long)(d * 1099511627776.0f);
+        cnt++;
+      }
+    }
+  }
+  atomicMax(reinterpret_cast<unsigned int *>(p.stats) + 2, __float_as_uint(worst));  // stats[1] low word
+  atomicAdd(p.stats + 2, cnt);
+  atomicAdd(p.stats + 3, sum);
+}
+
+// Self-test run once per context: out[0] = shared-window address of dynamic shared memory (the gamma table's
+// one-instruction addressing assumes kSpecSmemBase), out[1] = max relative error, as float bits, of the XU-pipe cube
+// root ex2(lg2(v)/3) against the correctly rounded one over EVERY float in [2^-8, 4] — the measured constant the
+// error bound of the cheap pass uses for its Lab transfer function.
+__global__ void k_spec_selftest(unsigned int *out) {
+  extern __shared__ __align__(128) unsigned char st_smem[];
+  if (blockIdx.x == 0 && threadIdx.x == 0) out[0] = smem_u32(st_smem);
+  float worst = 0.0f;
+  const uint32_t lo = 0x3b800000u, hi = 0x40800000u;  // 2^-8 .. 4.0
+  for (uint32_t b = lo + blockIdx.x * blockDim.x + threadIdx.x; b <= hi; b += gridDim.x * blockDim.x) {
+    const float v = __uint_as_float(b);
+    const float got = ex2a(lg2a(v) * (1.0f / 3.0f));
+    const double want = cbrt((double)v);
+    worst = fmaxf(worst, (float)(fabs((double)got - want) / want));
+  }
+  atomicMax(out + 1, __float_as_uint(worst));
+}
+
+thread_local const char *g_spec_err = "";
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = [] {
+    void *f = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &qres) != cudaSuccess ||
+        qres != cudaDriverEntryPointSuccess)
+      f = nullptr;
+    return (EncodeTiledFn)f;
+  }();
+  return fn;
+}
+bool make_raw_tmap(CUtensorMap *map, const uint16_t *raw, size_t pitch_elems, size_t rows) {
+  EncodeTiledFn enc = encode_tiled_fn();
+  if (!enc) return false;
+  if ((reinterpret_cast<uintptr_t>(raw) & 15) || ((pitch_elems * sizeof(uint16_t)) & 15) || rows == 0) return false;
+  const cuuint64_t dims[2] = {(cuuint64_t)pitch_elems, (cuuint64_t)rows};
+  const cuuint64_t strides[1] = {(cuuint64_t)(pitch_elems * sizeof(uint16_t))};
+  const cuuint32_t box[2] = {(cuuint32_t)kTileStride, (cuuint32_t)kTileRows};
+  const cuuint32_t estr[2] = {1, 1};
+  return enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, const_cast<uint16_t *>(raw), dims, strides, box, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+template <int NT, bool GF0, bool AR0>
+cudaError_t launch_variant(cudaStream_t s, const SpecParams &p, const CfaDev &cfa, const ColorParams &P,
+                           const CUtensorMap &tmap, int ntiles, int sm_count) {
+  const size_t smem = sizeof(SmemSpec);
+  const int ctas = sm_count * (NT == 512 ? 2 : 1);
+  const int grid = ntiles < ctas ? ntiles : ctas;
+  cudaError_t e = cudaFuncSetAttribute(k_spec8<NT, GF0, AR0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  k_spec8<NT, GF0, AR0><<<grid, NT, smem, s>>>(p, cfa, P, tmap);
+  return cudaGetLastError();
+}
+
+}  // namespace
+
+const char *spec_last_error() { return g_spec_err; }
+
+bool spec_supported(const FusedArgs &a, const CfaDev &cfa, const ColorParams &P) {
+  if (a.out_kind != kOutU8 || P.linear || P.use_e) return false;
+  if (cfa.width != 2 || cfa.height != 2) return false;
+  const int c0 = cfa.pat[0], c1 = cfa.pat[1], c2_ = cfa.pat[48], c3 = cfa.pat[49];
+  const bool bayer = (c1 == 1 && c2_ == 1 && ((c0 == 0 && c3 == 2) || (c0 == 2 && c3 == 0))) ||
+                     (c0 == 1 && c3 == 1 && ((c1 == 0 && c2_ == 2) || (c1 == 2 && c2_ == 0)));
+  if (!bayer) return false;
+  if (!a.use_tma || (a.crop_x % 8) != 0) return false;
+  if ((reinterpret_cast<uintptr_t>(a.raw) & 15) || ((a.raw_pitch * sizeof(uint16_t)) & 15)) return false;
+  if (a.width < 8 || a.height < 4) return false;
+  if ((unsigned long long)a.width * (a.out_row1 - a.out_row0) >= 0xffffffffull) return false;  // 32-bit queue entries
+  return true;
+}
+
+cudaError_t launch_fused_spec8(cudaStream_t s, const FusedArgs &a, const CfaDev &cfa, const ColorParams &P,
+                               const SpecTables &T, int sm_count, int threads) {
+  if (a.out_row1 <= a.out_row0 || a.width == 0) return cudaSuccess;
+  SpecParams p = T.consts;
+  p.raw = a.raw; p.raw_pitch = (long long)a.raw_pitch;
+  p.src_row0 = (int)a.src_row0; p.src_rows = (int)a.src_rows;
+  p.crop_x = (int)a.crop_x; p.crop_y = (int)a.crop_y;
+  p.width = (int)a.width; p.height = (int)a.height;
+  p.out_row0 = (int)a.out_row0; p.out_row1 = (int)a.out_row1;
+  p.out = (uint8_t *)a.out;
+  p.black = a.black; p.range = a.range; p.range_rc = a.range_rc; p.exact_rc = a.exact_rc;
+  {
+    const bool integral = a.black >= 0.0f && a.black < 4194304.0f && a.black == floorf(a.black);
+    p.sub_a = integral ? -(8388608.0f + a.black) : -8388608.0f;
+    p.sub_b = integral ? 0.0f : -a.black;
+  }
+  p.bias58 = 0x58000000u;
+  p.lut_lab = a.lut_lab; p.lut_gamma = a.lut_gamma;
+  p.g8a = T.g8a; p.stab = T.stab; p.stats = T.stats;
+  p.tiles_x = (p.width + kTW - 1) / kTW;
+  p.tiles_y = (p.out_row1 - p.out_row0 + kTH - 1) / kTH;
+  CUtensorMap tmap;
+  memset(&tmap, 0, sizeof(tmap));
+  if (!make_raw_tmap(&tmap, a.raw, a.raw_pitch, a.src_rows)) {
+    g_spec_err = "spec8: tensor map";
+    return cudaErrorInvalidValue;
+  }
+  const int ntiles = p.tiles_x * p.tiles_y;
+  const bool gf0 = cfa.pat[0] == 1;
+  const bool ar0 = (gf0 ? cfa.pat[1] : cfa.pat[0]) == 0;
+  const int variant = (threads == 1024 ? 4 : 0) | (gf0 ? 2 : 0) | (ar0 ? 1 : 0);
+  switch (variant) {
+    case 0: return launch_variant<512, false, false>(s, p, cfa, P, tmap, ntiles, sm_count);
+    case 1: return launch_variant<512, false, true>(s, p, cfa, P, tmap, ntiles, sm_count);
+    case 2: return launch_variant<512, true, false>(s, p, cfa, P, tmap, ntiles, sm_count);
+    case 3: return launch_variant<512, true, true>(s, p, cfa, P, tmap, ntiles, sm_count);
+    case 4: return launch_variant<1024, false, false>(s, p, cfa, P, tmap, ntiles, sm_count);
+    case 5: return launch_variant<1024, false, true>(s, p, cfa, P, tmap, ntiles, sm_count);
+    case 6: return launch_variant<1024, true, false>(s, p, cfa, P, tmap, ntiles, sm_count);
+    default: return launch_variant<1024, true, true>(s, p, cfa, P, tmap, ntiles, sm_count);
+  }
+}
+
+cudaError_t launch_spec_selftest(cudaStream_t s, unsigned int *out2) {
+  const size_t smem = sizeof(SmemSpec);
+  cudaError_t e = cudaFuncSetAttribute(k_spec_selftest, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  k_spec_selftest<<<592, 512, smem, s>>>(out2);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_spec_probe(cudaStream_t s, const FusedArgs &a, const CfaDev &cfa, const ColorParams &P,
+                              const SpecTables &T, int sm_count) {
+  SpecParams p = T.consts;
+  p.raw = a.raw; p.raw_pitch = (long long)a.raw_pitch;
+  p.src_row0 = (int)a.src_row0; p.src_rows = (int)a.src_rows;
+  p.crop_x = (int)a.crop_x; p.crop_y = (int)a.crop_y;
+  p.width = (int)a.width; p.height = (int)a.height;
+  p.out_row0 = 0; p.out_row1 = (int)a.height;
+  p.out = nullptr;
+  p.black = a.black; p.range = a.range; p.range_rc = a.range_rc; p.exact_rc = a.exact_rc;
+  {
+    const bool integral = a.black >= 0.0f && a.black < 4194304.0f && a.black == floorf(a.black);
+    p.sub_a = integral ? -(8388608.0f + a.black) : -8388608.0f;
+    p.sub_b = integral ? 0.0f : -a.black;
+  }
+  p.bias58 = 0x58000000u;
+  p.lut_lab = a.lut_lab; p.lut_gamma = a.lut_gamma;
+  p.g8a = T.g8a; p.stab = T.stab; p.stats = T.stats;
+  const size_t smem = kG8Offset + kSpecG8Entries * 4;
+  cudaError_t e = cudaFuncSetAttribute(k_spec_probe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  k_spec_probe<<<sm_count * 2, 256, smem, s>>>(p, cfa, P);
+  return cudaGetLastError();
+}
+
+}  // namespace ipb

@@ -36,6 +36,18 @@ class Context:
         _capi.check(self.handle, lib().ipb_ctx_set_stream(self.handle, C.c_void_p(stream) if stream else None))
 
     @property
+    def set_spec(self, delta=0.0, threads=512):
+        """Test / tuning hook of the speculative 8-bit kernel: forced bound (0 = certified) and CTA size."""
+        _capi.check(self.handle, lib().ipb_ctx_set_spec(self.handle, float(delta), int(threads)))
+
+    def spec_stats(self, reset=False):
+        """dict(fixups, bad_window, delta, mufu_err) of the speculative kernel since the last reset."""
+        import struct
+        out = (C.c_ulonglong * 4)()
+        _capi.check(self.handle, lib().ipb_ctx_spec_stats(self.handle, out, int(reset)))
+        f = lambda v: struct.unpack("<f", struct.pack("<I", v & 0xffffffff))[0]
+        return {"fixups": int(out[0]), "bad_window": int(out[1]), "delta": f(out[2]), "mufu_err": f(out[3])}
+
     def launch_count(self):
         return int(lib().ipb_ctx_launch_count(self.handle))
 
@@ -457,6 +469,16 @@ class Pipeline:
     def set_fused(self, fused):
         """True (default): run may use the fused raw->sRGB kernel; False: one kernel + one OpBuffer per op."""
         _capi.check(self.ctx.handle, lib().ipb_pipeline_set_fused(self.handle, int(fused)))
+
+    def set_speculative(self, on):
+        """True (default): 8-bit output of RGB Bayer frames through the speculative kernel (identical bytes)."""
+        _capi.check(self.ctx.handle, lib().ipb_pipeline_set_speculative(self.handle, int(on)))
+
+    def spec_probe(self):
+        """(max |cheap - exact|, mean, certified delta) over the linear channel values of this frame's interior pixels."""
+        mx, mean, delta = C.c_float(), C.c_double(), C.c_float()
+        _capi.check(self.ctx.handle, lib().ipb_pipeline_spec_probe(self.handle, C.byref(mx), C.byref(mean), C.byref(delta)))
+        return mx.value, mean.value, delta.value
 
     def set_band_mb(self, megabytes):
         """Host source/destination: band size of the overlapped H2D / kernel / D2H schedule (0 = whole-frame copies)."""

@@ -247,6 +247,29 @@ int ipb_pipeline_set_fused(ipb_pipeline *p, int fused);
 /* 1 (default): the full-resolution fused kernel stages raw tiles with TMA when the source allows it (16-byte
  * aligned base and row pitch); 0: always use the plain-load staging path.  Results are identical. */
 int ipb_pipeline_set_tma(ipb_pipeline *p, int use_tma);
+/* 8-bit output of a full-resolution RGB Bayer frame (the path of Pipeline::output_8bit, pipeline.rs:377-422, for raw
+ * sources) runs by default through the speculative kernel: every pixel in cheap contracted arithmetic whose distance
+ * from the reference's f32 result is bounded by a certified delta, and the pixels that come within delta of one of
+ * the 255 thresholds of output8bit(apply_srgb_gamma(v)) recomputed in the reference's exact arithmetic.  The bytes are
+ * identical to the exact kernel's by construction; 0 selects the exact kernel for every pixel. */
+int ipb_pipeline_set_speculative(ipb_pipeline *p, int on);
+/* Tuning / test hooks of the speculative kernel.  delta > 0 forces the bound used for the threshold test (a huge
+ * delta recomputes almost every pixel: results must not change; a delta below the certified one voids the guarantee),
+ * 0 restores the certified bound; threads = 512 or 1024 selects the CTA size. */
+int ipb_ctx_set_spec(ipb_ctx *ctx, float delta, int threads);
+/* counters since the last reset: out[0] = pixels recomputed exactly, out[1] = 1 if a launch found the shared window
+ * where the tables' addressing does not expect it (never), out[2] = the certified delta of the current tables as
+ * float bits, out[3] = measured max relative error of the XU-pipe cube root as float bits */
+int ipb_ctx_spec_stats(ipb_ctx *ctx, unsigned long long out[4], int reset);
+/* Measures, on the pipeline's own source frame and parameters, the largest and the mean |cheap - exact| over the
+ * clamped linear channel values of every interior pixel, next to the certified bound the kernel would use.  The
+ * parity suite asserts max_dev <= delta on every frame it runs.  IPB_ERR_UNSUPPORTED when the pipeline would not take
+ * the speculative path. */
+int ipb_pipeline_spec_probe(ipb_pipeline *p, float *max_dev, double *mean_dev, float *delta);
+/* The certified bound itself, without a context or a GPU (pure host arithmetic, ipb_spec_host.cu): *delta for the colour
+ * parameters of `ops`, given the relative error of the XU-pipe cube root (ipb_ctx_spec_stats out[3] on a GPU box; the
+ * hardware documentation's 2^-22 otherwise).  IPB_ERR_UNSUPPORTED when these parameters would run on the exact kernel. */
+int ipb_spec_bound(const ipb_ops *ops, float mufu_rel_err, float *delta);
 /* Host-resident source and/or destination: output_8bit / output_16bit cut the frame into bands of about `megabytes`
  * of PCIe traffic and overlap the H2D copy, the kernel and the D2H copy of neighbouring bands on three streams
  * (default 16: lowest latency of a single call).  0 = one band: whole-frame copies, which use the PCIe link better
