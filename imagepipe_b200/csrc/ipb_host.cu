@@ -2259,6 +2259,7 @@ int ipb_pipeline_spec_probe(ipb_pipeline *p, float *max_dev, double *mean_dev, f
   a.range_rc = 1.0f / a.range;
   a.exact_rc = golevel_rc_exact(a.black, a.range, a.range_rc) ? 1 : 0;
   a.lut_lab = ctx->lut_lab; a.lut_gamma = ctx->lut_gamma; a.lut_gamma8 = ctx->lut_gamma8;
+  a.cbrt_tab = ctx->cbrt_tab;
   a.use_tma = 1;
   bool use = false;
   if (a.exact_rc && spec_supported(a, plan.cfa, P)) IPB_TRY(ensure_spec_tables(ctx, P, a.black, a.range, &use));

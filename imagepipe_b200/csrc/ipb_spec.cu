@@ -42,12 +42,14 @@ constexpr int kStageElems = (kTileElems * 2 + 127) / 128 * 64;
 constexpr int kPS = kTileStride / 2;   // plane stride (floats): 72
 constexpr uint32_t kFull = 0xffffffffu;
 constexpr int kG8Offset = 32768 - (int)kSpecSmemBase;  // the gamma table starts on a 32 KB boundary of the shared window
-constexpr int kQueueCap = (kG8Offset - kSpecSTabEntries * 8 - 32) / 4;
+constexpr int kSplRows = kMaxSplinePts + 2;
+constexpr int kQueueCap = (kG8Offset - kSpecSTabEntries * 8 - kSplRows * 32 - 32) / 4;
 constexpr int kFlushAt = kQueueCap / 2;
 
 struct SmemSpec {
   float2 stab[kSpecSTabEntries];                // basecurve in f-space: {intercept, slope} per segment
   uint32_t queue[kQueueCap];                    // fix-up queue: pixel index inside the launch's output rows
+  float spl[kSplRows][8];                       // exact basecurve: [0] below the first knot, [1 + i] segment i, [n] at / above the last
   alignas(8) unsigned long long mbar;
   alignas(8) unsigned long long mbar_tab;
   int conv_ctr[2];
@@ -221,48 +223,106 @@ __device__ __forceinline__ void demosaic_pairs(const Window &w, F2 &a02, F2 &g02
 }
 
 // ---------------------------------------------------------------- exact pixel (fix-up)
-// gofloat (gofloat.rs:127) + demosaic::full (demosaic.rs:67-119) + to_lab + basecurve + from_lab + gamma for ONE
-// pixel straight from the raw frame, in the bit-exact arithmetic of ipb_device.cuh; any CFA, any position.
-// `gamma`: apply OpGamma (false: the clamped linear value, for the probe).
-__device__ __noinline__ void exact_pixel(const SpecParams &p, const CfaDev &cfa, const ColorParams &P, int x, int y,
-                                         bool gamma, float out[3]) {
-  const int pix = cfa.pat[(y % 48) * 48 + x % 48];
-  float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;
-  int n0 = 0, n1 = 0, n2 = 0, n3 = 0;
-#pragma unroll
-  for (int dy = -1; dy <= 1; dy++)
-#pragma unroll
-    for (int dx = -1; dx <= 1; dx++) {
-      const int yy = y + dy, xx = x + dx;
-      if (yy < 0 || yy >= p.height || xx < 0 || xx >= p.width) continue;  // demosaic.rs:103-104
-      const int oc = cfa.pat[(yy % 48) * 48 + xx % 48];
-      if (oc == pix && (dx != 0 || dy != 0)) continue;                    // :87 the discarded fifth bin
-      const float v = golevel((float)__ldg(p.raw + (long long)(yy + p.crop_y - p.src_row0) * p.raw_pitch + p.crop_x + xx),
-                              p.black, p.range, p.range_rc, p.exact_rc);
-      if (oc == 0) { s0 = s0 + v; n0++; }
-      else if (oc == 1) { s1 = s1 + v; n1++; }
-      else if (oc == 2) { s2 = s2 + v; n2++; }
-      else if (oc == 3) { s3 = s3 + v; n3++; }
-    }
-  const float r = n0 ? __fdiv_rn(s0, (float)n0) : 0.0f, g = n1 ? __fdiv_rn(s1, (float)n1) : 0.0f;
-  const float b = n2 ? __fdiv_rn(s2, (float)n2) : 0.0f, e = n3 ? __fdiv_rn(s3, (float)n3) : 0.0f;
-  const LutGlobal lab{p.lut_lab}, gam{p.lut_gamma};
-  float l, a, bb;
-  camera_to_lab<true>(P, lab, r, g, b, e, l, a, bb);
-  if (P.sp.n > 0) l = spline_eval(P.sp, l);
-  lab_to_rgb<true>(P, l, a, bb, out[0], out[1], out[2]);
-#pragma unroll
-  for (int c = 0; c < 3; c++) out[c] = gamma ? gamma_elem(gam, out[c]) : fminf(fmaxf(out[c], 0.0f), 1.0f);
+// SplineFunc::interpolate (curves.rs:126-157) from the table in shared memory — the evaluation k_fused_full uses
+// (ipb_fused.cu spline_eval_smem): entry = number of knots <= val; entries 0 and n are the constant end pieces
+// {y, 0, 0, 0}.  The launch is gated on finite, strictly increasing knots (ipb_host.cu fused_params_bounded).
+__device__ __forceinline__ float spline_exact(const float (*spl)[8], const SplineDev &s, float val) {
+  int idx = (val >= s.x[0] ? 1 : 0) + (val >= s.x[1] ? 1 : 0);
+  for (int j = 2; j < s.n; j++) idx += val >= s.x[j] ? 1 : 0;
+  const float4 c = *reinterpret_cast<const float4 *>(spl[idx]);
+  const float c3 = spl[idx][4];
+  const float diff = val - c.x;
+  return c.y + c.z * diff + c.w * diff * diff + c3 * diff * diff * diff;
 }
 
-__device__ __forceinline__ void fixup_pixel(const SpecParams &p, const CfaDev &cfa, const ColorParams &P, uint32_t idx) {
+// XYZ_LAB_TRANSFORM.lookup (color_conversions.rs:102-114,120-124) without divergent calls, the scheme of k_fused_full
+// (ipb_fused.cu lab_outside_table): the table lerp for +0 <= v <= 1, the host libm's cbrtf from the context's table for
+// 1 < v <= 1.5, the line for v < 0 (its division in the verified reciprocal form), lab_f_slow for what is left
+// (v > 1.5, -0.0, NaN).
+__device__ __forceinline__ float lab_f_exact(const float2 *__restrict__ lut, const float *__restrict__ cbrt_tab, float v) {
+  const float pos = v * kLutMax;
+  const float tf = __fadd_rd(pos, 8388608.0f);
+  const float a = pos - (tf - 8388608.0f);
+  const float2 e = __ldg(lut + (__float_as_uint(tf) & 0x1fffu));
+  float r = e.x + a * e.y;
+  const uint32_t u = __float_as_uint(v), first = 0x3f800001u, size = 1u << 22;
+  if (u - first < size) r = __ldg(cbrt_tab + (u - first));
+  if (v < 0.0f) r = div_rc(kLabK * v + 16.0f, 116.0f, 1.0f / 116.0f);
+  if (u - (first + size) <= 0x80000000u - (first + size) || u > 0xff800000u) r = lab_f_slow(v);
+  return r;
+}
+
+// gofloat (gofloat.rs:127) + demosaic::full (demosaic.rs:67-119) + to_lab + basecurve + from_lab for ONE pixel of an
+// RGB Bayer frame straight from the raw frame, in the reference's arithmetic (the per-pixel code of ipb_device.cuh with
+// the verified reciprocal divisions; k_fused_full's table for cube roots above one); any position, frame borders
+// included (a tap outside the frame is dropped from sum and count, :103-107).  Taps reach their colour's sum in the
+// reference's raster order.  Both kinds of site run the same instructions (all nine taps, four means, a select), so a
+// warp of queue entries does not diverge.  `phase` holds the colour of position (row & 1, col & 1) in bits
+// 2*(2*(row&1)+(col&1)).  Out: linear RGB before OpGamma.
+__device__ __forceinline__ void exact_bayer_linear(const SpecParams &p, const ColorParams &P, const float (*spl)[8],
+                                                   uint32_t phase, int x, int y, float out[3]) {
+  const uint16_t *ctr = p.raw + (long long)(y + p.crop_y - p.src_row0) * p.raw_pitch + p.crop_x + x;
+  const long long pitch = p.raw_pitch;
+  const bool hn = y > 0, hs = y < p.height - 1, hw = x > 0, he = x < p.width - 1;
+  auto tap = [&](bool have, long long off) {
+    const float raw = have ? (float)__ldg(ctr + off) : 0.0f;
+    return fminf(div_rc(raw - p.black, p.range, p.range_rc), 1.0f);
+  };
+  auto mean = [](float s, int n) { return n == 4 ? s * 0.25f : n == 2 ? s * 0.5f : n ? __fdiv_rn(s, (float)n) : 0.0f; };
+  const float t_nw = tap(hn && hw, -pitch - 1), t_n = tap(hn, -pitch), t_ne = tap(hn && he, -pitch + 1);
+  const float t_w = tap(hw, -1), v = tap(true, 0), t_e = tap(he, 1);
+  const float t_sw = tap(hs && hw, pitch - 1), t_s = tap(hs, pitch), t_se = tap(hs && he, pitch + 1);
+  // sums start at +0.0 and skip missing taps (x + 0.0 == x for these sums, which are never -0.0)
+  float sg = 0.0f, sd = 0.0f, sh = 0.0f, sv = 0.0f;
+  if (hn && hw) sd = sd + t_nw;
+  if (hn) { sg = sg + t_n; sv = sv + t_n; }
+  if (hn && he) sd = sd + t_ne;
+  if (hw) { sg = sg + t_w; sh = sh + t_w; }
+  if (he) { sg = sg + t_e; sh = sh + t_e; }
+  if (hs && hw) sd = sd + t_sw;
+  if (hs) { sg = sg + t_s; sv = sv + t_s; }
+  if (hs && he) sd = sd + t_se;
+  const int nv = (int)hn + (int)hs, nh = (int)hw + (int)he;
+  const float mg = mean(sg, nv + nh), md = mean(sd, nv * nh), mh = mean(sh, nh), mv = mean(sv, nv);
+  const int c = (phase >> (2 * (2 * (y & 1) + (x & 1)))) & 3;            // this site's colour
+  const int ch = (phase >> (2 * (2 * (y & 1) + ((x & 1) ^ 1)))) & 3;     // the colour of its left / right neighbours
+  // green site: own sample, left/right mean for colour ch, up/down mean for the third; red / blue site: own sample,
+  // edge mean for green, corner mean for the third
+  const bool gsite = c == 1;
+  const int first = gsite ? ch : c;  // colour (0 or 2) that receives `a0`
+  const float a0 = gsite ? mh : v, a1 = gsite ? mv : md;
+  const float r = first == 0 ? a0 : a1, g = gsite ? v : mg, b = first == 0 ? a1 : a0;
+  // camera_to_lab (color_conversions.rs:42-55,156-169), statement for statement as ipb_device.cuh camera_to_lab<true>
+  const float cr = fminf(r * P.mul[0], 1.0f), cg = fminf(g * P.mul[1], 1.0f), cb = fminf(b * P.mul[2], 1.0f);
+  const float X = cr * P.cm[0] + cg * P.cm[1] + cb * P.cm[2];
+  const float Y = cr * P.cm[4] + cg * P.cm[5] + cb * P.cm[6];
+  const float Z = cr * P.cm[8] + cg * P.cm[9] + cb * P.cm[10];
+  const float fx = lab_f_exact(p.lut_lab, p.cbrt_tab, divc<true>(X, 0.95047f));
+  const float fy = lab_f_exact(p.lut_lab, p.cbrt_tab, Y);
+  const float fz = lab_f_exact(p.lut_lab, p.cbrt_tab, divc<true>(Z, 1.08883f));
+  float l = divc<true>(116.0f * fy - 16.0f, 100.0f);
+  const float a = divc<true>(500.0f * (fx - fy) + 127.0f, 255.0f);
+  const float bb = divc<true>(200.0f * (fy - fz) + 127.0f, 255.0f);
+  if (P.sp.n > 0) l = spline_exact(spl, P.sp, l);
+  lab_to_rgb<true>(P, l, a, bb, out[0], out[1], out[2]);
+}
+
+__device__ __forceinline__ void fixup_pixel(const SpecParams &p, const ColorParams &P, const float (*spl)[8], uint32_t phase,
+                                            uint32_t idx) {
   const int row = (int)(idx / (uint32_t)p.width), x = (int)(idx - (uint32_t)row * (uint32_t)p.width);
   float v[3];
-  exact_pixel(p, cfa, P, x, p.out_row0 + row, true, v);
+  exact_bayer_linear(p, P, spl, phase, x, p.out_row0 + row, v);
+  const LutGlobal gam{p.lut_gamma};
   uint8_t *o = p.out + (size_t)idx * 3;
-  o[0] = (uint8_t)output8bit(v[0]);
-  o[1] = (uint8_t)output8bit(v[1]);
-  o[2] = (uint8_t)output8bit(v[2]);
+  o[0] = (uint8_t)output8bit(gamma_elem(gam, v[0]));  // gamma.rs:21, color_conversions.rs:323-325
+  o[1] = (uint8_t)output8bit(gamma_elem(gam, v[1]));
+  o[2] = (uint8_t)output8bit(gamma_elem(gam, v[2]));
+}
+
+// out of line, for the queue-overflow path only (parameters reached through a generic pointer: slow, and rare)
+__device__ __noinline__ void fixup_pixel_slow(const SpecParams &p, const ColorParams &P, const float (*spl)[8], uint32_t phase,
+                                              uint32_t idx) {
+  fixup_pixel(p, P, spl, phase, idx);
 }
 
 __device__ __forceinline__ void issue_tile(const SpecParams &p, const CUtensorMap *tmap, uint32_t raw_stage, uint32_t bar,
@@ -295,7 +355,8 @@ __device__ __forceinline__ uint32_t cheap_task(const SpecParams &p, uint32_t g8_
   if (min(min(d0, d1), min(d2, d3)) <= p.amb2) {
     flags = (d0 <= p.amb2 ? 1u : 0u) | (d1 <= p.amb2 ? 2u : 0u) | (d2 <= p.amb2 ? 4u : 0u) | (d3 <= p.amb2 ? 8u : 0u);
   }
-  if (fminf(y02, y13) < p.y_min) flags = 0xfu;  // outside the certified domain (far below black): all four exactly
+  if (fminf(y02, y13) < p.y_min)  // outside the certified domain (far below black): that pixel pair exactly
+    flags |= (y02 < p.y_min ? 5u : 0u) | (y13 < p.y_min ? 10u : 0u);
   return flags;
 }
 
@@ -345,6 +406,15 @@ k_spec8(const __grid_constant__ SpecParams p, const __grid_constant__ CfaDev cfa
     return;
   }
   const uint32_t stab_bias = smem_u32(sm.stab) - p.bias58;  // (0x4B000000 << 3) mod 2^32: tf = 2^23 + key
+  for (int i = tid; i < kSplRows; i += NT) {
+    float e[5] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
+    if (i == 0) e[1] = P.sp.y_first;
+    else if (i >= P.sp.n) e[1] = P.sp.y_last;
+    else { e[0] = P.sp.x[i - 1]; e[1] = P.sp.y[i - 1]; e[2] = P.sp.c1[i - 1]; e[3] = P.sp.c2[i - 1]; e[4] = P.sp.c3[i - 1]; }
+#pragma unroll
+    for (int k = 0; k < 5; k++) sm.spl[i][k] = e[k];
+  }
+  const uint32_t phase = (uint32_t)cfa.pat[0] | ((uint32_t)cfa.pat[1] << 2) | ((uint32_t)cfa.pat[48] << 4) | ((uint32_t)cfa.pat[49] << 6);
 
   // gofloat (gofloat.rs:127) of the staged raw box into tile buffer `buf`, exactly as the reference rounds it (the
   // cheap pass and the reference then start from identical samples).  Even / odd columns go to separate planes.
@@ -404,7 +474,7 @@ k_spec8(const __grid_constant__ SpecParams p, const __grid_constant__ CfaDev cfa
       const int j = __ffs(flags) - 1;
       flags &= flags - 1u;
       if (pos < kQueueCap) sm.queue[pos] = pix + j;
-      else fixup_pixel(p, cfa, P, pix + j);
+      else fixup_pixel_slow(p, P, sm.spl, phase, pix + j);
       pos++;
     }
   };
@@ -483,7 +553,7 @@ k_spec8(const __grid_constant__ SpecParams p, const __grid_constant__ CfaDev cfa
     // fix-up queue: recompute when it is half full (dense: every thread takes entries)
     const int qn = min(sm.qn, kQueueCap);
     if (qn >= kFlushAt) {
-      for (int i = tid; i < qn; i += NT) fixup_pixel(p, cfa, P, sm.queue[i]);
+      for (int i = tid; i < qn; i += NT) fixup_pixel(p, P, sm.spl, phase, sm.queue[i]);
       __syncthreads();
       if (tid == 0) {
         if (p.stats) atomicAdd(p.stats, (unsigned long long)sm.qn);
@@ -494,7 +564,7 @@ k_spec8(const __grid_constant__ SpecParams p, const __grid_constant__ CfaDev cfa
   }
   // the last barrier of the loop ordered every push before this read
   const int qn = min(sm.qn, kQueueCap);
-  for (int i = tid; i < qn; i += NT) fixup_pixel(p, cfa, P, sm.queue[i]);
+  for (int i = tid; i < qn; i += NT) fixup_pixel(p, P, sm.spl, phase, sm.queue[i]);
   if (tid == 0 && p.stats && sm.qn) atomicAdd(p.stats, (unsigned long long)sm.qn);
 }
 
@@ -508,6 +578,15 @@ __global__ void k_spec_probe(const __grid_constant__ SpecParams p, const __grid_
   float2 *stab = reinterpret_cast<float2 *>(probe_smem);
   for (int i = threadIdx.x; i < kSpecG8Entries; i += blockDim.x) g8a[i] = p.g8a[i];
   for (int i = threadIdx.x; i < kSpecSTabEntries; i += blockDim.x) stab[i] = p.stab[i];
+  float (*spl)[8] = reinterpret_cast<float (*)[8]>(probe_smem + kSpecSTabEntries * 8);
+  for (int i = threadIdx.x; i < kSplRows; i += blockDim.x) {
+    float e[5] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
+    if (i == 0) e[1] = P.sp.y_first;
+    else if (i >= P.sp.n) e[1] = P.sp.y_last;
+    else { e[0] = P.sp.x[i - 1]; e[1] = P.sp.y[i - 1]; e[2] = P.sp.c1[i - 1]; e[3] = P.sp.c2[i - 1]; e[4] = P.sp.c3[i - 1]; }
+    for (int k = 0; k < 5; k++) spl[i][k] = e[k];
+  }
+  const uint32_t phase = (uint32_t)cfa.pat[0] | ((uint32_t)cfa.pat[1] << 2) | ((uint32_t)cfa.pat[48] << 4) | ((uint32_t)cfa.pat[49] << 6);
   __syncthreads();
   const uint32_t g8_base = smem_u32(g8a), stab_bias = smem_u32(stab) - p.bias58;
   if ((g8_base & 0x7fffu) != 0u) return;
@@ -541,7 +620,8 @@ __global__ void k_spec_probe(const __grid_constant__ SpecParams p, const __grid_
     if (fminf(y02, y13) < p.y_min) continue;  // outside the certified domain: the kernel recomputes these
     for (int j = 0; j < 4; j++) {
       float ex[3];
-      exact_pixel(p, cfa, P, x0 + j, y, false, ex);
+      exact_bayer_linear(p, P, spl, phase, x0 + j, y, ex);
+      for (int c = 0; c < 3; c++) ex[c] = fminf(fmaxf(ex[c], 0.0f), 1.0f);  // gamma.rs:21 clamps before the table
       const float *l = (j & 1) ? l13 : l02;
       const int h = j >> 1;
       for (int c = 0; c < 3; c++) {
@@ -651,7 +731,7 @@ cudaError_t launch_fused_spec8(cudaStream_t s, const FusedArgs &a, const CfaDev 
     p.sub_b = integral ? 0.0f : -a.black;
   }
   p.bias58 = 0x58000000u;
-  p.lut_lab = a.lut_lab; p.lut_gamma = a.lut_gamma;
+  p.lut_lab = a.lut_lab; p.lut_gamma = a.lut_gamma; p.cbrt_tab = a.cbrt_tab;
   p.g8a = T.g8a; p.stab = T.stab; p.stats = T.stats;
   p.tiles_x = (p.width + kTW - 1) / kTW;
   p.tiles_y = (p.out_row1 - p.out_row0 + kTH - 1) / kTH;
@@ -701,7 +781,7 @@ cudaError_t launch_spec_probe(cudaStream_t s, const FusedArgs &a, const CfaDev &
     p.sub_b = integral ? 0.0f : -a.black;
   }
   p.bias58 = 0x58000000u;
-  p.lut_lab = a.lut_lab; p.lut_gamma = a.lut_gamma;
+  p.lut_lab = a.lut_lab; p.lut_gamma = a.lut_gamma; p.cbrt_tab = a.cbrt_tab;
   p.g8a = T.g8a; p.stab = T.stab; p.stats = T.stats;
   const size_t smem = kG8Offset + kSpecG8Entries * 4;
   cudaError_t e = cudaFuncSetAttribute(k_spec_probe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

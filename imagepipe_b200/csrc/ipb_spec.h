@@ -11,7 +11,7 @@ constexpr int kSpecG8Entries = 8192;          // gamma table segments: F >> 10, 
 constexpr double kSpecFScale = 8388608.0 - 1024.0;  // 2^23 - 2^10: v = 1 lands on the first value of segment 8191
 constexpr int kSpecSTabN = 2048;              // basecurve table: segments over fy in [16/116, 1]
 constexpr int kSpecSTabEntries = kSpecSTabN + 4;  // + one guard below, two above, one of padding (16-byte multiple)
-constexpr float kSpecYMin = -0.01f;           // pixels whose Y ratio lies below are outside the certified domain: recomputed
+constexpr float kSpecYMin = -0.03f;           // pixels whose Y ratio lies below are outside the certified domain: recomputed
 constexpr uint32_t kSpecSmemBase = 0x400;     // shared-window address of dynamic shared memory (probed at context creation)
 
 struct SpecParams {
@@ -28,6 +28,7 @@ struct SpecParams {
   float black, range, range_rc;
   int exact_rc;
   const float2 *lut_lab, *lut_gamma;
+  const float *cbrt_tab;  // host cbrtf of every float in (1, 1.5] (ipb_host.cu ensure_cbrt_table)
   // ---- cheap path: tables
   const uint32_t *g8a;   // kSpecG8Entries words: (byte << 24) + (2^24 - thrF) + deltaF - 0x3F800000
   const float2 *stab;    // kSpecSTabEntries {intercept, slope}

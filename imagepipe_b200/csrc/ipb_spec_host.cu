@@ -146,10 +146,16 @@ bool spec_build(const ColorParams &P, float black, float range, float mufu_rel_e
       smag = std::max(smag, fabs(s));
       d_max = std::max(d_max, s - f);
       const double pos = (f - f0) / h + 1.0, frac = pos - floor(pos);
-      if (pos <= 1e-3 || pos >= kSpecSTabN + 2 - 1e-3) continue;  // saturated index: no neighbour can be chosen
-      if (frac < 1e-3) chord = std::max(chord, fabs(tab_eval(f, -1) - s));
-      if (frac > 1.0 - 1e-3) chord = std::max(chord, fabs(tab_eval(f, +1) - s));
+      (void)frac;
     }
+    // the kernel's index comes from one f32 FMA: it can be one off within 3e-4 of a segment boundary (2 ulp of the
+    // scaled position), where it then extrapolates the neighbouring chord
+    for (int k = 1; k <= kSpecSTabN + 1; k++)
+      for (double off : {-3e-4, 3e-4}) {
+        const double f = f0 + (k - 1 + off) * h;
+        if (f < fy_lo || f > fy_hi) continue;
+        chord = std::max(chord, fabs(tab_eval(f, off < 0 ? +1 : -1) - S_real(sp, f)));
+      }
     for (int k = 0; k <= kSpecSTabN + 2; k++) {
       ls_max = std::max(ls_max, fabs(B[k] - 1.0));
       sp_max = std::max(sp_max, fabs(B[k]));
@@ -180,8 +186,9 @@ bool spec_build(const ColorParams &P, float black, float range, float mufu_rel_e
   std::vector<double> axis[3];
   for (int j = 0; j < 3; j++) {
     const double m = (double)P.mul[j], cmax = std::min(m * gmax, 1.0), cmin = m * gmin;
-    for (int k = 0; k <= 4; k++) axis[j].push_back(cmin * (4 - k) / 4.0);  // cmin .. 0
-    for (int k = 0; k < 40; k++) axis[j].push_back(cmax * pow(10.0, -4.0 + 4.0 * (k + 1) / 40.0));  // 1e-4*cmax .. cmax
+    for (int k = 0; k <= 4; k++) axis[j].push_back(cmin * (4 - k) / 4.0);                  // cmin .. 0
+    for (int k = 0; k < 12; k++) axis[j].push_back(cmax * pow(10.0, -4.0 + 3.0 * k / 12.0));  // 1e-4*cmax .. 0.1*cmax
+    for (int k = 0; k <= 27; k++) axis[j].push_back(cmax * (0.1 + 0.9 * k / 27.0));          // 0.1*cmax .. cmax
   }
   const double hS = h * 0.5;
   double delta = 0.0, worst_ex[3] = {0, 0, 0};
@@ -233,6 +240,9 @@ bool spec_build(const ColorParams &P, float black, float range, float mufu_rel_e
         for (int ch = 0; ch < 3; ch++) {
           double d = 0.0;
           for (int j = 0; j < 3; j++) d += fabs(RO[ch][j]) * (EXp[j] + 9.0 * U * Xp[j]);
+          if (d > delta && getenv("IPB_SPEC_DEBUG2"))
+            fprintf(stderr, "  ch %d c (%.4f %.4f %.4f) x (%.4f %.4f %.4f) ef %.1f %.1f %.1f u e_sE %.1f e_stab %.1f ls %.3f spl %.3f D %.3f EX %.1f %.1f %.1f u X' %.3f %.3f %.3f d %.3g\n",
+                    ch, ca, cb, cc, x[0], x[1], x[2], ef[0] / U, ef[1] / U, ef[2] / U, e_sE / U, e_stab / U, ls, spl, D, EXp[0] / U, EXp[1] / U, EXp[2] / U, Xp[0], Xp[1], Xp[2], d);
           delta = std::max(delta, d);
         }
       }

@@ -35,7 +35,6 @@ class Context:
     def set_stream(self, stream):
         _capi.check(self.handle, lib().ipb_ctx_set_stream(self.handle, C.c_void_p(stream) if stream else None))
 
-    @property
     def set_spec(self, delta=0.0, threads=512):
         """Test / tuning hook of the speculative 8-bit kernel: forced bound (0 = certified) and CTA size."""
         _capi.check(self.handle, lib().ipb_ctx_set_spec(self.handle, float(delta), int(threads)))
@@ -48,6 +47,7 @@ class Context:
         f = lambda v: struct.unpack("<f", struct.pack("<I", v & 0xffffffff))[0]
         return {"fixups": int(out[0]), "bad_window": int(out[1]), "delta": f(out[2]), "mufu_err": f(out[3])}
 
+    @property
     def launch_count(self):
         return int(lib().ipb_ctx_launch_count(self.handle))
 

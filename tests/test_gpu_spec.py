@@ -70,7 +70,7 @@ def test_queue_flush_and_overflow(ip, orc, ctx):
     the black level puts every pixel outside the certified domain, the queue overflows and pixels are recomputed in place."""
     params = common.raw_params()
     rng = np.random.default_rng(5)
-    dark = rng.integers(0, 300, (256, 1280)).astype(np.uint16)       # far below black (512): Y ratio < -0.01 everywhere
+    dark = rng.integers(0, 30, (256, 1280)).astype(np.uint16)        # far below black (512): Y ratio < -0.03 everywhere
     ctx.spec_stats(reset=True)
     got = out8(ip, ctx, dark, params)
     assert ctx.spec_stats()["fixups"] >= dark.size * 0.9

@@ -52,3 +52,5 @@ run("speculative 512, delta 7.9e-5", True, 512, 7.9e-5)
 ctx.set_spec(0.0, 512)
 mx, mean, delta = sets[0][0].spec_probe()
 print(f"probe: max |cheap-exact| {mx:.3g}  mean {mean:.3g}  certified delta {delta:.3g}  mufu err {ctx.spec_stats()['mufu_err']:.3g}")
+run("speculative 512, delta 1e-7 (cheap pass only)", True, 512, 1e-7)
+run("speculative 1024, delta 1e-7 (cheap pass only)", True, 1024, 1e-7)
