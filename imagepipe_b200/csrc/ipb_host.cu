@@ -50,6 +50,7 @@ struct ipb_ctx {
   float spec_delta_override = 0.0f; // tests: force the bound (0 = the certified one)
   uint32_t *spec_g8a = nullptr;
   float2 *spec_stab = nullptr;
+  float *spec_thr = nullptr;        // the 255 exact thresholds of the 8-bit gamma step function
   unsigned long long *spec_stats = nullptr;   // 8 counters, see SpecParams::stats
   void *spec_stage = nullptr;       // pinned staging for table uploads (capturable copies)
   SpecTables spec_tab{};
@@ -637,6 +638,7 @@ int ipb_ctx_create(int device, void *stream, ipb_ctx **out) {
     unsigned int *d_st = nullptr, h_st[2] = {0, 0};
     if ((e = cudaMalloc((void **)&ctx->spec_g8a, kSpecG8Entries * sizeof(uint32_t))) != cudaSuccess ||
         (e = cudaMalloc((void **)&ctx->spec_stab, kSpecSTabEntries * sizeof(float2))) != cudaSuccess ||
+        (e = cudaMalloc((void **)&ctx->spec_thr, 256 * sizeof(float))) != cudaSuccess ||
         (e = cudaMalloc((void **)&ctx->spec_stats, 8 * sizeof(unsigned long long))) != cudaSuccess ||
         (e = cudaMemset(ctx->spec_stats, 0, 8 * sizeof(unsigned long long))) != cudaSuccess ||
         (e = cudaHostAlloc(&ctx->spec_stage, kSpecG8Entries * sizeof(uint32_t) + kSpecSTabEntries * sizeof(float2), cudaHostAllocDefault)) != cudaSuccess ||
@@ -651,6 +653,17 @@ int ipb_ctx_create(int device, void *stream, ipb_ctx **out) {
     }
     cudaFree(d_st);
     memcpy(&ctx->mufu_cbrt_err, &h_st[1], 4);
+    if (g_gamma8_ok) {
+      std::vector<float> thr;
+      for (const Gamma8Entry &g : g_gamma8)
+        if (g.thr <= 1.0f) thr.push_back(g.thr);
+      if (thr.size() != 255) g_gamma8_ok = false;
+      thr.resize(256, 2.0f);
+      if ((e = cudaMemcpy(ctx->spec_thr, thr.data(), 256 * sizeof(float), cudaMemcpyHostToDevice)) != cudaSuccess) {
+        ctx->err = cudaGetErrorString(e);
+        return bail(IPB_ERR_CUDA);
+      }
+    }
     ctx->spec_ok = (h_st[0] == kSpecSmemBase && g_gamma8_ok && ctx->mufu_cbrt_err < 4.0e-6f) ? 1 : 0;
   }
   *out = ctx;
@@ -668,6 +681,7 @@ void ipb_ctx_destroy(ipb_ctx *ctx) {
   if (ctx->cbrt_tab) cudaFree(ctx->cbrt_tab);
   if (ctx->spec_g8a) cudaFree(ctx->spec_g8a);
   if (ctx->spec_stab) cudaFree(ctx->spec_stab);
+  if (ctx->spec_thr) cudaFree(ctx->spec_thr);
   if (ctx->spec_stats) cudaFree(ctx->spec_stats);
   if (ctx->spec_stage) cudaFreeHost(ctx->spec_stage);
   for (auto &t : ctx->lz_tabs) cudaFree(t.start);
@@ -1550,7 +1564,8 @@ static int ensure_spec_tables(ipb_ctx *ctx, const ColorParams &P, float black, f
   std::vector<uint32_t> g8a;
   std::vector<float2> stab;
   SpecTables T{};
-  if (!spec_build(P, black, range, ctx->mufu_cbrt_err, ctx->spec_delta_override, thr, &g8a, &stab, &T.consts, &T.delta))
+  float dl[4] = {0, 0, 0, 0};
+  if (!spec_build(P, black, range, ctx->mufu_cbrt_err, ctx->spec_delta_override, thr, &g8a, &stab, &T.consts, dl))
     return IPB_OK;
   // the previous upload may still be in flight from the pinned staging buffer
   IPB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -1560,8 +1575,11 @@ static int ensure_spec_tables(ipb_ctx *ctx, const ColorParams &P, float black, f
   IPB_CUDA(ctx, cudaMemcpyAsync(ctx->spec_g8a, st, kSpecG8Entries * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
   IPB_CUDA(ctx, cudaMemcpyAsync(ctx->spec_stab, st + kSpecG8Entries * sizeof(uint32_t), kSpecSTabEntries * sizeof(float2),
                                 cudaMemcpyHostToDevice, ctx->stream));
+  T.delta = dl[0];
+  for (int ch = 0; ch < 3; ch++) T.delta_ch[ch] = dl[1 + ch];
   T.g8a = ctx->spec_g8a;
   T.stab = ctx->spec_stab;
+  T.thr8 = ctx->spec_thr;
   T.stats = ctx->spec_stats;
   ctx->spec_tab = T;
   ctx->spec_tab_state = 1;
@@ -2224,7 +2242,10 @@ int ipb_spec_bound(const ipb_ops *ops, float mufu_rel_err, float *delta) {
   std::vector<float2> stab;
   SpecParams c;
   const float black = ops->gofloat.blacklevels[0], range = ops->gofloat.whitelevels[0] - black;
-  return spec_build(P, black, range, mufu_rel_err, 0.0f, thr, &g8a, &stab, &c, delta) ? IPB_OK : IPB_ERR_UNSUPPORTED;
+  float dl[4];
+  if (!spec_build(P, black, range, mufu_rel_err, 0.0f, thr, &g8a, &stab, &c, dl)) return IPB_ERR_UNSUPPORTED;
+  for (int k = 0; k < 4; k++) delta[k] = dl[k];
+  return IPB_OK;
 }
 
 int ipb_pipeline_spec_probe(ipb_pipeline *p, float *max_dev, double *mean_dev, float *delta) {

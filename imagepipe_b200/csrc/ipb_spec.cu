@@ -43,17 +43,24 @@ constexpr int kPS = kTileStride / 2;   // plane stride (floats): 72
 constexpr uint32_t kFull = 0xffffffffu;
 constexpr int kG8Offset = 32768 - (int)kSpecSmemBase;  // the gamma table starts on a 32 KB boundary of the shared window
 constexpr int kSplRows = kMaxSplinePts + 2;
-constexpr int kQueueCap = (kG8Offset - kSpecSTabEntries * 8 - kSplRows * 32 - 32) / 4;
-constexpr int kFlushAt = kQueueCap / 2;
+constexpr int kChunks = (kTileElems / 8 + 31) / 32;  // conversion chunks per tile: 32 lanes x 8 samples
 
-struct SmemSpec {
+struct SmemFront {
   float2 stab[kSpecSTabEntries];                // basecurve in f-space: {intercept, slope} per segment
-  uint32_t queue[kQueueCap];                    // fix-up queue: pixel index inside the launch's output rows
-  float spl[kSplRows][8];                       // exact basecurve: [0] below the first knot, [1 + i] segment i, [n] at / above the last
+  alignas(16) float spl[kSplRows][8];           // exact basecurve: [0] below the first knot, [1 + i] segment i, [n] at / above the last
+  float thr[260];                               // the 255 thresholds of output8bit(apply_srgb_gamma(v)), then +inf
+  alignas(16) SpecParams sp;                    // copies for the out-of-line exact path (a generic pointer into the
+  alignas(16) ColorParams cp;                   // constant bank would turn every parameter access into a global load)
   alignas(8) unsigned long long mbar;
   alignas(8) unsigned long long mbar_tab;
   int conv_ctr[2];
   int qn, pad;
+};
+constexpr int kQueueCap = (kG8Offset - (int)sizeof(SmemFront)) / 4;
+
+struct SmemSpec : SmemFront {
+  uint32_t queue[kQueueCap];                    // uncertified pixels: row << 16 | column (row inside the launch's output rows)
+  unsigned char fill[kG8Offset - (int)sizeof(SmemFront) - kQueueCap * 4];
   uint32_t g8a[kSpecG8Entries];                 // {byte, threshold} fixed-point gamma table; 32 KB aligned: its
                                                 // entries are addressed by (bits & 0x7ffc) | base, one LOP3
   float plane[2][kTileRows][2][kPS];            // [buffer][tile row][even / odd columns][column / 2]
@@ -176,10 +183,10 @@ __device__ __forceinline__ float chain_pair(const SpecParams &p, uint32_t g8_bas
   const F2 g{__saturatef(fmaf(Z.x, p.ro[1][2], g0.x)), __saturatef(fmaf(Z.y, p.ro[1][2], g0.y))};
   const F2 b{__saturatef(fmaf(Z.x, p.ro[2][2], b0.x)), __saturatef(fmaf(Z.y, p.ro[2][2], b0.y))};
   if (PROBE) { lin[0] = r.x; lin[1] = r.y; lin[2] = g.x; lin[3] = g.y; lin[4] = b.x; lin[5] = b.y; }
-  // fixed point: u = 1 + v*(1 - 2^-13) has the bit pattern 0x3F800000 + F, F = round(v * (2^23 - 2^10)); table
-  // segment = floor(v * 8191), taken from a second float whose mantissa is floor(v * 32764): bits 2..14 = the segment
+  // fixed point: u = one[c] + v*(1 - 2^-13) has the bit pattern 0x3F800000 + F + deltaF_c, F = round(v * (2^23 - 2^10));
+  // table segment = floor(v * 8191), taken from a second float whose mantissa is floor(v * 32764): bits 2..14
   const float c = 1.0f - 1.0f / 8192.0f, c1 = 32764.0f / 8388608.0f;
-  const F2 ur = f2(r, splat(c), splat(1.0f)), ug = f2(g, splat(c), splat(1.0f)), ub = f2(b, splat(c), splat(1.0f));
+  const F2 ur = f2(r, splat(c), splat(p.one[0])), ug = f2(g, splat(c), splat(p.one[1])), ub = f2(b, splat(c), splat(p.one[2]));
   const F2 kr = pk_fma_rm(r, splat(c1), splat(1.0f)), kg = pk_fma_rm(g, splat(c1), splat(1.0f)), kb = pk_fma_rm(b, splat(c1), splat(1.0f));
   const float uu[6] = {ur.x, ur.y, ug.x, ug.y, ub.x, ub.y}, kk[6] = {kr.x, kr.y, kg.x, kg.y, kb.x, kb.y};
 #pragma unroll
@@ -252,36 +259,28 @@ __device__ __forceinline__ float lab_f_exact(const float2 *__restrict__ lut, con
   return r;
 }
 
-// gofloat (gofloat.rs:127) + demosaic::full (demosaic.rs:67-119) + to_lab + basecurve + from_lab for ONE pixel of an
-// RGB Bayer frame straight from the raw frame, in the reference's arithmetic (the per-pixel code of ipb_device.cuh with
-// the verified reciprocal divisions; k_fused_full's table for cube roots above one); any position, frame borders
-// included (a tap outside the frame is dropped from sum and count, :103-107).  Taps reach their colour's sum in the
-// reference's raster order.  Both kinds of site run the same instructions (all nine taps, four means, a select), so a
-// warp of queue entries does not diverge.  `phase` holds the colour of position (row & 1, col & 1) in bits
-// 2*(2*(row&1)+(col&1)).  Out: linear RGB before OpGamma.
+// demosaic::full (demosaic.rs:67-119) + to_lab + basecurve + from_lab for ONE pixel of an RGB Bayer frame from its nine
+// level-mapped taps t[0..8] (raster order; whatever sits in a tap outside the frame is ignored), in the reference's
+// arithmetic: the per-pixel code of ipb_device.cuh with the verified reciprocal divisions and k_fused_full's table
+// for cube roots above one.  Any position, frame borders included (a tap outside the frame is dropped from sum and
+// count, :103-107).  Taps reach their colour's sum in the reference's raster order.  Both kinds of site run the same
+// instructions (four means, a select), so a warp of queue entries does not diverge.  `phase` holds the colour of
+// position (row & 1, col & 1) in bits 2*(2*(row&1)+(col&1)).  Out: linear RGB before OpGamma.
 __device__ __forceinline__ void exact_bayer_linear(const SpecParams &p, const ColorParams &P, const float (*spl)[8],
-                                                   uint32_t phase, int x, int y, float out[3]) {
-  const uint16_t *ctr = p.raw + (long long)(y + p.crop_y - p.src_row0) * p.raw_pitch + p.crop_x + x;
-  const long long pitch = p.raw_pitch;
+                                                   uint32_t phase, int x, int y, const float t[9], float out[3]) {
   const bool hn = y > 0, hs = y < p.height - 1, hw = x > 0, he = x < p.width - 1;
-  auto tap = [&](bool have, long long off) {
-    const float raw = have ? (float)__ldg(ctr + off) : 0.0f;
-    return fminf(div_rc(raw - p.black, p.range, p.range_rc), 1.0f);
-  };
   auto mean = [](float s, int n) { return n == 4 ? s * 0.25f : n == 2 ? s * 0.5f : n ? __fdiv_rn(s, (float)n) : 0.0f; };
-  const float t_nw = tap(hn && hw, -pitch - 1), t_n = tap(hn, -pitch), t_ne = tap(hn && he, -pitch + 1);
-  const float t_w = tap(hw, -1), v = tap(true, 0), t_e = tap(he, 1);
-  const float t_sw = tap(hs && hw, pitch - 1), t_s = tap(hs, pitch), t_se = tap(hs && he, pitch + 1);
+  const float v = t[4];
   // sums start at +0.0 and skip missing taps (x + 0.0 == x for these sums, which are never -0.0)
   float sg = 0.0f, sd = 0.0f, sh = 0.0f, sv = 0.0f;
-  if (hn && hw) sd = sd + t_nw;
-  if (hn) { sg = sg + t_n; sv = sv + t_n; }
-  if (hn && he) sd = sd + t_ne;
-  if (hw) { sg = sg + t_w; sh = sh + t_w; }
-  if (he) { sg = sg + t_e; sh = sh + t_e; }
-  if (hs && hw) sd = sd + t_sw;
-  if (hs) { sg = sg + t_s; sv = sv + t_s; }
-  if (hs && he) sd = sd + t_se;
+  if (hn && hw) sd = sd + t[0];
+  if (hn) { sg = sg + t[1]; sv = sv + t[1]; }
+  if (hn && he) sd = sd + t[2];
+  if (hw) { sg = sg + t[3]; sh = sh + t[3]; }
+  if (he) { sg = sg + t[5]; sh = sh + t[5]; }
+  if (hs && hw) sd = sd + t[6];
+  if (hs) { sg = sg + t[7]; sv = sv + t[7]; }
+  if (hs && he) sd = sd + t[8];
   const int nv = (int)hn + (int)hs, nh = (int)hw + (int)he;
   const float mg = mean(sg, nv + nh), md = mean(sd, nv * nh), mh = mean(sh, nh), mv = mean(sv, nv);
   const int c = (phase >> (2 * (2 * (y & 1) + (x & 1)))) & 3;            // this site's colour
@@ -307,22 +306,71 @@ __device__ __forceinline__ void exact_bayer_linear(const SpecParams &p, const Co
   lab_to_rgb<true>(P, l, a, bb, out[0], out[1], out[2]);
 }
 
-__device__ __forceinline__ void fixup_pixel(const SpecParams &p, const ColorParams &P, const float (*spl)[8], uint32_t phase,
-                                            uint32_t idx) {
-  const int row = (int)(idx / (uint32_t)p.width), x = (int)(idx - (uint32_t)row * (uint32_t)p.width);
-  float v[3];
-  exact_bayer_linear(p, P, spl, phase, x, p.out_row0 + row, v);
-  const LutGlobal gam{p.lut_gamma};
-  uint8_t *o = p.out + (size_t)idx * 3;
-  o[0] = (uint8_t)output8bit(gamma_elem(gam, v[0]));  // gamma.rs:21, color_conversions.rs:323-325
-  o[1] = (uint8_t)output8bit(gamma_elem(gam, v[1]));
-  o[2] = (uint8_t)output8bit(gamma_elem(gam, v[2]));
+// gofloat (gofloat.rs:127) of the nine taps of pixel (x, y) straight from the raw frame, one 2-byte load per tap (probe)
+__device__ __forceinline__ void taps_from_frame(const SpecParams &p, int x, int y, float t[9]) {
+  const uint16_t *ctr = p.raw + (long long)(y + p.crop_y - p.src_row0) * p.raw_pitch + p.crop_x + x;
+  const bool hn = y > 0, hs = y < p.height - 1, hw = x > 0, he = x < p.width - 1;
+#pragma unroll
+  for (int dy = -1; dy <= 1; dy++)
+#pragma unroll
+    for (int dx = -1; dx <= 1; dx++) {
+      const bool have = (dy < 0 ? hn : dy > 0 ? hs : true) && (dx < 0 ? hw : dx > 0 ? he : true);
+      const float raw = have ? (float)__ldg(ctr + dy * p.raw_pitch + dx) : 0.0f;
+      t[(dy + 1) * 3 + dx + 1] = fminf(div_rc(raw - p.black, p.range, p.range_rc), 1.0f);
+    }
 }
 
-// out of line, for the queue-overflow path only (parameters reached through a generic pointer: slow, and rare)
-__device__ __noinline__ void fixup_pixel_slow(const SpecParams &p, const ColorParams &P, const float (*spl)[8], uint32_t phase,
-                                              uint32_t idx) {
-  fixup_pixel(p, P, spl, phase, idx);
+// The same taps with two aligned 4-byte loads per row instead of three 2-byte ones: a recomputed pixel's loads are
+// scattered (every lane its own sector), and it is the number of load instructions that the load/store unit pays for.
+// Rows start on 16-byte boundaries (the kernel's TMA precondition), so an even sample index is a 4-byte boundary.
+__device__ __forceinline__ void taps_from_frame_wide(const SpecParams &p, int x, int y, float t[9]) {
+  const int cx = p.crop_x + x - 1;                                   // sensor column of the left tap
+  const int b = min(max(cx & ~1, 0), (int)p.raw_pitch - 4);          // four samples b .. b+3 inside the row
+  const int d = cx - b;                                              // the left tap is sample d of them (-1 .. 3)
+#pragma unroll
+  for (int dy = -1; dy <= 1; dy++) {
+    const int yy = y + dy;
+    uint32_t w0 = 0, w1 = 0;
+    if (yy >= 0 && yy < p.height) {
+      const uint32_t *row = reinterpret_cast<const uint32_t *>(p.raw + (long long)(yy + p.crop_y - p.src_row0) * p.raw_pitch + b);
+      w0 = __ldg(row);
+      w1 = __ldg(row + 1);
+    }
+    const unsigned long long v = ((unsigned long long)w1 << 32) | w0;
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+      const int j = d + k;
+      const uint32_t sample = (j >= 0 && j < 4) ? (uint32_t)(v >> (16 * j)) & 0xffffu : 0u;  // out of the row: unused tap
+      t[(dy + 1) * 3 + k] = fminf(div_rc((float)sample - p.black, p.range, p.range_rc), 1.0f);
+    }
+  }
+}
+
+// output8bit(apply_srgb_gamma(clamp(v))) (gamma.rs:21, color_conversions.rs:323-325) exactly, from shared memory only:
+// the byte is the number of thresholds T[j] <= v (ipb_host.cu build_gamma8: the function is a verified step function
+// of v).  The fixed-point table of the cheap pass names it to within one — its segment holds at most one threshold and
+// its integer comparison can only be off where v is within a unit of that threshold — and two exact comparisons settle it.
+__device__ __forceinline__ uint32_t gamma8_exact(uint32_t g8_base, uint32_t thr_base, float v) {
+  const float vc = fminf(fmaxf(v, 0.0f), 1.0f);
+  const float u = fmaf(vc, 1.0f - 1.0f / 8192.0f, 1.0f), k = __fmaf_rd(vc, 32764.0f / 8388608.0f, 1.0f);
+  const uint32_t guess = (lds32u((__float_as_uint(k) & 0x7ffcu) | g8_base) + __float_as_uint(u)) >> 24;
+  const uint32_t lo = guess > 0u ? guess - 1u : 0u;
+  const float t0 = lds32f(thr_base + lo * 4u), t1 = lds32f(thr_base + lo * 4u + 4u);
+  return lo + (vc >= t0 ? 1u : 0u) + (vc >= t1 ? 1u : 0u);
+}
+
+// queue entry: (row inside the launch's output rows) << 16 | column.  Out of line: the exact path keeps its registers
+// (and the instruction cache footprint of its ~450 instructions) to itself; p and P are the copies in shared memory.
+__device__ __noinline__ void fixup_entry(const SpecParams &p, const ColorParams &P, const float (*spl)[8], uint32_t phase,
+                                         uint32_t g8_base, uint32_t thr_base, uint32_t entry) {
+  const int row = (int)(entry >> 16), x = (int)(entry & 0xffffu), y = p.out_row0 + row;
+  float t[9], v[3];
+  taps_from_frame_wide(p, x, y, t);
+  exact_bayer_linear(p, P, spl, phase, x, y, t, v);
+  uint8_t *o = p.out + ((size_t)row * (size_t)p.width + (size_t)x) * 3;
+  o[0] = (uint8_t)gamma8_exact(g8_base, thr_base, v[0]);
+  o[1] = (uint8_t)gamma8_exact(g8_base, thr_base, v[1]);
+  o[2] = (uint8_t)gamma8_exact(g8_base, thr_base, v[2]);
 }
 
 __device__ __forceinline__ void issue_tile(const SpecParams &p, const CUtensorMap *tmap, uint32_t raw_stage, uint32_t bar,
@@ -348,12 +396,13 @@ __device__ __forceinline__ uint32_t cheap_task(const SpecParams &p, uint32_t g8_
   words[0] = __byte_perm(__byte_perm(r0, g0, 0x0073), __byte_perm(b0, r1, 0x0073), 0x5410);
   words[1] = __byte_perm(__byte_perm(g1, b1, 0x0073), __byte_perm(r2, g2, 0x0073), 0x5410);
   words[2] = __byte_perm(__byte_perm(b2, r3, 0x0073), __byte_perm(g3, b3, 0x0073), 0x5410);
-  const uint32_t M = 0x00ffffffu;
-  const uint32_t d0 = min(min(r0 & M, g0 & M), b0 & M), d1 = min(min(r1 & M, g1 & M), b1 & M);
-  const uint32_t d2 = min(min(r2 & M, g2 & M), b2 & M), d3 = min(min(r3 & M, g3 & M), b3 & M);
+  // distance certificates: the product drops the byte field and weighs the channel's distance by deltaF_max / deltaF_c
+  const uint32_t wr = p.wmul[0], wg = p.wmul[1], wb = p.wmul[2], T = p.amb_t;
+  const uint32_t d0 = min(min(r0 * wr, g0 * wg), b0 * wb), d1 = min(min(r1 * wr, g1 * wg), b1 * wb);
+  const uint32_t d2 = min(min(r2 * wr, g2 * wg), b2 * wb), d3 = min(min(r3 * wr, g3 * wg), b3 * wb);
   uint32_t flags = 0;
-  if (min(min(d0, d1), min(d2, d3)) <= p.amb2) {
-    flags = (d0 <= p.amb2 ? 1u : 0u) | (d1 <= p.amb2 ? 2u : 0u) | (d2 <= p.amb2 ? 4u : 0u) | (d3 <= p.amb2 ? 8u : 0u);
+  if (min(min(d0, d1), min(d2, d3)) <= T) {
+    flags = (d0 <= T ? 1u : 0u) | (d1 <= T ? 2u : 0u) | (d2 <= T ? 4u : 0u) | (d3 <= T ? 8u : 0u);
   }
   if (fminf(y02, y13) < p.y_min)  // outside the certified domain (far below black): that pixel pair exactly
     flags |= (y02 < p.y_min ? 5u : 0u) | (y13 < p.y_min ? 10u : 0u);
@@ -415,13 +464,16 @@ k_spec8(const __grid_constant__ SpecParams p, const __grid_constant__ CfaDev cfa
     for (int k = 0; k < 5; k++) sm.spl[i][k] = e[k];
   }
   const uint32_t phase = (uint32_t)cfa.pat[0] | ((uint32_t)cfa.pat[1] << 2) | ((uint32_t)cfa.pat[48] << 4) | ((uint32_t)cfa.pat[49] << 6);
+  const uint32_t thr_base = smem_u32(sm.thr);
+  for (int i = tid; i < 260; i += NT) sm.thr[i] = i < 255 ? __ldg(p.thr8 + i) : __int_as_float(0x7f800000);
+  for (int i = tid; i < (int)(sizeof(SpecParams) / 4); i += NT) reinterpret_cast<uint32_t *>(&sm.sp)[i] = reinterpret_cast<const uint32_t *>(&p)[i];
+  for (int i = tid; i < (int)(sizeof(ColorParams) / 4); i += NT) reinterpret_cast<uint32_t *>(&sm.cp)[i] = reinterpret_cast<const uint32_t *>(&P)[i];
 
   // gofloat (gofloat.rs:127) of the staged raw box into tile buffer `buf`, exactly as the reference rounds it (the
   // cheap pass and the reference then start from identical samples).  Even / odd columns go to separate planes.
   // Warps pull chunks from a counter, so whichever warps finish their pixels first convert the next tile.
   auto convert_tile = [&](int buf, int ctr) {
     constexpr int kGroups = kTileElems / 8;          // 8 samples per thread per chunk
-    constexpr int kChunks = (kGroups + 31) / 32;
     const F2 rc = splat(p.range_rc), nrange = splat(-p.range), sub_a = splat(p.sub_a), sub_b = splat(p.sub_b);
     const bool two_subs = p.sub_b != 0.0f;
     for (;;) {
@@ -466,15 +518,15 @@ k_spec8(const __grid_constant__ SpecParams p, const __grid_constant__ CfaDev cfa
   }
   mbar_wait(bar_tab, 0);
 
-  // queue the flagged pixels of a task (pix = index of its first pixel); a full queue recomputes right away — the
-  // cheap bytes are already stored by this very thread, so the exact ones land on top
-  auto push = [&](uint32_t flags, uint32_t pix) {
+  // queue the uncertified pixels of a task (entry = row << 16 | column of its first pixel); a full queue recomputes
+  // right away — the cheap bytes are already stored by this very thread, so the exact ones land on top
+  auto push = [&](uint32_t flags, uint32_t entry) {
     int pos = atoms_add(qn_addr, __popc(flags));
     while (flags) {
       const int j = __ffs(flags) - 1;
       flags &= flags - 1u;
-      if (pos < kQueueCap) sm.queue[pos] = pix + j;
-      else fixup_pixel_slow(p, P, sm.spl, phase, pix + j);
+      if (pos < kQueueCap) sm.queue[pos] = entry + j;
+      else fixup_entry(sm.sp, sm.cp, sm.spl, phase, g8_base, thr_base, entry + j);
       pos++;
     }
   };
@@ -513,7 +565,7 @@ k_spec8(const __grid_constant__ SpecParams p, const __grid_constant__ CfaDev cfa
       if (inner) {
         uint32_t *o4 = reinterpret_cast<uint32_t *>(p.out + (size_t)pix * 3);
         o4[0] = words[0]; o4[1] = words[1]; o4[2] = words[2];
-        if (flags) push(flags, pix);
+        if (flags && !(p.dbg & 2)) push(flags, ((uint32_t)(y - p.out_row0) << 16) | (uint32_t)(tx0 + 4 * lane));
       } else {
         const int x0 = tx0 + 4 * lane;
         const bool live = y < p.out_row1 && x0 < p.width;
@@ -533,7 +585,7 @@ k_spec8(const __grid_constant__ SpecParams p, const __grid_constant__ CfaDev cfa
           if (x0 < 1) flags |= 1u;
           if (x0 + 3 > p.width - 2) flags |= 0xfu & ~((1u << max(p.width - 1 - x0, 0)) - 1u);
           flags &= (1u << npx) - 1u;
-          if (flags) push(flags, pix);
+          if (flags) push(flags, ((uint32_t)(y - p.out_row0) << 16) | (uint32_t)x0);
         }
       }
     }
@@ -550,10 +602,14 @@ k_spec8(const __grid_constant__ SpecParams p, const __grid_constant__ CfaDev cfa
       next_tile(ntx, nty);
       issue_tile(p, &tmap, raw_addr, bar, ntx, nty);
     }
-    // fix-up queue: recompute when it is half full (dense: every thread takes entries)
+    // Uncertified pixels are recomputed exactly when the queue is nearly full and after the last tile, densely: every
+    // thread takes entries, all lanes busy.  What bounds this step is the number of scattered load / store
+    // instructions (each lane its own sector), which is why the exact path loads its taps as six words, reads its
+    // gamma thresholds from shared memory, and runs rarely.  The barrier above ordered every push before this read.
     const int qn = min(sm.qn, kQueueCap);
-    if (qn >= kFlushAt) {
-      for (int i = tid; i < qn; i += NT) fixup_pixel(p, P, sm.spl, phase, sm.queue[i]);
+    if (qn >= kQueueCap - 1024 || (!have_next && qn > 0)) {
+      if (!(p.dbg & 1))
+        for (int i = tid; i < qn; i += NT) fixup_entry(sm.sp, sm.cp, sm.spl, phase, g8_base, thr_base, sm.queue[i]);
       __syncthreads();
       if (tid == 0) {
         if (p.stats) atomicAdd(p.stats, (unsigned long long)sm.qn);
@@ -562,10 +618,6 @@ k_spec8(const __grid_constant__ SpecParams p, const __grid_constant__ CfaDev cfa
       __syncthreads();
     }
   }
-  // the last barrier of the loop ordered every push before this read
-  const int qn = min(sm.qn, kQueueCap);
-  for (int i = tid; i < qn; i += NT) fixup_pixel(p, P, sm.spl, phase, sm.queue[i]);
-  if (tid == 0 && p.stats && sm.qn) atomicAdd(p.stats, (unsigned long long)sm.qn);
 }
 
 // ---------------------------------------------------------------- probe: cheap vs exact linear values
@@ -620,7 +672,9 @@ __global__ void k_spec_probe(const __grid_constant__ SpecParams p, const __grid_
     if (fminf(y02, y13) < p.y_min) continue;  // outside the certified domain: the kernel recomputes these
     for (int j = 0; j < 4; j++) {
       float ex[3];
-      exact_bayer_linear(p, P, spl, phase, x0 + j, y, ex);
+      float tp[9];
+      taps_from_frame(p, x0 + j, y, tp);
+      exact_bayer_linear(p, P, spl, phase, x0 + j, y, tp, ex);
       for (int c = 0; c < 3; c++) ex[c] = fminf(fmaxf(ex[c], 0.0f), 1.0f);  // gamma.rs:21 clamps before the table
       const float *l = (j & 1) ? l13 : l02;
       const int h = j >> 1;
@@ -710,7 +764,7 @@ bool spec_supported(const FusedArgs &a, const CfaDev &cfa, const ColorParams &P)
   if (!a.use_tma || (a.crop_x % 8) != 0) return false;
   if ((reinterpret_cast<uintptr_t>(a.raw) & 15) || ((a.raw_pitch * sizeof(uint16_t)) & 15)) return false;
   if (a.width < 8 || a.height < 4) return false;
-  if ((unsigned long long)a.width * (a.out_row1 - a.out_row0) >= 0xffffffffull) return false;  // 32-bit queue entries
+  if (a.width >= 65536 || a.out_row1 - a.out_row0 >= 65536) return false;  // queue entries are row << 16 | column
   return true;
 }
 
@@ -731,8 +785,12 @@ cudaError_t launch_fused_spec8(cudaStream_t s, const FusedArgs &a, const CfaDev 
     p.sub_b = integral ? 0.0f : -a.black;
   }
   p.bias58 = 0x58000000u;
+  {
+    static const int dbg = getenv("IPB_SPEC_DBG") ? atoi(getenv("IPB_SPEC_DBG")) : 0;
+    p.dbg = dbg;
+  }
   p.lut_lab = a.lut_lab; p.lut_gamma = a.lut_gamma; p.cbrt_tab = a.cbrt_tab;
-  p.g8a = T.g8a; p.stab = T.stab; p.stats = T.stats;
+  p.g8a = T.g8a; p.stab = T.stab; p.thr8 = T.thr8; p.stats = T.stats;
   p.tiles_x = (p.width + kTW - 1) / kTW;
   p.tiles_y = (p.out_row1 - p.out_row0 + kTH - 1) / kTH;
   CUtensorMap tmap;
@@ -782,7 +840,7 @@ cudaError_t launch_spec_probe(cudaStream_t s, const FusedArgs &a, const CfaDev &
   }
   p.bias58 = 0x58000000u;
   p.lut_lab = a.lut_lab; p.lut_gamma = a.lut_gamma; p.cbrt_tab = a.cbrt_tab;
-  p.g8a = T.g8a; p.stab = T.stab; p.stats = T.stats;
+  p.g8a = T.g8a; p.stab = T.stab; p.thr8 = T.thr8; p.stats = T.stats;
   const size_t smem = kG8Offset + kSpecG8Entries * 4;
   cudaError_t e = cudaFuncSetAttribute(k_spec_probe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;

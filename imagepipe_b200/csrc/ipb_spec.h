@@ -32,6 +32,7 @@ struct SpecParams {
   // ---- cheap path: tables
   const uint32_t *g8a;   // kSpecG8Entries words: (byte << 24) + (2^24 - thrF) + deltaF - 0x3F800000
   const float2 *stab;    // kSpecSTabEntries {intercept, slope}
+  const float *thr8;     // the 255 thresholds of output8bit(apply_srgb_gamma(v)), ascending (exact path)
   unsigned long long *stats;  // optional: [0] pixels recomputed, [1] probe max |diff| bits, [2] probe count, [3] probe sum
   // ---- cheap path: constants (scalars: packed instructions take them as broadcast operands)
   float sub_a, sub_b;    // level mapping: -(2^23 + black), 0 for an integral black level, else -2^23, -black
@@ -41,15 +42,24 @@ struct SpecParams {
   float s_scale, s_off;  // u = sat(fy * s_scale + s_off), key = floor(u * (N + 2))
   float y_min;           // kSpecYMin
   uint32_t bias58;       // 0x58000000 = (0x4B000000 << 3) mod 2^32, as a run-time value (keeps the table address one LEA)
-  uint32_t amb2;         // 2 * deltaF: a channel with (sum & 0xffffff) <= amb2 is within deltaF of a threshold
+  // per-channel certificate: u_c = v * (1 - 2^-13) + one[c] carries F + deltaF_c, so the low 24 bits of (entry + bits(u_c))
+  // are r = F - thrF + deltaF_c, and the channel is within deltaF_c of a threshold iff r <= 2 * deltaF_c.  The three
+  // tests share one comparison: r * wmul[c] <= amb_t with wmul[c] = 256 * floor(4 * deltaF_max / deltaF_c) (the factor
+  // 256 shifts the byte field out of the 32-bit product) and amb_t = 256 * 4 * 2 * deltaF_max.
+  float one[3];
+  uint32_t wmul[3];
+  uint32_t amb_t;
+  int dbg;               // timing experiments only (IPB_SPEC_DBG): 1 = skip the recomputation, 2 = skip the queueing too
 };
 
 struct SpecTables {
   SpecParams consts;     // the constant part of SpecParams
   const uint32_t *g8a;
   const float2 *stab;
+  const float *thr8;
   unsigned long long *stats;
-  float delta;           // the certified bound on |cheap - exact| in linear units this table set was built for
+  float delta;           // the certified bound on |cheap - exact| in linear units (largest channel) of this table set
+  float delta_ch[3];     // per output channel
 };
 
 // host: tables, folded constants and the certified bound for one parameter set (ipb_spec_host.cu).  `thresholds` are the
@@ -57,7 +67,7 @@ struct SpecTables {
 // cannot take the speculative path (the caller launches k_fused_full instead).
 bool spec_build(const ColorParams &P, float black, float range, float mufu_rel_err, float delta_override,
                 const std::vector<float> &thresholds, std::vector<uint32_t> *g8a, std::vector<float2> *stab,
-                SpecParams *consts, float *delta_out);
+                SpecParams *consts, float delta_out[4]);
 bool spec_supported(const FusedArgs &a, const CfaDev &cfa, const ColorParams &P);
 cudaError_t launch_fused_spec8(cudaStream_t s, const FusedArgs &a, const CfaDev &cfa, const ColorParams &P,
                                const SpecTables &T, int sm_count, int threads);

@@ -63,7 +63,7 @@ double lab_gap(double v) {
 
 bool spec_build(const ColorParams &P, float black, float range, float mufu_rel_err, float delta_override,
                 const std::vector<float> &thresholds, std::vector<uint32_t> *g8a, std::vector<float2> *stab,
-                SpecParams *consts, float *delta_out) {
+                SpecParams *consts, float delta_out[4]) {
   if (thresholds.size() != 255 || P.use_e || P.linear) return false;
   SpecParams c;
   memset(&c, 0, sizeof(c));
@@ -191,7 +191,7 @@ bool spec_build(const ColorParams &P, float black, float range, float mufu_rel_e
     for (int k = 0; k <= 27; k++) axis[j].push_back(cmax * (0.1 + 0.9 * k / 27.0));          // 0.1*cmax .. cmax
   }
   const double hS = h * 0.5;
-  double delta = 0.0, worst_ex[3] = {0, 0, 0};
+  double delta = 0.0, dch[3] = {0, 0, 0}, worst_ex[3] = {0, 0, 0};
   for (double ca : axis[0])
     for (double cb : axis[1])
       for (double cc : axis[2]) {
@@ -244,22 +244,29 @@ bool spec_build(const ColorParams &P, float black, float range, float mufu_rel_e
             fprintf(stderr, "  ch %d c (%.4f %.4f %.4f) x (%.4f %.4f %.4f) ef %.1f %.1f %.1f u e_sE %.1f e_stab %.1f ls %.3f spl %.3f D %.3f EX %.1f %.1f %.1f u X' %.3f %.3f %.3f d %.3g\n",
                     ch, ca, cb, cc, x[0], x[1], x[2], ef[0] / U, ef[1] / U, ef[2] / U, e_sE / U, e_stab / U, ls, spl, D, EXp[0] / U, EXp[1] / U, EXp[2] / U, Xp[0], Xp[1], Xp[2], d);
           delta = std::max(delta, d);
+          dch[ch] = std::max(dch[ch], d);
         }
       }
   delta *= 1.25;  // variation between grid points, second-order terms
+  for (int ch = 0; ch < 3; ch++) dch[ch] *= 1.25;
   if (getenv("IPB_SPEC_DEBUG"))
     fprintf(stderr, "spec_build: x in [%.3f,%.3f] [%.3f,%.3f] [%.3f,%.3f] chord %.3g e_stab %.3g u  worst EX %.3g %.3g %.3g  mufu %.3g  delta %.4g\n",
             xlo[0], xhi[0], xlo[1], xhi[1], xlo[2], xhi[2], chord, e_stab / U, worst_ex[0], worst_ex[1], worst_ex[2], mufu, delta);
 
-  if (delta_override > 0.0f) delta = (double)delta_override;
-  if (!(delta > 0.0) || delta > 8.0e-5) return false;  // thresholds are >= 3.0e-4 apart: one per extended segment
+  if (delta_override > 0.0f) delta = dch[0] = dch[1] = dch[2] = (double)delta_override;
+  if (!(delta > 0.0) || delta > 8.0e-5) return false;  // thresholds are >= 3.0e-4 (2536 F units) apart: at most one per
+                                                        // extended segment of 1024 + 2 * (2 * deltaF + 4) units
 
   // ------------------------------------------------------------ gamma table in fixed point
   // F = round(v * kSpecFScale) is what the kernel reads from the bit pattern of 1 + v * (1 - 2^-13); a reference
   // threshold T sits at tau = T * kSpecFScale.  With |v_cheap - v_ref| <= delta and half a unit of rounding in F,
   // |F - tau| > deltaF = ceil(delta * 2^23) + 2 on every threshold means both values lie on the same side of all of them.
-  const uint32_t dF = (uint32_t)ceil(delta * 8388608.0) + 2u;
-  const int64_t margin = (int64_t)dF + 4;  // + the segment index is floor(v*8191), F's may be one segment over
+  uint32_t dFc[3], dF = 0;
+  for (int ch = 0; ch < 3; ch++) {
+    dFc[ch] = (uint32_t)ceil(dch[ch] * 8388608.0) + 2u;
+    dF = std::max(dF, dFc[ch]);
+  }
+  const int64_t margin = (int64_t)dF + 4;  // thresholds within deltaF of an F of the segment; the index may be one over
   g8a->assign(kSpecG8Entries, 0u);
   std::vector<double> tau(255);
   for (int i = 0; i < 255; i++) tau[i] = (double)thresholds[i] * kSpecFScale;
@@ -270,15 +277,23 @@ bool spec_build(const ColorParams &P, float black, float range, float mufu_rel_e
       if (tau[i] < (double)lo) below++;
       else if (tau[i] <= (double)hi) { if (found >= 0) return false; found = i; }
     }
+    // entry + bits(u_c) = (base << 24) + 2^24 + (F + deltaF_c - thrF): the byte is base below the threshold and base + 1
+    // from it on.  A segment without a threshold pretends to one 2^19 units below its start (byte = base + 1 throughout):
+    // its distance field stays near 2^19, which the weighted comparison (products below 2^32) never takes for "close".
     uint32_t base, thrF;
-    if (found >= 0) { base = (uint32_t)found; thrF = (uint32_t)ceil(tau[found]); }  // bytes: found below it, found + 1 from it on
-    else { base = (uint32_t)below; thrF = (uint32_t)k * 1024u + 8388608u; }          // no threshold anywhere near
-    (*g8a)[k] = (base << 24) + (16777216u - thrF) + dF - 0x3F800000u;
+    if (found >= 0) { base = (uint32_t)found; thrF = (uint32_t)ceil(tau[found]); }
+    else { base = ((uint32_t)below - 1u) & 0xffu; thrF = (uint32_t)k * 1024u - 524288u; }
+    (*g8a)[k] = (base << 24) + (16777216u - thrF) - 0x3F800000u;
   }
-  c.amb2 = 2u * dF;
+  for (int ch = 0; ch < 3; ch++) {
+    c.one[ch] = 1.0f + (float)dFc[ch] * 1.1920928955078125e-07f;  // exact: deltaF < 2^10
+    c.wmul[ch] = 256u * ((4u * dF) / dFc[ch]);
+  }
+  c.amb_t = 256u * 4u * 2u * dF;
   c.y_min = kSpecYMin;
   *consts = c;
-  *delta_out = (float)delta;
+  delta_out[0] = (float)delta;
+  for (int ch = 0; ch < 3; ch++) delta_out[1 + ch] = (float)dch[ch];
   return true;
 }
 

@@ -266,10 +266,11 @@ int ipb_ctx_spec_stats(ipb_ctx *ctx, unsigned long long out[4], int reset);
  * parity suite asserts max_dev <= delta on every frame it runs.  IPB_ERR_UNSUPPORTED when the pipeline would not take
  * the speculative path. */
 int ipb_pipeline_spec_probe(ipb_pipeline *p, float *max_dev, double *mean_dev, float *delta);
-/* The certified bound itself, without a context or a GPU (pure host arithmetic, ipb_spec_host.cu): *delta for the colour
+/* The certified bound itself, without a context or a GPU (pure host arithmetic, ipb_spec_host.cu): delta[0] = the largest,
+ * delta[1..3] = per output channel (R, G, B), for the colour
  * parameters of `ops`, given the relative error of the XU-pipe cube root (ipb_ctx_spec_stats out[3] on a GPU box; the
  * hardware documentation's 2^-22 otherwise).  IPB_ERR_UNSUPPORTED when these parameters would run on the exact kernel. */
-int ipb_spec_bound(const ipb_ops *ops, float mufu_rel_err, float *delta);
+int ipb_spec_bound(const ipb_ops *ops, float mufu_rel_err, float delta[4]);
 /* Host-resident source and/or destination: output_8bit / output_16bit cut the frame into bands of about `megabytes`
  * of PCIe traffic and overlap the H2D copy, the kernel and the D2H copy of neighbouring bands on three streams
  * (default 16: lowest latency of a single call).  0 = one band: whole-frame copies, which use the PCIe link better

@@ -27,6 +27,22 @@ def build(force=False):
     return _LIB_PATH
 
 
+NATIVE_FLAGS = "-O3 -march=native -ffp-contract=off -fno-fast-math -fopenmp"
+
+
+def use_native():
+    """bench.py's CPU-baseline legs only: rebuild the same sources with BASELINE.md's flags (-O3 -march=native) on THIS
+    machine and route lib() to that build.  Returns the flags actually in use (the portable build's when gcc is absent)."""
+    global _LIB_PATH, _lib
+    path = os.path.join(_HERE, "liboracle_native.so")
+    try:
+        subprocess.run(["make", "-C", _HERE, "-B", "liboracle_native.so"], check=True, capture_output=True)
+    except Exception:
+        return "-O2 -march=x86-64-v2 -ffp-contract=off -fopenmp (portable checker build; native rebuild failed)"
+    _LIB_PATH, _lib = path, None
+    return NATIVE_FLAGS
+
+
 class Buffer(C.Structure):
     _fields_ = [("width", C.c_size_t), ("height", C.c_size_t), ("colors", C.c_size_t),
                 ("monochrome", C.c_int), ("data", C.POINTER(C.c_float))]
