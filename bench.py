@@ -40,7 +40,7 @@ CFA = "RGGB"
 SETTINGS = {}          # PipelineSettings overrides of the workload (c4: maxwidth / maxheight)
 OUT_W, OUT_H = W, H    # size of the result
 WORKLOAD_NAME = "C2: 6000x4000 RGGB Bayer -> 8-bit sRGB, fused demosaic->gamma kernel"
-KERNEL_NAME, TRAFFIC_KEY = "k_fused_full<u8>", "k_fused_full<u8> C2 6000x4000"
+KERNEL_NAME, TRAFFIC_KEY = "k_spec8<512> (speculative 8-bit kernel)", "k_spec8 C2 6000x4000"
 NSETS = 8
 FRAMES_PER_STEP = 32
 E2E_THREADS = 2
@@ -68,6 +68,13 @@ def select_workload(name):
 METRIC = "megapixels/sec raw->sRGB full pipe"
 
 
+def workload_config(world, frames_per_step):
+    """config of the JSON line — the same dict on both arms (the reference arm times bounded samples of this workload)."""
+    return {"workload": WORKLOAD_NAME, "frames_per_step": frames_per_step, "buffer_sets": NSETS,
+            "l2": f"inputs larger than L2: {NSETS} rotating sets x {(W * H * 2 + OUT_W * OUT_H * 3) / 1e6:.0f} MB",
+            "parallelism": f"frames round-robin, {world} replica(s), no collective"}
+
+
 def workload_params():
     import common
     return common.raw_params(cfa=CFA)
@@ -79,6 +86,16 @@ def measured_traffic(key):
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
             e = json.load(f)[key]
         return e["dram_read_bytes"] + e["dram_write_bytes"]
+    except Exception:
+        return None
+
+
+def measured_issue(key):
+    """{warp_inst_per_px, issue_active} of the dominant kernel from the same committed capture, or None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            e = json.load(f)[key]
+        return {"warp_inst_per_px": e["warp_inst_per_px"], "issue_active": e["issue_active"], "source": e.get("capture")}
     except Exception:
         return None
 
@@ -143,15 +160,22 @@ def pinned_array(ip, nbytes, dtype, shape):
     return np.frombuffer(buf, dtype=dtype).reshape(shape), p
 
 
-def cpu_reference_leg(steps, warmup, frames_note=True):
-    """Times the oracle's op-by-op CPU pipeline (same pass structure as the reference) on all host cores."""
+def cpu_reference_leg(steps, warmup):
+    """Times the oracle's op-by-op CPU pipeline (same pass structure as the reference: one pass and one allocation per
+    op, clones before basecurve / from_lab / gamma, serial pack loop) on all host cores, one frame of the workload per
+    step, built on this machine with BASELINE.md's flags (-O3 -march=native -ffp-contract=off)."""
     import common
     import oracle
     oracle.build()
+    data = common.synth_cfa(W, H)
+    small = common.synth_cfa(640, 360)
+    want_small = oracle.pipeline_output_8bit(oracle.make_pipeline(small, "raw", workload_params(), SETTINGS or None))
+    flags = oracle.use_native()
     L = oracle.lib()
     L.orc_set_threads(0)
     cores = L.orc_get_threads()
-    data = common.synth_cfa(W, H)
+    same = bool(np.array_equal(want_small, oracle.pipeline_output_8bit(
+        oracle.make_pipeline(small, "raw", workload_params(), SETTINGS or None))))
     p = oracle.make_pipeline(data, "raw", workload_params(), SETTINGS or None)
     for _ in range(warmup):
         oracle.pipeline_output_8bit(p)
@@ -162,29 +186,36 @@ def cpu_reference_leg(steps, warmup, frames_note=True):
         times.append(time.perf_counter() - t0)
     per = float(np.mean(times))
     return {"value": MP / per, "unit": "MP/s", "cores": int(cores), "kind": "port",
-            "sample": f"{steps} x one {W}x{H} frame of the workload, output_8bit, OpenMP row-parallel C port of the reference "
-                      f"CPU path (Rust toolchain absent)", "ms_per_frame": per * 1e3}
+            "sample": f"{steps} steps x one {W}x{H} frame of the workload through output_8bit; C port of the reference CPU "
+                      f"path (Rust toolchain absent), OpenMP over rows on {int(cores)} threads, gcc {flags}; "
+                      f"same bytes as the checker build on a 640x360 frame: {same}",
+            "ms_per_frame": per * 1e3, "flags": flags}
 
 
 def run_reference(args, rank, world):
+    """--impl reference: the reference's CPU path (its C port) on this box's host cores, one frame of the workload per
+    step, the driver's --steps / --warmup, the same metric and config as our arm.  Rank 0 alone works."""
     if rank != 0:
         return
-    steps, warmup = max(1, min(args.steps, 12)), max(1, min(args.warmup, 2))
+    steps, warmup = max(1, args.steps), max(0, args.warmup)
     cb = cpu_reference_leg(steps, warmup)
     line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "MP/s", "n_gpus": args.gpus,
             "steps": steps, "warmup": warmup, "ms_per_step": cb["ms_per_frame"], "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD_NAME + " — one frame per step on host cores", "frames_per_step": 1},
+            "config": workload_config(max(world, args.gpus), args.frames_per_step),
             "cpu_baseline": cb,
             "e2e": {"value": cb["value"], "unit": "MP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
 
-def run_c5(args, ip, common, torch, dist, ctx, stream, barrier, rank, world, local_rank, params, K, Wm, F):
-    """BASELINE config 5: one 11648x8736 RGGB frame cut into row stripes, one per rank; every frame of a step does the
-    halo exchange (NCCL send/recv of the stencil rows between neighbours) and one fused launch per rank."""
+def strong_leg(args, ip, common, torch, dist, ctx, stream, barrier, rank, world, local_rank, params, K, Wm):
+    """BASELINE config 5 (strong scaling): one 11648x8736 RGGB frame cut into row stripes, one per rank.  The stencil
+    rows travel through the C ABI's halo exchange (ipb_halo_exchange: grouped ncclSend / ncclRecv between stripe
+    neighbours on the compute stream; torch.distributed only carries the 128-byte NCCL id to the ranks), then every
+    rank runs one fused launch on its stripe.  Returns the dict of the JSON line's "strong" key (rank 0) — with
+    `parity`: every rank's stripe equals, byte for byte, the same rows of a single-launch run of the whole frame."""
     from imagepipe_b200 import _capi
-    from imagepipe_b200.sharded import DevicePtr, exchange_halos, plan_stripes, run_stripe_8bit
+    from imagepipe_b200.sharded import Comm, DevicePtr, exchange_halos_nccl, halo_plan, plan_stripes, run_stripe_8bit
     W5, H5 = 11648, 8736
     mp5 = W5 * H5 / 1e6
     dummy = ip.DeviceArray(64, ctx)
@@ -195,6 +226,11 @@ def run_c5(args, ip, common, torch, dist, ctx, stream, barrier, rank, world, loc
     rows_out = me.out_row1 - me.out_row0
     set_bytes = (me.src_row1 - me.src_row0) * W5 * 2 + rows_out * W5 * 3
     nsets = max(2, -(-600_000_000 // set_bytes))  # rotating working set of >= 600 MB per GPU (L2 is 126 MB)
+    comm = None
+    if world > 1:
+        box = [Comm.unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        comm = Comm(box[0], rank, world, local_rank, stream.cuda_stream)
     bufs, outs = [], []
     with torch.cuda.stream(stream):
         for i in range(nsets):
@@ -203,26 +239,27 @@ def run_c5(args, ip, common, torch, dist, ctx, stream, barrier, rank, world, loc
             ip.lib().ipb_synth_cfa_u16(ctx.handle, common.SEED + i, W5, me.own_row0, me.own_row1 - me.own_row0, own.data_ptr())
             bufs.append(b)
             outs.append(torch.empty((rows_out, W5, 3), dtype=torch.uint8, device="cuda"))
+    ptrs = [b.data_ptr() for b in bufs]
+    hp = halo_plan(lays, rank, W5 * 2)
+    halo_bytes = hp.send_up_bytes + hp.send_down_bytes + hp.recv_up_bytes + hp.recv_down_bytes
 
     # A step is F = nsets frames, each in its own buffer set.  Their halo rows (one raw row per neighbour and frame)
-    # travel in one batched NCCL send/recv group at the head of the step, then every frame is one fused launch: the
-    # exchange latency (tens of microseconds, against ~0.15 ms of compute per stripe at 8 GPUs) is paid once per step.
-    # (Measured and dropped: exchanging on a second stream while the previous frame's kernel runs — the NCCL kernel
-    # holds an SM while it waits for its peer, the persistent kernel's 148th CTA starts late, and the step gets slower.)
+    # travel in one NCCL group at the head of the step, then every frame is one fused launch: the exchange latency
+    # (tens of microseconds, against < 0.1 ms of compute per stripe at 8 GPUs) is paid once per step.
     F = nsets
 
     def step():
-        if world > 1:
-            exchange_halos(bufs, lays, rank)
+        if comm is not None:
+            exchange_halos_nccl(comm, ptrs, lays, W5 * 2)
         for j in range(F):
-            run_stripe_8bit(p, bufs[j].data_ptr(), me, DevicePtr(outs[j].data_ptr(), outs[j].numel()))
+            run_stripe_8bit(p, ptrs[j], me, DevicePtr(outs[j].data_ptr(), outs[j].numel()))
 
     with torch.cuda.stream(stream):
         for _ in range(Wm):
             step()
     barrier()
-    # One step (F frames: exchange + fused launch each) is captured into a CUDA graph and replayed: at 8 GPUs a stripe
-    # takes ~0.15 ms and the Python / NCCL-group host path per frame (~0.2 ms) would otherwise be the bottleneck.
+    # One step is captured into a CUDA graph and replayed: at 8 GPUs a stripe takes < 0.1 ms and the host path per
+    # frame (Python + ctypes, ~0.2 ms) would otherwise be the bottleneck.
     graph, mode = None, "eager"
     if not args.no_graph:
         try:
@@ -233,8 +270,8 @@ def run_c5(args, ip, common, torch, dist, ctx, stream, barrier, rank, world, loc
         except Exception as e:  # noqa: BLE001
             print(f"bench.py: graph capture failed on rank {rank} ({e}); running eagerly", file=sys.stderr)
             torch.cuda.synchronize()
-    modes = [None] * world
     if world > 1:
+        modes = [None] * world
         dist.all_gather_object(modes, mode)
         if any(m != modes[0] for m in modes) or modes[0] == "eager":
             graph, mode = None, "eager"   # all ranks must agree, or the exchange would not pair up
@@ -248,8 +285,6 @@ def run_c5(args, ip, common, torch, dist, ctx, stream, barrier, rank, world, loc
     with torch.cuda.stream(stream):
         run_step()
     barrier()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
     with torch.cuda.stream(stream):
         ev[0].record(stream)
@@ -257,57 +292,93 @@ def run_c5(args, ip, common, torch, dist, ctx, stream, barrier, rank, world, loc
             run_step()
         ev[1].record(stream)
     barrier()
-    clocks = sampler.stop()
-    launches = K * F   # one fused launch per frame (replayed from the graph when mode says so)
     t = torch.tensor([ev[0].elapsed_time(ev[1])], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     total_ms = float(t.item())
     value = K * F * mp5 / (total_ms / 1e3)
 
+    # parity: the whole frame of buffer set 0 in one launch on this GPU, against this rank's stripe of the sharded run
+    with torch.cuda.stream(stream):
+        full = ip.synth_cfa_u16(common.SEED, W5, 0, H5, ctx=ctx)
+        pf = ip.Pipeline.new_from_source(ip.ImageSource.Raw(full, width=W5, height=H5, cpp=1), ctx=ctx)
+        common.fill_ipb_ops(pf.ops, params)
+        ref = torch.empty((H5, W5, 3), dtype=torch.uint8, device="cuda")
+        pf.output_8bit(dst=DevicePtr(ref.data_ptr(), ref.numel()))
+        ok = int(torch.equal(ref[me.out_row0:me.out_row1], outs[0])) if rows_out else 1
+    torch.cuda.synchronize()
+    okt = torch.tensor([int(ok)], dtype=torch.int32, device="cuda")
+    if world > 1:
+        dist.all_reduce(okt, op=dist.ReduceOp.MIN)
+    del ref, full
+
     # e2e: every rank's source rows (halo included: the host holds the whole frame) in pinned host memory, its output
     # stripe back to pinned host memory, through the banded H2D / kernel / D2H path
     src_rows = me.src_row1 - me.src_row0
     host_in, _hin = pinned_array(ip, src_rows * W5 * 2, np.uint16, (src_rows, W5))
     host_out, _hout = pinned_array(ip, rows_out * W5 * 3, np.uint8, (rows_out, W5, 3))
+    with torch.cuda.stream(stream):
+        if comm is not None:
+            exchange_halos_nccl(comm, ptrs[:1], lays, W5 * 2)
+    torch.cuda.synchronize()
     host_in[:] = bufs[0].cpu().numpy().view(np.uint16)
-    e2e_steps, e2e_frames = 3, 2
+    e2e_calls = 6
     for _ in range(2):
         run_stripe_8bit(p, host_in, me, host_out)
     barrier()
     t0 = time.perf_counter()
-    for _ in range(e2e_steps * e2e_frames):
+    for _ in range(e2e_calls):
         run_stripe_8bit(p, host_in, me, host_out)
     torch.cuda.synchronize()
     te = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_value = e2e_steps * e2e_frames * mp5 / float(te.item())
+    e2e_value = e2e_calls * mp5 / float(te.item())
     same = bool(np.array_equal(host_out, outs[0].cpu().numpy()))
+    if comm is not None:
+        comm.close()
+    launch_ms = total_ms / (K * F)
+    return {
+        "workload": "C5: 11648x8736 RGGB Bayer -> 8-bit sRGB, one frame cut into row stripes (one per GPU), halo rows "
+                    "by ipb_halo_exchange (NCCL send/recv), one fused launch per stripe",
+        "value": value, "unit": "MP/s", "scaling": "strong", "steps": K, "frames_per_step": F,
+        "ms_per_step": total_ms / K, "ms_per_frame": launch_ms, "stripe_rows": rows_out,
+        "halo_rows": (me.own_row0 - me.src_row0) + (me.src_row1 - me.own_row1), "halo_bytes": int(halo_bytes),
+        "launch": mode, "nccl": Comm.nccl_version() if world > 1 else None,
+        "buffer_sets": nsets, "set_mb": set_bytes / 1e6,
+        "achieved_gbs": ALGO_BYTES_PER_PX * rows_out * W5 / (launch_ms / 1e3) / 1e9,
+        "e2e": {"value": e2e_value, "unit": "MP/s", "h2d_bytes_per_frame": src_rows * W5 * 2,
+                "d2h_bytes_per_frame": rows_out * W5 * 3, "frames_timed": e2e_calls, "matches_device_path": same,
+                "note": "bytes are per rank; every rank copies its own stripe"},
+        "parity": bool(int(okt.item()) == 1),
+        "parity_what": "each rank's stripe == the same rows of a single-launch run of the whole frame on that rank's GPU",
+    }
+
+
+def run_c5(args, ip, common, torch, dist, ctx, stream, barrier, rank, world, local_rank, params, K, Wm, F):
+    """--workload c5: the strong-scaling leg as the line's headline."""
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    st = strong_leg(args, ip, common, torch, dist, ctx, stream, barrier, rank, world, local_rank, params, K, Wm)
+    clocks = sampler.stop()
     if rank == 0:
         peak, peak_kind = measured_peak()
-        launch_ms = total_ms / (K * F)
-        achieved = ALGO_BYTES_PER_PX * rows_out * W5 / (launch_ms / 1e3) / 1e9
         line = {
-            "metric": METRIC, "value": value, "unit": "MP/s", "n_gpus": world, "steps": K, "warmup": Wm,
-            "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "metric": METRIC, "value": st["value"], "unit": "MP/s", "n_gpus": world, "steps": K, "warmup": Wm,
+            "ms_per_step": st["ms_per_step"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "C5: 11648x8736 RGGB Bayer -> 8-bit sRGB, row stripes + NCCL halo exchange",
-                       "frames_per_step": F, "buffer_sets": nsets, "stripe_rows": rows_out,
-                       "halo_rows": (me.own_row0 - me.src_row0) + (me.src_row1 - me.own_row1),
-                       "l2": f"inputs larger than L2: {nsets} rotating sets x {set_bytes / 1e6:.0f} MB per GPU",
-                       "launch": mode,
-                                      "parallelism": f"{world} row stripe(s); the stencil rows of a step's frames go to the neighbours in one "
-                                      "batched NCCL send/recv group"},
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "kernel": "k_fused_full<u8> (one stripe, exchange included in the time)",
-                         "kernel_ms": launch_ms, "peak_kind": peak_kind,
-                         "algorithmic_bytes_per_launch": ALGO_BYTES_PER_PX * rows_out * W5},
-            "e2e": {"value": e2e_value, "unit": "MP/s", "h2d_bytes_per_step": e2e_frames * src_rows * W5 * 2,
-                    "d2h_bytes_per_step": e2e_frames * rows_out * W5 * 3, "steps": e2e_steps,
-                    "frames_per_step": e2e_frames, "matches_device_path": same,
-                    "note": "bytes are per rank; every rank copies its own stripe"},
-            "gpu_launches": int(launches), "clocks": clocks,
+            "config": {"workload": st["workload"], "frames_per_step": st["frames_per_step"], "buffer_sets": st["buffer_sets"],
+                       "stripe_rows": st["stripe_rows"], "halo_rows": st["halo_rows"],
+                       "l2": f"inputs larger than L2: {st['buffer_sets']} rotating sets x {st['set_mb']:.0f} MB per GPU",
+                       "launch": st["launch"], "parallelism": f"{world} row stripe(s)"},
+            "roofline": {"bound": "hbm", "achieved": st["achieved_gbs"], "peak": peak, "unit": "GB/s",
+                         "frac": st["achieved_gbs"] / peak, "traffic": None,
+                         "kernel": "k_spec8 (one stripe, exchange included in the time)", "kernel_ms": st["ms_per_frame"],
+                         "peak_kind": peak_kind,
+                         "algorithmic_bytes_per_launch": ALGO_BYTES_PER_PX * st["stripe_rows"] * 11648},
+            "e2e": {"value": st["e2e"]["value"], "unit": "MP/s", "h2d_bytes_per_step": st["e2e"]["h2d_bytes_per_frame"],
+                    "d2h_bytes_per_step": st["e2e"]["d2h_bytes_per_frame"], "matches_device_path": st["e2e"]["matches_device_path"]},
+            "gpu_launches": int(K * st["frames_per_step"]), "clocks": clocks, "parity": st["parity"],
         }
         print(json.dumps(line), flush=True)
 
@@ -320,6 +391,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--frames-per-step", type=int, default=None)
+    ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling (C5 stripes) leg of the default line")
     ap.add_argument("--no-graph", action="store_true", help="c5: launch every frame from Python instead of replaying a CUDA graph")
     ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c4", "c5"],
                     help="c2 (default, the contract's line): 24 MP frames, replicas; c3: 45 MP X-Trans frames; c4: 24 MP frames "
@@ -386,6 +458,7 @@ def main():
     sampler = ClockSampler(local_rank)
     sampler.start()
     launches0 = ctx.launch_count
+    ctx.spec_stats(reset=True)
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(K + 1)]
     with torch.cuda.stream(stream):
         ev[0].record(stream)
@@ -395,6 +468,9 @@ def main():
     barrier()
     clocks = sampler.stop()
     launches = ctx.launch_count - launches0
+    st = ctx.spec_stats()
+    spec_stats = {"recomputed_fraction": st["fixups"] / max(1, launches) / (W * H), "certified_delta": st["delta"],
+                  "xu_cbrt_rel_err": st["mufu_err"]} if args.workload == "c2" else None
     total_ms = ev[0].elapsed_time(ev[K])
     step_ms = [ev[k].elapsed_time(ev[k + 1]) for k in range(K)]
     t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
@@ -456,6 +532,13 @@ def main():
     # result check on the last e2e frame: the device-resident path produced the same bytes
     same = all(bool(np.array_equal(w[3], outs[0].to_numpy(np.uint8, (OUT_H, OUT_W, 3)))) for w in workers)
 
+    # ---- strong scaling on the same record: BASELINE config 5, one 101.8 MP frame over the N GPUs (every N, N = 1 too)
+    strong = None
+    if args.workload == "c2" and not args.no_strong:
+        del workers
+        strong = strong_leg(args, ip, common, torch, dist, ctx, stream, barrier, rank, world, local_rank, params,
+                            max(5, min(K, 20)), 3)
+
     if rank == 0:
         peak, peak_kind = measured_peak()
         kernel_ms = float(np.mean(step_ms)) / F  # one fused launch per frame, nothing else in the step
@@ -464,14 +547,12 @@ def main():
             "metric": METRIC, "value": value, "unit": "MP/s", "n_gpus": world, "steps": K, "warmup": Wm,
             "ms_per_step": total_ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD_NAME,
-                       "frames_per_step": F, "buffer_sets": NSETS,
-                       "l2": f"inputs larger than L2: {NSETS} rotating sets x {(W * H * 2 + OUT_W * OUT_H * 3) / 1e6:.0f} MB",
-                       "parallelism": f"frames round-robin, {world} replica(s), no collective"},
+            "config": workload_config(world, F),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": measured_traffic(TRAFFIC_KEY), "kernel": KERNEL_NAME,
                          "kernel_ms": kernel_ms, "peak_kind": peak_kind,
-                         "algorithmic_bytes_per_launch": ALGO_BYTES_PER_PX * W * H},
+                         "algorithmic_bytes_per_launch": ALGO_BYTES_PER_PX * W * H,
+                         "issue": measured_issue(TRAFFIC_KEY), "spec": spec_stats},
             "e2e": {"value": e2e_value, "unit": "MP/s", "h2d_bytes_per_step": e2e_frames * W * H * 2,
                     "d2h_bytes_per_step": e2e_frames * OUT_W * OUT_H * 3, "steps": e2e_steps, "frames_per_step": e2e_frames,
                     "host_threads": E2E_THREADS, "frames_timed": per_thread * E2E_THREADS,
@@ -479,6 +560,8 @@ def main():
             "gpu_launches": int(launches),
             "clocks": clocks,
         }
+        if strong is not None:
+            line["strong"] = strong
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_reference_leg(3, 1)
         print(json.dumps(line), flush=True)

@@ -73,6 +73,14 @@ class Stripe(C.Structure):
                 ("out_row1", C.c_size_t)]
 
 
+class Halo(C.Structure):
+    """ipb_halo: byte offsets / sizes of the rows exchanged with the stripe above (rank - 1) and below (rank + 1)."""
+    _fields_ = [(n, C.c_size_t) for n in ("send_up_off", "send_up_bytes", "recv_up_off", "recv_up_bytes",
+                                          "send_down_off", "send_down_bytes", "recv_down_off", "recv_down_bytes")]
+
+
+COMM_ID_BYTES = 128
+
 _lib = None
 
 
@@ -159,6 +167,14 @@ def lib():
         "ipb_pipeline_set_tma": (i, [vp, i]),
         "ipb_pipeline_set_band_mb": (i, [vp, i]),
         "ipb_pipeline_set_speculative": (i, [vp, i]),
+        "ipb_comm_unique_id": (i, [C.c_char_p]),
+        "ipb_comm_create": (i, [i, vp, C.c_char_p, i, i, C.POINTER(vp)]),
+        "ipb_comm_destroy": (None, [vp]),
+        "ipb_comm_rank": (i, [vp]),
+        "ipb_comm_size": (i, [vp]),
+        "ipb_comm_nccl_version": (i, [C.POINTER(i)]),
+        "ipb_comm_last_error": (C.c_char_p, [vp]),
+        "ipb_halo_exchange": (i, [vp, C.POINTER(vp), sz, C.POINTER(Halo)]),
         "ipb_ctx_set_spec": (i, [vp, C.c_float, i]),
         "ipb_spec_bound": (i, [vp, C.c_float, C.POINTER(C.c_float)]),
         "ipb_ctx_spec_stats": (i, [vp, C.POINTER(C.c_ulonglong), i]),

@@ -40,9 +40,10 @@ class StripeLayout:
         return self.own_row1, self.src_row1
 
 
-def partition_rows(nrows, world, multiple=32):
-    """Balanced split of output rows; interior boundaries on multiples of `multiple` (the fused kernel's tile height),
-    relaxed to smaller powers of two for short frames so that no stripe is empty while nrows >= world."""
+def partition_rows(nrows, world, multiple=2):
+    """Balanced split of output rows; interior boundaries on multiples of `multiple` (2: the Bayer period — the kernels
+    work in full-frame coordinates, so any boundary is correct; even ones keep a stripe's first row on the pattern's
+    first row), relaxed for short frames so that no stripe is empty while nrows >= world."""
     while multiple > 1 and nrows // world < multiple:
         multiple //= 2
     bounds = [0]
@@ -62,7 +63,7 @@ def stripe_plan(ops, settings, width, height, out_row0=0, out_row1=0):
     return s0.value, s1.value, ow.value, oh.value
 
 
-def plan_stripes(ops, settings, width, height, world, multiple=32):
+def plan_stripes(ops, settings, width, height, world, multiple=2):
     """One StripeLayout per rank.  Source-row ownership is cut in the middle of each overlap, so both neighbours
     receive about half of the shared rows; halos never reach past the adjacent rank (checked)."""
     _, _, ow, oh = stripe_plan(ops, settings, width, height)
@@ -90,6 +91,74 @@ def plan_stripes(ops, settings, width, height, world, multiple=32):
                              f"for a {height}-row frame")
         layouts.append(StripeLayout(k, r0, r1, s0, s1, own[k], own[k + 1], ow, oh))
     return layouts
+
+
+class Comm:
+    """ipb_comm: the NCCL communicator of the stripe ranks, created inside libipb200.so (which resolves libnccl at run
+    time).  `unique_id()` on rank 0, hand the 128 bytes to every rank, then Comm(id, rank, nranks, device, stream)."""
+
+    def __init__(self, uid, rank, nranks, device, stream):
+        self.handle = C.c_void_p()
+        rc = lib().ipb_comm_create(int(device), C.c_void_p(int(stream)) if stream else None, bytes(uid), int(rank),
+                                   int(nranks), C.byref(self.handle))
+        if rc != 0:
+            raise _capi.IpbError(rc, (lib().ipb_comm_last_error(None) or b"").decode())
+        self.rank, self.nranks = int(rank), int(nranks)
+
+    @staticmethod
+    def unique_id():
+        buf = C.create_string_buffer(_capi.COMM_ID_BYTES)
+        rc = lib().ipb_comm_unique_id(buf)
+        if rc != 0:
+            raise _capi.IpbError(rc, (lib().ipb_comm_last_error(None) or b"").decode())
+        return buf.raw
+
+    @staticmethod
+    def nccl_version():
+        v = C.c_int()
+        return v.value if lib().ipb_comm_nccl_version(C.byref(v)) == 0 else None
+
+    def close(self):
+        if self.handle:
+            lib().ipb_comm_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def halo_plan(layouts, rank, row_bytes):
+    """ipb_halo of stripe `rank`: which bytes of its buffer (rows src_row0.. of the frame) go to / come from the neighbours."""
+    me = layouts[rank]
+    h = _capi.Halo()
+    for nb in (rank - 1, rank + 1):
+        if nb < 0 or nb >= len(layouts):
+            continue
+        other = layouts[nb]
+        sa, sb = (other.halo_down if nb < rank else other.halo_up)   # what the neighbour's stencil reads ...
+        sa, sb = max(sa, me.own_row0), min(sb, me.own_row1)           # ... of the rows this rank owns
+        ra, rb = (me.halo_up if nb < rank else me.halo_down)
+        side = "up" if nb < rank else "down"
+        if sb > sa:
+            setattr(h, f"send_{side}_off", (sa - me.src_row0) * row_bytes)
+            setattr(h, f"send_{side}_bytes", (sb - sa) * row_bytes)
+        if rb > ra:
+            setattr(h, f"recv_{side}_off", (ra - me.src_row0) * row_bytes)
+            setattr(h, f"recv_{side}_bytes", (rb - ra) * row_bytes)
+    return h
+
+
+def exchange_halos_nccl(comm, ptrs, layouts, row_bytes):
+    """The halo exchange through the C ABI (ipb_halo_exchange: grouped ncclSend / ncclRecv on the communicator's stream).
+    `ptrs`: device addresses of the stripe buffers (one per frame; all share the layout).  No torch involved."""
+    h = halo_plan(layouts, comm.rank, row_bytes)
+    arr = (C.c_void_p * len(ptrs))(*[int(p) for p in ptrs])
+    rc = lib().ipb_halo_exchange(comm.handle, arr, len(ptrs), C.byref(h))
+    if rc != 0:
+        raise _capi.IpbError(rc, (lib().ipb_comm_last_error(comm.handle) or b"").decode())
 
 
 def exchange_halos(buf, layouts, rank, group=None):

@@ -319,6 +319,33 @@ int ipb_pipeline_set_stripe_source(ipb_pipeline *p, const ipb_source *rows, cons
 int ipb_pipeline_output_8bit_stripe(ipb_pipeline *p, uint8_t *dst, size_t dst_capacity, int dst_on_device,
                                     size_t *width, size_t *rows);
 
+/* Halo exchange between stripe neighbours: the only collective of the path.  One process per
+ * GPU; rank r holds stripe r.  NCCL is resolved at run time (dlopen of libnccl.so.2): the library links neither NCCL
+ * nor any framework.  Rank 0 draws a unique id, the host program hands its bytes to every rank through whatever channel
+ * it has (torch.distributed in bench.py, MPI, a file), every rank creates its communicator on its device and stream.
+ * ipb_halo_exchange enqueues, on that stream, one grouped ncclSend / ncclRecv per neighbour and buffer: the rows this
+ * rank owns and a neighbour's stencil reads (1 raw row for demosaic::full, demosaic.rs:70-74; the window rows of
+ * scaled_demosaic, scaling.rs:77-87) go out, the rows this rank's stencil reads come in.  `bufs`: nbufs device
+ * buffers of identical layout (several frames may share one group, which amortises NCCL's launch latency); offsets
+ * are bytes from the start of each buffer.  Stream-ordered: no host synchronisation; capturable into a CUDA graph. */
+#define IPB_COMM_ID_BYTES 128
+typedef struct ipb_comm ipb_comm;
+typedef struct ipb_halo {
+  size_t send_up_off, send_up_bytes;     /* rows sent to rank - 1 (0 bytes: nothing; must be 0 on rank 0) */
+  size_t recv_up_off, recv_up_bytes;     /* rows received from rank - 1 */
+  size_t send_down_off, send_down_bytes; /* rows sent to rank + 1 (must be 0 on the last rank) */
+  size_t recv_down_off, recv_down_bytes; /* rows received from rank + 1 */
+} ipb_halo;
+int ipb_comm_unique_id(unsigned char id[IPB_COMM_ID_BYTES]);
+int ipb_comm_create(int device, void *stream, const unsigned char id[IPB_COMM_ID_BYTES], int rank, int nranks,
+                    ipb_comm **out);
+void ipb_comm_destroy(ipb_comm *comm);
+int ipb_comm_rank(const ipb_comm *comm);
+int ipb_comm_size(const ipb_comm *comm);
+int ipb_comm_nccl_version(int *version);
+const char *ipb_comm_last_error(const ipb_comm *comm);
+int ipb_halo_exchange(ipb_comm *comm, void *const *bufs, size_t nbufs, const ipb_halo *halo);
+
 /* ------------------------------------------------------------------ self-checks of derived tables
  * The fused 8-bit path evaluates output8bit(apply_srgb_gamma(v)) (gamma.rs:21, color_conversions.rs:323-325)
  * through a per-segment threshold table derived from SRGB_GAMMA_TRANSFORM.  ipb_selftest_gamma8 compares it on

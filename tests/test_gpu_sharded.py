@@ -114,10 +114,17 @@ def _nccl_worker(rank, world, port, ret):
             own = buf[me.own_row0 - me.src_row0: me.own_row1 - me.src_row0]
             # every rank generates only its own block of the frame, on its own GPU
             ip.lib().ipb_synth_cfa_u16(ctx.handle, common.SEED, w, me.own_row0, me.own_row1 - me.own_row0, own.data_ptr())
-            exchange_halos(buf, lays, rank)
+            # the exchange goes through the C ABI (ipb_halo_exchange: NCCL send/recv between stripe neighbours);
+            # torch.distributed only hands the 128-byte communicator id to the ranks
+            from imagepipe_b200.sharded import Comm, exchange_halos_nccl
+            box = [Comm.unique_id() if rank == 0 else None]
+            dist.broadcast_object_list(box, src=0)
+            comm = Comm(box[0], rank, world, rank, stream.cuda_stream)
+            exchange_halos_nccl(comm, [buf.data_ptr()], lays, w * 2)
             out = torch.empty(((me.out_row1 - me.out_row0), me.out_width, 3), dtype=torch.uint8, device="cuda")
             run_stripe_8bit(p, buf.data_ptr(), me, DevicePtr(out.data_ptr(), out.numel(), out))
         stream.synchronize()
+        comm.close()
         gathered = [torch.empty((l.out_row1 - l.out_row0, l.out_width, 3), dtype=torch.uint8, device="cuda") for l in lays]
         if rank == 0:  # stripes may differ in height: gather through rank 0 with send/recv
             gathered[0] = out

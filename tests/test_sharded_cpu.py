@@ -32,11 +32,14 @@ def test_partition_rows():
         assert parts[0][0] == 0 and parts[-1][1] == n and len(parts) == w
         for (a0, a1), (b0, b1) in zip(parts, parts[1:]):
             assert a1 == b0 and a0 <= a1
+        if n // w >= 2:
+            assert all(a % 2 == 0 for a, _ in parts[1:])       # boundaries on the Bayer period
         if n // w >= 32:
-            assert all(a % 32 == 0 for a, _ in parts[1:])
+            assert all(a % 32 == 0 for a, _ in partition_rows(n, w, 32)[1:])
         if n >= w:
             assert all(b > a for a, b in parts)
-    assert partition_rows(8736, 8)[0] == (0, 1088)  # C5: 1092 rounded to the tile height
+    assert partition_rows(8736, 8)[0] == (0, 1092)             # C5: eight equal stripes
+    assert partition_rows(8736, 8, 32)[0] == (0, 1088)         # ... or rounded to the tile height
 
 
 def test_stripe_plan_full_resolution(ip):

@@ -1,9 +1,14 @@
 #!/bin/bash
-# one full ncu capture of the speculative kernel on the C2 frame (+ summary and per-instruction dump)
+# ncu captures of the speculative kernel on the C2 frame: one full set (+ summary and per-instruction dump) of the
+# second launch, and the DRAM traffic of the ninth of twelve back-to-back launches over 8 rotating buffer sets with
+# the caches left alone (steady state: the write-back of earlier frames is part of the count).
 set -u
 mkdir -p gpurun_out
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_spec8 -s 1 -c 1 -f -o gpurun_out/prof_spec_c2 \
   python tools/run_frames.py c2 3 > gpurun_out/prof_spec_c2.log 2>&1; echo "ncu rc=$?"
 python tools/ncu_summary.py gpurun_out/prof_spec_c2.ncu-rep > gpurun_out/prof_spec_c2.txt 2>&1
 python tools/ncu_sass.py gpurun_out/prof_spec_c2.ncu-rep 187500 --dump > gpurun_out/prof_spec_c2_sass.txt 2>&1
-tail -60 gpurun_out/prof_spec_c2.txt
+IPB_SETS=8 timeout 600 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --cache-control none \
+  --clock-control none -k regex:k_spec8 -s 8 -c 3 --csv --log-file gpurun_out/prof_spec_c2_traffic.csv \
+  python tools/run_frames.py c2 12 > gpurun_out/prof_spec_c2_traffic.log 2>&1; echo "traffic rc=$?"
+head -26 gpurun_out/prof_spec_c2.txt; cat gpurun_out/prof_spec_c2_traffic.csv | tail -12

@@ -20,10 +20,12 @@ elif which == "c4":
     w, h, cfa, st = 6000, 4000, "RGGB", {"maxwidth": 1500, "maxheight": 1000}
 else:
     w, h, cfa, st = 6000, 4000, "RGGB", {}
-frames = [ip.synth_cfa_u16(common.SEED + i, w, 0, h, ctx=ctx) for i in range(2)]
-dst = ip.DeviceArray(w * h * 3 * (4 if which == "c2f32" else 1), ctx)
+nsets = int(os.environ.get("IPB_SETS", "2"))  # rotating input / output sets (8: steady-state DRAM traffic, write-back included)
+frames = [ip.synth_cfa_u16(common.SEED + i, w, 0, h, ctx=ctx) for i in range(nsets)]
+dsts = [ip.DeviceArray(w * h * 3 * (4 if which == "c2f32" else 1), ctx) for _ in range(nsets if which != "c2f32" else 1)]
 for i in range(n):
-    p = ip.Pipeline.new_from_source(ip.ImageSource.Raw(frames[i % 2], width=w, height=h, cpp=1), ctx=ctx)
+    dst = dsts[i % len(dsts)]
+    p = ip.Pipeline.new_from_source(ip.ImageSource.Raw(frames[i % nsets], width=w, height=h, cpp=1), ctx=ctx)
     common.fill_ipb_ops(p.ops, common.raw_params(cfa=cfa))
     for k, v in st.items():
         setattr(p.globals.settings, k, v)
