@@ -70,7 +70,8 @@ METRIC = "megapixels/sec raw->sRGB full pipe"
 
 def workload_config(world, frames_per_step):
     """config of the JSON line — the same dict on both arms (the reference arm times bounded samples of this workload)."""
-    return {"workload": WORKLOAD_NAME, "frames_per_step": frames_per_step, "buffer_sets": NSETS,
+    return {"workload": WORKLOAD_NAME, "frames_per_step": frames_per_step, "frames_per_step_all_gpus": world * frames_per_step,
+            "buffer_sets": NSETS,
             "l2": f"inputs larger than L2: {NSETS} rotating sets x {(W * H * 2 + OUT_W * OUT_H * 3) / 1e6:.0f} MB",
             "parallelism": f"frames round-robin, {world} replica(s), no collective"}
 
@@ -149,6 +150,31 @@ class ClockSampler(threading.Thread):
         self.join(timeout=2)
         med = float(np.median(self.samples)) if self.samples else None
         return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def bind_to_gpu_numa(index):
+    """Pin this process (and the pinned host buffers it allocates afterwards: first touch) to the CPUs of the NUMA node
+    the GPU hangs off, when the box tells (sysfs).  Returns the node, or None when unknown / single-node."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(index)).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        with open(f"/sys/bus/pci/devices/{bus[-12:].lower()}/numa_node") as f:
+            node = int(f.read())
+        if node < 0:
+            return None
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            cpus = set()
+            for part in f.read().strip().split(","):
+                a, _, b = part.partition("-")
+                cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+        return node
+    except Exception:
+        return None
 
 
 def pinned_array(ip, nbytes, dtype, shape):
@@ -282,6 +308,7 @@ def strong_leg(args, ip, common, torch, dist, ctx, stream, barrier, rank, world,
         else:
             step()
 
+    g = None
     with torch.cuda.stream(stream):
         run_step()
     barrier()
@@ -335,7 +362,11 @@ def strong_leg(args, ip, common, torch, dist, ctx, stream, barrier, rank, world,
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = e2e_calls * mp5 / float(te.item())
     same = bool(np.array_equal(host_out, outs[0].cpu().numpy()))
+    # the captured step holds the communicator: drop the graph before the communicator goes
+    graph = None
+    torch.cuda.synchronize()
     if comm is not None:
+        barrier()
         comm.close()
     launch_ms = total_ms / (K * F)
     return {
@@ -398,6 +429,9 @@ def main():
                          "with the 4x down-scale; c5: one 101.8 MP frame per step-frame, row stripes over the ranks with an "
                          "NCCL halo exchange (strong scaling)")
     args = ap.parse_args()
+    # a hung collective must not hang the caller: dump every thread's stack and exit after IPB_BENCH_WATCHDOG seconds
+    import faulthandler
+    faulthandler.dump_traceback_later(int(os.environ.get("IPB_BENCH_WATCHDOG", "1500")), exit=True)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     select_workload(args.workload)
     if args.frames_per_step is None:
@@ -418,6 +452,7 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
     torch.cuda.set_device(local_rank)
+    numa_node = bind_to_gpu_numa(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     stream = torch.cuda.Stream()
@@ -531,6 +566,30 @@ def main():
     e2e_value = world * per_thread * E2E_THREADS * MP / float(te.item())
     # result check on the last e2e frame: the device-resident path produced the same bytes
     same = all(bool(np.array_equal(w[3], outs[0].to_numpy(np.uint8, (OUT_H, OUT_W, 3)))) for w in workers)
+    # the box's copy ceiling for this traffic at N GPUs: every rank moves one frame's bytes (48 MB in, 72 MB out, pinned,
+    # both directions at once on the two copy streams) with nothing else, all ranks at once
+    ceil_in = torch.empty(W * H * 2, dtype=torch.uint8, device="cuda")
+    ceil_out = torch.empty(OUT_W * OUT_H * 3, dtype=torch.uint8, device="cuda")
+    hin_t, hout_t = torch.from_numpy(workers[0][2].reshape(-1).view(np.uint8)), torch.from_numpy(workers[0][3].reshape(-1))
+    cs1, cs2 = torch.cuda.Stream(), torch.cuda.Stream()
+
+    def raw_copies():
+        with torch.cuda.stream(cs1):
+            ceil_in.copy_(hin_t, non_blocking=True)
+        with torch.cuda.stream(cs2):
+            hout_t.copy_(ceil_out, non_blocking=True)
+
+    for _ in range(4):
+        raw_copies()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(40):
+        raw_copies()
+    torch.cuda.synchronize()
+    tc = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tc, op=dist.ReduceOp.MAX)
+    pcie_ceiling = world * 40 * MP / float(tc.item())
 
     # ---- strong scaling on the same record: BASELINE config 5, one 101.8 MP frame over the N GPUs (every N, N = 1 too)
     strong = None
@@ -556,7 +615,10 @@ def main():
             "e2e": {"value": e2e_value, "unit": "MP/s", "h2d_bytes_per_step": e2e_frames * W * H * 2,
                     "d2h_bytes_per_step": e2e_frames * OUT_W * OUT_H * 3, "steps": e2e_steps, "frames_per_step": e2e_frames,
                     "host_threads": E2E_THREADS, "frames_timed": per_thread * E2E_THREADS,
-                    "single_call_ms": single_call_ms, "matches_device_path": same},
+                    "single_call_ms": single_call_ms, "matches_device_path": same,
+                    "numa_node": numa_node, "pcie_ceiling": pcie_ceiling, "frac_of_ceiling": e2e_value / pcie_ceiling,
+                    "pcie_ceiling_what": "the same bytes per frame as bare pinned-memory copies, both directions at once, "
+                                         "all ranks at the same time (no kernel, no API)"},
             "gpu_launches": int(launches),
             "clocks": clocks,
         }
