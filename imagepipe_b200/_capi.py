@@ -160,6 +160,8 @@ def lib():
         "ipb_pipeline_last_run_info": (None, [vp, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
         "ipb_pipeline_output_8bit": (i, [vp, vp, sz, i, szp, szp]),
         "ipb_pipeline_output_16bit": (i, [vp, vp, sz, i, szp, szp]),
+        "ipb_pipeline_output_8bit_cached": (i, [vp, vp, vp, sz, i, szp, szp]),
+        "ipb_pipeline_output_16bit_cached": (i, [vp, vp, vp, sz, i, szp, szp]),
         "ipb_pipeline_stripe_rows": (i, [vp, sz, sz, szp, szp]),
         "ipb_stripe_plan": (i, [vp, vp, sz, sz, sz, sz, szp, szp, szp, szp]),
         "ipb_pipeline_set_stripe_source": (i, [vp, vp, vp]),

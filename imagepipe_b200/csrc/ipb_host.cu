@@ -77,6 +77,7 @@ struct ipb_pipeline {
   ipb_settings settings{};
   int fused = 1;
   int use_tma = 1;
+  unsigned long long source_gen = 0;  // bumped by set_source: part of the cache key (a refilled buffer is a new image)
   int spec = 1;      // 8-bit output of RGB Bayer frames through the speculative kernel (results identical; 0: k_fused_full)
   int band_mb = 16;  // host<->device paths: band size of the overlapped H2D / kernel / D2H schedule (0 = no bands)
   // golevel_rc_exact() result for the last (black, range) pair: the check walks all 65536 samples
@@ -1360,6 +1361,7 @@ int ipb_pipeline_set_source(ipb_pipeline *p, const ipb_source *image) {
   if (!p || !image) return IPB_ERR_INVALID;
   p->image = *image;
   p->has_stripe = false;
+  p->source_gen++;
   return IPB_OK;
 }
 int ipb_pipeline_set_fused(ipb_pipeline *p, int fused) {
@@ -1435,6 +1437,10 @@ static bool fused_params_bounded(const ipb_pipeline *p) {
   if (!build_spline(&c, &sp)) return false;
   for (int i = 0; i + 1 < sp.n; i++)
     if (!(sp.x[i] < sp.x[i + 1])) return false;
+  // ... and finite coefficients: on a knot the fused evaluation returns y + 0 * c, which is NaN for an infinite c
+  // (tiny knot spacing overflows 1/dx) where the reference's early return gives y
+  for (int i = 0; i < sp.nseg; i++)
+    if (!std::isfinite(sp.c1[i]) || !std::isfinite(sp.c2[i]) || !std::isfinite(sp.c3[i])) return false;
   if (sp.n > 0 && (std::signbit(sp.y_first) && sp.y_first == 0.0f)) return false;
   if (sp.n > 0 && (std::signbit(sp.y_last) && sp.y_last == 0.0f)) return false;
   return true;
@@ -1938,13 +1944,15 @@ int ipb_pipeline_run_cached(ipb_pipeline *p, ipb_cache *cache, ipb_buffer **out)
   if (p->image.width < 10 || p->image.height < 10) return fail(ctx, IPB_ERR_INVALID, "source smaller than 10x10");
   if (p->has_stripe) return fail(ctx, IPB_ERR_UNSUPPORTED, "pipeline_run on a stripe source: use output_8bit_stripe");
   negotiate(p, nullptr, nullptr);
-  // the hash chain: settings first (pipeline.rs:346), then every op cumulatively (:350-361).  The source's identity
-  // is hashed too (the reference leaves that to the caller: one cache per image).
+  // the hash chain: settings first (pipeline.rs:346), then every op cumulatively (:350-361).  The source's identity is
+  // hashed too (the reference leaves that to the caller: one cache per image): its address, shape, and a counter that
+  // ipb_pipeline_set_source bumps — a ring buffer refilled with the next frame is a different image at the same address.
+  // (Pixels rewritten in place WITHOUT set_source are not seen: like the reference, call set_source or clear the cache.)
   ChainHash h;
   const ipb_settings &st = p->settings;
   h.pod(st.maxwidth); h.pod(st.maxheight); h.pod(st.demosaic_width); h.pod(st.demosaic_height);
   h.pod(st.linear); h.pod(st.use_fastpath);
-  h.pod(p->image.kind); h.pod(p->image.width); h.pod(p->image.height); h.pod(p->image.cpp); h.pod(p->image.data);
+  h.pod(p->image.kind); h.pod(p->image.width); h.pod(p->image.height); h.pod(p->image.cpp); h.pod(p->image.data); h.pod(p->source_gen);
   ipb_cache::Key keys[8];
   const ipb_ops &o = p->ops;
   h.name("gofloat");
@@ -2023,7 +2031,7 @@ static bool ops_are_default_other(const ipb_pipeline *p) {  // Pipeline::default
 
 extern "C++" {
 template <typename T>
-static int output_impl(ipb_pipeline *p, T *dst, size_t cap, int dst_on_device, size_t *width, size_t *height) {
+static int output_impl(ipb_pipeline *p, ipb_cache *cache, T *dst, size_t cap, int dst_on_device, size_t *width, size_t *height) {
   if (!p || !dst) return IPB_ERR_INVALID;
   ipb_ctx *ctx = p->ctx;
   IPB_TRY(enter(ctx));
@@ -2073,6 +2081,16 @@ static int output_impl(ipb_pipeline *p, T *dst, size_t cap, int dst_on_device, s
   }
 
   p->settings.linear = want8 ? 0 : 1;  // pipeline.rs:405 / :452
+  if (cache) {  // self.run(cache) + the pack loop (pipeline.rs:406-414 / :453-461); the fast path above came first, as in the reference
+    ipb_buffer *b;
+    IPB_TRY(ipb_pipeline_run_cached(p, cache, &b));
+    const size_t n = b->width * b->height * 3;
+    int rc = n > cap ? fail(ctx, IPB_ERR_INVALID, "destination too small: %zu < %zu", cap, n) : pack_impl<T>(ctx, b, dst, dst_on_device);
+    if (width) *width = b->width;
+    if (height) *height = b->height;
+    ipb_buffer_release(b);
+    return rc;
+  }
   size_t fw, fh;
   negotiate(p, &fw, &fh);
   FusedPlan plan;
@@ -2104,11 +2122,19 @@ static int output_impl(ipb_pipeline *p, T *dst, size_t cap, int dst_on_device, s
 }  // extern "C++"
 int ipb_pipeline_output_8bit(ipb_pipeline *p, uint8_t *dst, size_t dst_capacity, int dst_on_device, size_t *width,
                              size_t *height) {
-  return output_impl<uint8_t>(p, dst, dst_capacity, dst_on_device, width, height);
+  return output_impl<uint8_t>(p, nullptr, dst, dst_capacity, dst_on_device, width, height);
 }
 int ipb_pipeline_output_16bit(ipb_pipeline *p, uint16_t *dst, size_t dst_capacity, int dst_on_device, size_t *width,
                               size_t *height) {
-  return output_impl<uint16_t>(p, dst, dst_capacity, dst_on_device, width, height);
+  return output_impl<uint16_t>(p, nullptr, dst, dst_capacity, dst_on_device, width, height);
+}
+int ipb_pipeline_output_8bit_cached(ipb_pipeline *p, ipb_cache *cache, uint8_t *dst, size_t dst_capacity, int dst_on_device,
+                                    size_t *width, size_t *height) {
+  return output_impl<uint8_t>(p, cache, dst, dst_capacity, dst_on_device, width, height);
+}
+int ipb_pipeline_output_16bit_cached(ipb_pipeline *p, ipb_cache *cache, uint16_t *dst, size_t dst_capacity, int dst_on_device,
+                                     size_t *width, size_t *height) {
+  return output_impl<uint16_t>(p, cache, dst, dst_capacity, dst_on_device, width, height);
 }
 
 // ---- row stripes
@@ -2116,9 +2142,14 @@ int ipb_pipeline_output_16bit(ipb_pipeline *p, uint16_t *dst, size_t dst_capacit
 static int stripe_plan(ipb_pipeline *p, FusedPlan *plan) {
   ipb_ctx *ctx = p->ctx;
   if (p->image.width < 10 || p->image.height < 10) return fail(ctx, IPB_ERR_INVALID, "source smaller than 10x10");
+  // the 8-bit output's plan (settings.linear = false, pipeline.rs:405) without leaving a trace in the settings: this is
+  // also reached from the pure size query ipb_pipeline_stripe_rows
+  const int keep_linear = p->settings.linear;
   p->settings.linear = 0;
   negotiate(p, nullptr, nullptr);
-  IPB_TRY(plan_fused(p, plan));
+  const int rc_plan = plan_fused(p, plan);
+  p->settings.linear = keep_linear;
+  IPB_TRY(rc_plan);
   int flips[3];
   orientation_flips(&p->ops.transform, flips);
   if (plan->mode == kNotFused || flips[0] || flips[1] || flips[2])

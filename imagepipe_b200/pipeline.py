@@ -513,13 +513,13 @@ class Pipeline:
         lib().ipb_pipeline_last_run_info(self.handle, C.byref(a), C.byref(b))
         return a.value, b.value
 
-    def _output_cached(self, cache, pack, dtype, linear):
-        # pipeline.rs:404-421 / :451-468: set settings.linear, run(cache), pack loop
-        self.globals.settings.linear = int(linear)
-        buf = self.run(cache)
-        host = np.empty(buf.width * buf.height * 3, dtype)
-        _capi.check(self.ctx.handle, pack(self.ctx.handle, buf.handle, host.ctypes.data, 0))
-        return SRGBImage(buf.width, buf.height, host)
+    def _output_cached(self, fn, cache, dtype):
+        # pipeline.rs:377-422 / :424-469 with Some(&cache): fast path first, else settings.linear, run(cache), pack loop
+        w, h = self.output_size()
+        host = np.empty(max(w * h, self.globals.image.width * self.globals.image.height) * 3, dtype)
+        ow, oh = C.c_size_t(), C.c_size_t()
+        _capi.check(self.ctx.handle, fn(self.handle, cache.handle, host.ctypes.data, host.size, 0, C.byref(ow), C.byref(oh)))
+        return SRGBImage(ow.value, oh.value, host[: ow.value * oh.value * 3])
 
     def _output(self, fn, dtype, dst):
         w, h = self.output_size()
@@ -541,12 +541,12 @@ class Pipeline:
 
     def output_8bit(self, cache=None, dst=None):
         if cache is not None:
-            return self._output_cached(cache, lib().ipb_pack_8bit, np.uint8, False)
+            return self._output_cached(lib().ipb_pipeline_output_8bit_cached, cache, np.uint8)
         return self._output(lib().ipb_pipeline_output_8bit, np.uint8, dst)
 
     def output_16bit(self, cache=None, dst=None):
         if cache is not None:
-            return self._output_cached(cache, lib().ipb_pack_16bit, np.uint16, True)
+            return self._output_cached(lib().ipb_pipeline_output_16bit_cached, cache, np.uint16)
         return self._output(lib().ipb_pipeline_output_16bit, np.uint16, dst)
 
     # ---- row stripes (multi-GPU sharding of one large frame; no reference equivalent)

@@ -301,36 +301,23 @@ class Pipeline {
     ctx_->check(ipb_pipeline_output_size(h_, &w, &h));
     return {w, h};
   }
-  // Pipeline::output_8bit / output_16bit (pipeline.rs:377-469)
+  // Pipeline::output_8bit / output_16bit (pipeline.rs:377-469); with a cache the library still tries the non-raw fast
+  // path first (pipeline.rs:381, :428), then runs from the first changed op and packs
   SRGBImage output_8bit(const PipelineCache *cache = nullptr) {
     SRGBImage img;
-    if (cache) {
-      settings().linear = 0;
-      OpBuffer buf = run(cache);
-      img.width = buf.width(); img.height = buf.height();
-      img.data.resize(img.width * img.height * 3);
-      ctx_->check(ipb_pack_8bit(ctx_->handle(), buf.handle(), img.data.data(), 0));
-      return img;
-    }
     auto wh = output_size();
     img.data.resize(wh.first * wh.second * 3);
-    ctx_->check(ipb_pipeline_output_8bit(h_, img.data.data(), img.data.size(), 0, &img.width, &img.height));
+    ctx_->check(ipb_pipeline_output_8bit_cached(h_, cache ? cache->handle() : nullptr, img.data.data(), img.data.size(), 0,
+                                                &img.width, &img.height));
     img.data.resize(img.width * img.height * 3);
     return img;
   }
   SRGBImage16 output_16bit(const PipelineCache *cache = nullptr) {
     SRGBImage16 img;
-    if (cache) {
-      settings().linear = 1;
-      OpBuffer buf = run(cache);
-      img.width = buf.width(); img.height = buf.height();
-      img.data.resize(img.width * img.height * 3);
-      ctx_->check(ipb_pack_16bit(ctx_->handle(), buf.handle(), img.data.data(), 0));
-      return img;
-    }
     auto wh = output_size();
     img.data.resize(wh.first * wh.second * 3);
-    ctx_->check(ipb_pipeline_output_16bit(h_, img.data.data(), img.data.size(), 0, &img.width, &img.height));
+    ctx_->check(ipb_pipeline_output_16bit_cached(h_, cache ? cache->handle() : nullptr, img.data.data(), img.data.size(), 0,
+                                                 &img.width, &img.height));
     img.data.resize(img.width * img.height * 3);
     return img;
   }

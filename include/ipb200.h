@@ -240,6 +240,10 @@ void ipb_pipeline_destroy(ipb_pipeline *p);
 /* pipeline.ops / pipeline.globals.settings are public fields in the reference; these return mutable views */
 ipb_ops *ipb_pipeline_ops(ipb_pipeline *p);
 ipb_settings *ipb_pipeline_settings(ipb_pipeline *p);
+/* Swap the source (the next frame of a batch).  A host-resident source is copied to the device asynchronously on the
+ * context's stream by the calls that read it: when their result stays on the device (ipb_pipeline_run, *_run entry
+ * points, dst_on_device != 0) the host pixels must stay untouched until ipb_ctx_synchronize (or any call that
+ * returns host data) — the lifetime rule of every asynchronous copy from pinned memory. */
 int ipb_pipeline_set_source(ipb_pipeline *p, const ipb_source *image);
 /* 1 (default): Pipeline::run may use the fused raw->sRGB kernel when the op chain allows it;
  * 0: always run op by op (one kernel + one OpBuffer per op, like the reference). */
@@ -301,6 +305,13 @@ int ipb_pipeline_output_8bit(ipb_pipeline *p, uint8_t *dst, size_t dst_capacity,
                              size_t *height);
 int ipb_pipeline_output_16bit(ipb_pipeline *p, uint16_t *dst, size_t dst_capacity, int dst_on_device,
                               size_t *width, size_t *height);
+/* output_8bit(Some(&cache)) / output_16bit(Some(&cache)): like the reference, the non-raw fast path is tried first with
+ * or without a cache (pipeline.rs:381, :428); otherwise settings.linear is set, the cached run restarts at the first op
+ * whose parameters changed, and the result is packed.  cache == NULL: the calls above. */
+int ipb_pipeline_output_8bit_cached(ipb_pipeline *p, ipb_cache *cache, uint8_t *dst, size_t dst_capacity, int dst_on_device,
+                                    size_t *width, size_t *height);
+int ipb_pipeline_output_16bit_cached(ipb_pipeline *p, ipb_cache *cache, uint16_t *dst, size_t dst_capacity, int dst_on_device,
+                                     size_t *width, size_t *height);
 
 /* Row-stripe sharding (multi-GPU).  Only for the fused raw CFA path with a
  * Normal orientation and no rotatecrop. */

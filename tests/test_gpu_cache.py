@@ -84,3 +84,50 @@ def test_two_pipelines_share_a_cache(ip, ctx):
     assert (ra != rb).any()
     assert_bit_exact(pa.run(cache).to_numpy(), ra, "pipeline a again")
     assert pa.last_run_info() == (8, 0)
+
+
+@pytest.mark.parametrize("depth", [np.uint8, np.uint16])
+@pytest.mark.parametrize("maxwidth", [0, 97])
+def test_other_source_with_a_cache_takes_the_fast_path_first(ip, orc, ctx, depth, maxwidth):
+    """pipeline.rs:381 / :428: for a non-raw source with default ops the fast path comes before run(cache), with or
+    without a cache — output_16bit(cache) is the gamma-encoded raster (not a linear run), output_8bit(cache) with a
+    size limit goes through scale_down_srgb on the integers.  Cached and uncached calls give the same image."""
+    rng = np.random.default_rng(7)
+    img = rng.integers(0, np.iinfo(depth).max + 1, (120, 200, 3)).astype(depth)
+    st = {"maxwidth": maxwidth} if maxwidth else None
+    cache = ip.Pipeline.new_cache(1 << 28, ctx)
+    for bits, call, ocall in ((8, "output_8bit", orc.pipeline_output_8bit), (16, "output_16bit", orc.pipeline_output_16bit)):
+        want = ocall(orc.make_pipeline(img, "rgb", None, st))
+        p = common.make_ipb_pipeline(ip, img, "rgb", None, st, ctx=ctx)
+        assert_bit_exact(getattr(p, call)().to_numpy(), want, f"{call}() fast path")
+        assert_bit_exact(getattr(p, call)(cache).to_numpy(), want, f"{call}(cache) fast path")
+        # without the fast path both go through the pipeline, cached or not, and still agree with the oracle's slow path
+        st_slow = dict(st or {}, use_fastpath=0)
+        want_slow = ocall(orc.make_pipeline(img, "rgb", None, st_slow))
+        ps = common.make_ipb_pipeline(ip, img, "rgb", None, st_slow, ctx=ctx)
+        assert_bit_exact(getattr(ps, call)(cache).to_numpy(), want_slow, f"{call}(cache) slow path")
+
+
+def test_set_source_invalidates_the_cache_for_a_refilled_buffer(ip, orc, ctx):
+    """A ring buffer refilled with the next frame keeps its address: set_source must still start a new hash chain."""
+    params = common.raw_params()
+    a, b = common.synth_cfa(256, 128, seed=301), common.synth_cfa(256, 128, seed=302)
+    d = ip.DeviceArray.from_numpy(a, ctx)
+    src = ip.ImageSource.Raw(d, 256, 128)
+    p = ip.Pipeline.new_from_source(src, ctx=ctx)
+    common.fill_ipb_ops(p.ops, params)
+    cache = ip.Pipeline.new_cache(1 << 28, ctx)
+    assert_bit_exact(p.run(cache).to_numpy(), orc.pipeline_run(orc.make_pipeline(a, "raw", params)), "frame a")
+    ip.lib().ipb_device_upload(ctx.handle, d.ptr, b.ctypes.data, b.nbytes)   # same device buffer, next frame
+    p.set_source(src)
+    assert_bit_exact(p.run(cache).to_numpy(), orc.pipeline_run(orc.make_pipeline(b, "raw", params)), "frame b")
+    assert p.last_run_info() == (0, 8)
+
+
+def test_stripe_rows_query_leaves_settings_alone(ip, ctx):
+    data = common.synth_cfa(256, 128, seed=311)
+    p = common.make_ipb_pipeline(ip, data, "raw", common.raw_params(), ctx=ctx, on_device=True)
+    p.output_16bit()
+    assert p.globals.settings.linear == 1          # sticky state of the last output call (pipeline.rs:452)
+    p.stripe_rows(0, 64)
+    assert p.globals.settings.linear == 1
