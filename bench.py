@@ -55,7 +55,7 @@ def select_workload(name):
         W, H, CFA = 8256, 5504, common.XTRANS
         OUT_W, OUT_H = W, H
         WORKLOAD_NAME = "C3: 8256x5504 Fuji X-Trans 6x6 -> 8-bit sRGB, fused demosaic->gamma kernel (generic CFA path)"
-        KERNEL_NAME, TRAFFIC_KEY = "k_fused_full<u8, generic CFA>", "k_fused_full<u8,generic> C3 8256x5504"
+        KERNEL_NAME, TRAFFIC_KEY = "k_spec8<512, generic CFA> (speculative 8-bit kernel)", "k_spec8 C3 8256x5504"
     elif name == "c4":
         SETTINGS = {"maxwidth": 1500, "maxheight": 1000}
         OUT_W, OUT_H = 1500, 1000

@@ -49,6 +49,8 @@ struct SmemFront {
   float2 stab[kSpecSTabEntries];                // basecurve in f-space: {intercept, slope} per segment
   alignas(16) float spl[kSplRows][8];           // exact basecurve: [0] below the first knot, [1 + i] segment i, [n] at / above the last
   float thr[260];                               // the 255 thresholds of output8bit(apply_srgb_gamma(v)), then +inf
+  uint2 taps[144];                              // generic patterns: per position the 9-bit tap masks of colours 0, 1 (.x) and 2 (.y)
+  uint8_t pat[144];                             // ... and one period of the colour table (ph rows of pw)
   alignas(16) SpecParams sp;                    // copies for the out-of-line exact path (a generic pointer into the
   alignas(16) ColorParams cp;                   // constant bank would turn every parameter access into a global load)
   alignas(8) unsigned long long mbar;
@@ -259,15 +261,14 @@ __device__ __forceinline__ float lab_f_exact(const float2 *__restrict__ lut, con
   return r;
 }
 
-// demosaic::full (demosaic.rs:67-119) + to_lab + basecurve + from_lab for ONE pixel of an RGB Bayer frame from its nine
-// level-mapped taps t[0..8] (raster order; whatever sits in a tap outside the frame is ignored), in the reference's
-// arithmetic: the per-pixel code of ipb_device.cuh with the verified reciprocal divisions and k_fused_full's table
-// for cube roots above one.  Any position, frame borders included (a tap outside the frame is dropped from sum and
-// count, :103-107).  Taps reach their colour's sum in the reference's raster order.  Both kinds of site run the same
-// instructions (four means, a select), so a warp of queue entries does not diverge.  `phase` holds the colour of
-// position (row & 1, col & 1) in bits 2*(2*(row&1)+(col&1)).  Out: linear RGB before OpGamma.
-__device__ __forceinline__ void exact_bayer_linear(const SpecParams &p, const ColorParams &P, const float (*spl)[8],
-                                                   uint32_t phase, int x, int y, const float t[9], float out[3]) {
+// demosaic::full (demosaic.rs:67-119) for ONE pixel of an RGB Bayer frame from its nine level-mapped taps t[0..8] (raster
+// order; whatever sits in a tap outside the frame is ignored), in the reference's arithmetic.  Any position, frame
+// borders included (a tap outside the frame is dropped from sum and count, :103-107).  Taps reach their colour's sum
+// in the reference's raster order.  Both kinds of site run the same instructions (four means, a select), so a warp of
+// queue entries does not diverge.  `phase` holds the colour of position (row & 1, col & 1) in bits
+// 2*(2*(row&1)+(col&1)).
+__device__ __forceinline__ void exact_rgb_bayer(const SpecParams &p, uint32_t phase, int x, int y, const float t[9], float &r,
+                                                float &g, float &b) {
   const bool hn = y > 0, hs = y < p.height - 1, hw = x > 0, he = x < p.width - 1;
   auto mean = [](float s, int n) { return n == 4 ? s * 0.25f : n == 2 ? s * 0.5f : n ? __fdiv_rn(s, (float)n) : 0.0f; };
   const float v = t[4];
@@ -290,7 +291,44 @@ __device__ __forceinline__ void exact_bayer_linear(const SpecParams &p, const Co
   const bool gsite = c == 1;
   const int first = gsite ? ch : c;  // colour (0 or 2) that receives `a0`
   const float a0 = gsite ? mh : v, a1 = gsite ? mv : md;
-  const float r = first == 0 ? a0 : a1, g = gsite ? v : mg, b = first == 0 ? a1 : a0;
+  r = first == 0 ? a0 : a1;
+  g = gsite ? v : mg;
+  b = first == 0 ? a1 : a0;
+}
+
+// The same for any three-colour pattern (X-Trans ...): `pat` is one period of the colour table (ph rows of pw bytes).
+// Statement for statement demosaic.rs:77-116: a tap of the centre's own colour other than the centre itself is discarded
+// (:87), a tap outside the frame is skipped (:103-104), a colour's value is sum / count, or 0.0 without taps (:110-114).
+__device__ __forceinline__ void exact_rgb_generic(const SpecParams &p, const uint8_t *pat, int x, int y, const float t[9], float &r,
+                                                  float &g, float &b) {
+  const int pr = y % p.ph, pc = x % p.pw;
+  const int pix = pat[pr * p.pw + pc];
+  float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f;
+  int n0 = 0, n1 = 0, n2 = 0;
+#pragma unroll
+  for (int dy = -1; dy <= 1; dy++)
+#pragma unroll
+    for (int dx = -1; dx <= 1; dx++) {
+      const int yy = y + dy, xx = x + dx;
+      if (yy < 0 || yy >= p.height || xx < 0 || xx >= p.width) continue;
+      const int rr = pr + dy < 0 ? p.ph - 1 : (pr + dy == p.ph ? 0 : pr + dy), cc = pc + dx < 0 ? p.pw - 1 : (pc + dx == p.pw ? 0 : pc + dx);
+      const int oc = pat[rr * p.pw + cc];
+      if (oc == pix && (dx != 0 || dy != 0)) continue;
+      const float v = t[(dy + 1) * 3 + dx + 1];
+      if (oc == 0) { s0 = s0 + v; n0++; }
+      else if (oc == 1) { s1 = s1 + v; n1++; }
+      else if (oc == 2) { s2 = s2 + v; n2++; }
+    }
+  r = n0 ? __fdiv_rn(s0, (float)n0) : 0.0f;
+  g = n1 ? __fdiv_rn(s1, (float)n1) : 0.0f;
+  b = n2 ? __fdiv_rn(s2, (float)n2) : 0.0f;
+}
+
+// to_lab + basecurve + from_lab of one demosaiced pixel in the reference's arithmetic: the per-pixel code of
+// ipb_device.cuh with the verified reciprocal divisions and k_fused_full's table for cube roots above one.
+// Out: linear RGB before OpGamma.
+__device__ __forceinline__ void exact_chain(const SpecParams &p, const ColorParams &P, const float (*spl)[8], float r, float g,
+                                            float b, float out[3]) {
   // camera_to_lab (color_conversions.rs:42-55,156-169), statement for statement as ipb_device.cuh camera_to_lab<true>
   const float cr = fminf(r * P.mul[0], 1.0f), cg = fminf(g * P.mul[1], 1.0f), cb = fminf(b * P.mul[2], 1.0f);
   const float X = cr * P.cm[0] + cg * P.cm[1] + cb * P.cm[2];
@@ -362,11 +400,13 @@ __device__ __forceinline__ uint32_t gamma8_exact(uint32_t g8_base, uint32_t thr_
 // queue entry: (row inside the launch's output rows) << 16 | column.  Out of line: the exact path keeps its registers
 // (and the instruction cache footprint of its ~450 instructions) to itself; p and P are the copies in shared memory.
 __device__ __noinline__ void fixup_entry(const SpecParams &p, const ColorParams &P, const float (*spl)[8], uint32_t phase,
-                                         uint32_t g8_base, uint32_t thr_base, uint32_t entry) {
+                                         const uint8_t *pat, uint32_t g8_base, uint32_t thr_base, uint32_t entry) {
   const int row = (int)(entry >> 16), x = (int)(entry & 0xffffu), y = p.out_row0 + row;
-  float t[9], v[3];
+  float t[9], v[3], r, g, b;
   taps_from_frame_wide(p, x, y, t);
-  exact_bayer_linear(p, P, spl, phase, x, y, t, v);
+  if (pat) exact_rgb_generic(p, pat, x, y, t, r, g, b);   // uniform: one pattern kind per launch
+  else exact_rgb_bayer(p, phase, x, y, t, r, g, b);
+  exact_chain(p, P, spl, r, g, b, v);
   uint8_t *o = p.out + ((size_t)row * (size_t)p.width + (size_t)x) * 3;
   o[0] = (uint8_t)gamma8_exact(g8_base, thr_base, v[0]);
   o[1] = (uint8_t)gamma8_exact(g8_base, thr_base, v[1]);
@@ -381,7 +421,27 @@ __device__ __forceinline__ void issue_tile(const SpecParams &p, const CUtensorMa
   tma_load_2d(raw_stage, tmap, x, y, bar);
 }
 
-// one four-pixel task of the cheap pass; returns the three output words and the flag mask of pixels to recompute
+// the twelve channel sums of a task, in pixel order (r, g, b of pixel 0 .. 3) -> the three output words and the mask of
+// pixels whose certificate failed (a channel within deltaF_c of a threshold) or that lie outside the certified domain
+__device__ __forceinline__ uint32_t pack_and_certify(const SpecParams &p, const uint32_t c[12], float ya, float yb, uint32_t ya_mask,
+                                                     uint32_t yb_mask, uint32_t words[3]) {
+  words[0] = __byte_perm(__byte_perm(c[0], c[1], 0x0073), __byte_perm(c[2], c[3], 0x0073), 0x5410);
+  words[1] = __byte_perm(__byte_perm(c[4], c[5], 0x0073), __byte_perm(c[6], c[7], 0x0073), 0x5410);
+  words[2] = __byte_perm(__byte_perm(c[8], c[9], 0x0073), __byte_perm(c[10], c[11], 0x0073), 0x5410);
+  // distance certificates: the product drops the byte field and weighs the channel's distance by deltaF_max / deltaF_c
+  const uint32_t wr = p.wmul[0], wg = p.wmul[1], wb = p.wmul[2], T = p.amb_t;
+  const uint32_t d0 = min(min(c[0] * wr, c[1] * wg), c[2] * wb), d1 = min(min(c[3] * wr, c[4] * wg), c[5] * wb);
+  const uint32_t d2 = min(min(c[6] * wr, c[7] * wg), c[8] * wb), d3 = min(min(c[9] * wr, c[10] * wg), c[11] * wb);
+  uint32_t flags = 0;
+  if (min(min(d0, d1), min(d2, d3)) <= T) {
+    flags = (d0 <= T ? 1u : 0u) | (d1 <= T ? 2u : 0u) | (d2 <= T ? 4u : 0u) | (d3 <= T ? 8u : 0u);
+  }
+  if (fminf(ya, yb) < p.y_min)  // outside the certified domain (far below black): that pixel pair exactly
+    flags |= (ya < p.y_min ? ya_mask : 0u) | (yb < p.y_min ? yb_mask : 0u);
+  return flags;
+}
+
+// one four-pixel task of the cheap pass (RGB Bayer); returns the three output words and the mask of pixels to recompute
 template <bool GF, bool AR>
 __device__ __forceinline__ uint32_t cheap_task(const SpecParams &p, uint32_t g8_base, uint32_t stab_bias, const Window &w,
                                                uint32_t words[3]) {
@@ -390,23 +450,46 @@ __device__ __forceinline__ uint32_t cheap_task(const SpecParams &p, uint32_t g8_
   uint32_t s02[6], s13[6];
   const float y02 = chain_pair<false>(p, g8_base, stab_bias, AR ? a02 : o02, g02, AR ? o02 : a02, s02, nullptr);
   const float y13 = chain_pair<false>(p, g8_base, stab_bias, AR ? a13 : o13, g13, AR ? o13 : a13, s13, nullptr);
-  // s[2c + h]: channel c of the pair's pixel h.  Bytes: px0 = s02[*][0], px1 = s13[*][0], px2 = s02[*][1], px3 = s13[*][1]
-  const uint32_t r0 = s02[0], g0 = s02[2], b0 = s02[4], r2 = s02[1], g2 = s02[3], b2 = s02[5];
-  const uint32_t r1 = s13[0], g1 = s13[2], b1 = s13[4], r3 = s13[1], g3 = s13[3], b3 = s13[5];
-  words[0] = __byte_perm(__byte_perm(r0, g0, 0x0073), __byte_perm(b0, r1, 0x0073), 0x5410);
-  words[1] = __byte_perm(__byte_perm(g1, b1, 0x0073), __byte_perm(r2, g2, 0x0073), 0x5410);
-  words[2] = __byte_perm(__byte_perm(b2, r3, 0x0073), __byte_perm(g3, b3, 0x0073), 0x5410);
-  // distance certificates: the product drops the byte field and weighs the channel's distance by deltaF_max / deltaF_c
-  const uint32_t wr = p.wmul[0], wg = p.wmul[1], wb = p.wmul[2], T = p.amb_t;
-  const uint32_t d0 = min(min(r0 * wr, g0 * wg), b0 * wb), d1 = min(min(r1 * wr, g1 * wg), b1 * wb);
-  const uint32_t d2 = min(min(r2 * wr, g2 * wg), b2 * wb), d3 = min(min(r3 * wr, g3 * wg), b3 * wb);
-  uint32_t flags = 0;
-  if (min(min(d0, d1), min(d2, d3)) <= T) {
-    flags = (d0 <= T ? 1u : 0u) | (d1 <= T ? 2u : 0u) | (d2 <= T ? 4u : 0u) | (d3 <= T ? 8u : 0u);
+  // s[2c + h]: channel c of the pair's pixel h: px0 = s02[*][0], px1 = s13[*][0], px2 = s02[*][1], px3 = s13[*][1]
+  const uint32_t c[12] = {s02[0], s02[2], s02[4], s13[0], s13[2], s13[4], s02[1], s02[3], s02[5], s13[1], s13[3], s13[5]};
+  return pack_and_certify(p, c, y02, y13, 5u, 10u, words);
+}
+
+// {1/n rounded to nearest, n} for tap counts n = 0..9 (entry 0 divides the empty sum by 1: +0.0)
+__constant__ float2 kTapRcpS[10] = {{0.0f, 1.0f}, {1.0f, 1.0f}, {0.5f, 2.0f}, {1.0f / 3.0f, 3.0f}, {0.25f, 4.0f},
+                                    {1.0f / 5.0f, 5.0f}, {1.0f / 6.0f, 6.0f}, {1.0f / 7.0f, 7.0f}, {0.125f, 8.0f},
+                                    {1.0f / 9.0f, 9.0f}};
+// One colour of demosaic::full for an interior pixel of any pattern, exactly as the reference rounds it: the selected taps
+// summed in raster order (predicated adds), s / n through the three-instruction reciprocal form, which equals IEEE
+// division for every divisor 1..9 (tools/verify_constdiv.c) — the scheme of k_fused_full (ipb_fused.cu bin_mean_rc).
+__device__ __forceinline__ float bin_mean_exact(uint32_t m, const float v[9]) {
+  float s = 0.0f;
+#pragma unroll
+  for (int i = 0; i < 9; i++)
+    if ((m >> i) & 1u) s = s + v[i];
+  const float2 e = kTapRcpS[__popc(m)];
+  return div_rc(s, e.y, e.x);
+}
+
+// the same task for any three-colour pattern: w = the 3 x 6 window (rows y-1 .. y+1, columns x0-1 .. x0+4), mm[j] = the
+// tap masks of pixel j's pattern position (colours 0, 1 in .x low / high half, colour 2 in .y low half)
+__device__ __forceinline__ uint32_t cheap_task_generic(const SpecParams &p, uint32_t g8_base, uint32_t stab_bias, const float w[3][6],
+                                                       const uint2 mm[4], uint32_t words[3]) {
+  float r[4], g[4], b[4];
+#pragma unroll
+  for (int j = 0; j < 4; j++) {
+    float v[9];
+#pragma unroll
+    for (int k = 0; k < 3; k++) { v[k * 3] = w[k][j]; v[k * 3 + 1] = w[k][j + 1]; v[k * 3 + 2] = w[k][j + 2]; }
+    r[j] = bin_mean_exact(mm[j].x & 0xffffu, v);
+    g[j] = bin_mean_exact(mm[j].x >> 16, v);
+    b[j] = bin_mean_exact(mm[j].y & 0xffffu, v);
   }
-  if (fminf(y02, y13) < p.y_min)  // outside the certified domain (far below black): that pixel pair exactly
-    flags |= (y02 < p.y_min ? 5u : 0u) | (y13 < p.y_min ? 10u : 0u);
-  return flags;
+  uint32_t s01[6], s23[6];
+  const float y01 = chain_pair<false>(p, g8_base, stab_bias, F2{r[0], r[1]}, F2{g[0], g[1]}, F2{b[0], b[1]}, s01, nullptr);
+  const float y23 = chain_pair<false>(p, g8_base, stab_bias, F2{r[2], r[3]}, F2{g[2], g[3]}, F2{b[2], b[3]}, s23, nullptr);
+  const uint32_t c[12] = {s01[0], s01[2], s01[4], s01[1], s01[3], s01[5], s23[0], s23[2], s23[4], s23[1], s23[3], s23[5]};
+  return pack_and_certify(p, c, y01, y23, 3u, 12u, words);
 }
 
 __device__ __forceinline__ int atoms_add(uint32_t addr, int v) {  // plain shared-memory atomic (no warp aggregation)
@@ -415,18 +498,21 @@ __device__ __forceinline__ int atoms_add(uint32_t addr, int v) {  // plain share
   return old;
 }
 
-// GF0 / AR0: Bayer phase of even rows of the cropped frame — the row starts with green / its other colour is red.
-// Odd rows are the opposite on both counts (green sits on one diagonal, red and blue on the other).
-template <int NT, bool GF0, bool AR0>
+// MODE 0..3: RGB Bayer, bit 1 = GF0 (even rows of the cropped frame start with green), bit 0 = AR0 (their other colour
+// is red); odd rows are the opposite on both counts (green sits on one diagonal, red and blue on the other).
+// MODE 4: any other three-colour pattern up to 12 x 12 (X-Trans): row-major tile, per-position tap masks.
+template <int NT, int MODE>
 __global__ void __launch_bounds__(NT, NT == 512 ? 2 : 1)
 k_spec8(const __grid_constant__ SpecParams p, const __grid_constant__ CfaDev cfa, const __grid_constant__ ColorParams P,
         const __grid_constant__ CUtensorMap tmap) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   SmemSpec &sm = *reinterpret_cast<SmemSpec *>(smem_raw);
+  constexpr bool BAYER = MODE < 4, GF0 = (MODE & 2) != 0, AR0 = (MODE & 1) != 0;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int ntiles = p.tiles_x * p.tiles_y;
   const uint32_t bar = smem_u32(&sm.mbar), bar_tab = smem_u32(&sm.mbar_tab), raw_addr = smem_u32(sm.raw);
   const uint32_t qn_addr = smem_u32(&sm.qn);
+  const uint8_t *pat = BAYER ? nullptr : sm.pat;   // the exact path's pattern kind
 
   int tyi = (int)blockIdx.x / p.tiles_x, txi = (int)blockIdx.x - tyi * p.tiles_x;
   const int step_y = (int)gridDim.x / p.tiles_x, step_x = (int)gridDim.x - step_y * p.tiles_x;
@@ -465,6 +551,23 @@ k_spec8(const __grid_constant__ SpecParams p, const __grid_constant__ CfaDev cfa
   }
   const uint32_t phase = (uint32_t)cfa.pat[0] | ((uint32_t)cfa.pat[1] << 2) | ((uint32_t)cfa.pat[48] << 4) | ((uint32_t)cfa.pat[49] << 6);
   const uint32_t thr_base = smem_u32(sm.thr);
+  if (!BAYER) {
+    // demosaic.rs:77-90 for every position of the period: which of the nine 3x3 taps feed which colour (taps of the
+    // centre's own colour other than the centre itself are discarded)
+    for (int pos = tid; pos < p.pw * p.ph; pos += NT) {
+      const int pr = pos / p.pw, pc = pos - pr * p.pw;
+      const int pix = cfa.pat[pr * 48 + pc];
+      uint32_t m[3] = {0u, 0u, 0u};
+      int i = 0;
+      for (int dy = -1; dy <= 1; dy++)
+        for (int dx = -1; dx <= 1; dx++, i++) {
+          const int oc = cfa.pat[((pr + 48 + dy) % 48) * 48 + (pc + 48 + dx) % 48];
+          if ((oc != pix || (dx == 0 && dy == 0)) && oc < 3) m[oc] |= 1u << i;
+        }
+      sm.taps[pos] = make_uint2(m[0] | (m[1] << 16), m[2]);
+      sm.pat[pos] = (uint8_t)pix;
+    }
+  }
   for (int i = tid; i < 260; i += NT) sm.thr[i] = i < 255 ? __ldg(p.thr8 + i) : __int_as_float(0x7f800000);
   for (int i = tid; i < (int)(sizeof(SpecParams) / 4); i += NT) reinterpret_cast<uint32_t *>(&sm.sp)[i] = reinterpret_cast<const uint32_t *>(&p)[i];
   for (int i = tid; i < (int)(sizeof(ColorParams) / 4); i += NT) reinterpret_cast<uint32_t *>(&sm.cp)[i] = reinterpret_cast<const uint32_t *>(&P)[i];
@@ -501,8 +604,13 @@ k_spec8(const __grid_constant__ SpecParams p, const __grid_constant__ CfaDev cfa
         }
         const int r = gi / (kTileStride / 8), g = gi - r * (kTileStride / 8);
         float *row = &sm.plane[buf][r][0][0];
-        *reinterpret_cast<float4 *>(row + 4 * g) = make_float4(ev[0], ev[1], ev[2], ev[3]);
-        *reinterpret_cast<float4 *>(row + kPS + 4 * g) = make_float4(od[0], od[1], od[2], od[3]);
+        if (BAYER) {
+          *reinterpret_cast<float4 *>(row + 4 * g) = make_float4(ev[0], ev[1], ev[2], ev[3]);
+          *reinterpret_cast<float4 *>(row + kPS + 4 * g) = make_float4(od[0], od[1], od[2], od[3]);
+        } else {  // row-major
+          *reinterpret_cast<float4 *>(row + 8 * g) = make_float4(ev[0], od[0], ev[1], od[1]);
+          *reinterpret_cast<float4 *>(row + 8 * g + 4) = make_float4(ev[2], od[2], ev[3], od[3]);
+        }
       }
     }
   };
@@ -526,7 +634,7 @@ k_spec8(const __grid_constant__ SpecParams p, const __grid_constant__ CfaDev cfa
       const int j = __ffs(flags) - 1;
       flags &= flags - 1u;
       if (pos < kQueueCap) sm.queue[pos] = entry + j;
-      else fixup_entry(sm.sp, sm.cp, sm.spl, phase, g8_base, thr_base, entry + j);
+      else fixup_entry(sm.sp, sm.cp, sm.spl, phase, pat, g8_base, thr_base, entry + j);
       pos++;
     }
   };
@@ -546,21 +654,47 @@ k_spec8(const __grid_constant__ SpecParams p, const __grid_constant__ CfaDev cfa
 #pragma unroll 1
     for (int r = warp; r < kTH; r += NT / 32) {
       const int y = ty0 + r;
-      // window: tile row r is frame row y-1; plane index of column x0 is 4 + 2 * lane
-      Window w;
-      const uint32_t a0 = tile_base + (uint32_t)(r * (2 * kPS) + 4 + 2 * lane) * 4u;
-      constexpr uint32_t RS = 2 * kPS * 4, OP = kPS * 4;
-      w.En = lds64f(a0); w.On = lds64f(a0 + OP);
-      w.Ec = lds64f(a0 + RS); w.Oc = lds64f(a0 + RS + OP);
-      w.Es = lds64f(a0 + 2 * RS); w.Os = lds64f(a0 + 2 * RS + OP);
-      w.e2c = lds32f(a0 + RS + 8); w.omc = lds32f(a0 + RS + OP - 4);
-      w.e2n = w.e2s = w.omn = w.oms = 0.0f;
-      const bool gf = ((y & 1) != 0) != GF0;  // rows alternate
-      if (gf) { w.e2n = lds32f(a0 + 8); w.e2s = lds32f(a0 + 2 * RS + 8); }
-      else { w.omn = lds32f(a0 + OP - 4); w.oms = lds32f(a0 + 2 * RS + OP - 4); }
       uint32_t words[3], flags;
-      if ((y & 1) == 0) flags = cheap_task<GF0, AR0>(p, g8_base, stab_bias, w, words);
-      else flags = cheap_task<!GF0, !AR0>(p, g8_base, stab_bias, w, words);
+      if (BAYER) {
+        // window: tile row r is frame row y-1; plane index of column x0 is 4 + 2 * lane
+        Window w;
+        const uint32_t a0 = tile_base + (uint32_t)(r * (2 * kPS) + 4 + 2 * lane) * 4u;
+        constexpr uint32_t RS = 2 * kPS * 4, OP = kPS * 4;
+        w.En = lds64f(a0); w.On = lds64f(a0 + OP);
+        w.Ec = lds64f(a0 + RS); w.Oc = lds64f(a0 + RS + OP);
+        w.Es = lds64f(a0 + 2 * RS); w.Os = lds64f(a0 + 2 * RS + OP);
+        w.e2c = lds32f(a0 + RS + 8); w.omc = lds32f(a0 + RS + OP - 4);
+        w.e2n = w.e2s = w.omn = w.oms = 0.0f;
+        const bool gf = ((y & 1) != 0) != GF0;  // rows alternate
+        if (gf) { w.e2n = lds32f(a0 + 8); w.e2s = lds32f(a0 + 2 * RS + 8); }
+        else { w.omn = lds32f(a0 + OP - 4); w.oms = lds32f(a0 + 2 * RS + OP - 4); }
+        if ((y & 1) == 0) flags = cheap_task<GF0, AR0>(p, g8_base, stab_bias, w, words);
+        else flags = cheap_task<!GF0, !AR0>(p, g8_base, stab_bias, w, words);
+      } else {
+        // 3 x 6 window of the row-major tile: rows y-1 .. y+1, columns x0-1 .. x0+4 (tile column of x0 is 8 + 4 * lane)
+        float w[3][6];
+        const uint32_t a0 = tile_base + (uint32_t)(r * kTileStride + 7 + 4 * lane) * 4u;
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+          const uint32_t a = a0 + (uint32_t)(k * kTileStride) * 4u;
+          float4 mid;
+          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(mid.x), "=f"(mid.y), "=f"(mid.z), "=f"(mid.w) : "r"(a + 4u));
+          w[k][0] = lds32f(a);
+          w[k][1] = mid.x; w[k][2] = mid.y; w[k][3] = mid.z; w[k][4] = mid.w;
+          w[k][5] = lds32f(a + 20u);
+        }
+        // position inside the period: n % d as n - mulhi(n, ceil(2^32 / d)) * d
+        const int xg = tx0 + 4 * lane;
+        const int pr = y - (int)__umulhi((uint32_t)y, p.rcp_ph) * p.ph;
+        int pc = xg - (int)__umulhi((uint32_t)xg, p.rcp_pw) * p.pw;
+        uint2 mm[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          mm[j] = sm.taps[pr * p.pw + pc];
+          pc = (pc + 1 == p.pw) ? 0 : pc + 1;
+        }
+        flags = cheap_task_generic(p, g8_base, stab_bias, w, mm, words);
+      }
       const uint32_t pix = pix0 + (uint32_t)r * (uint32_t)p.width;
       if (inner) {
         uint32_t *o4 = reinterpret_cast<uint32_t *>(p.out + (size_t)pix * 3);
@@ -609,7 +743,7 @@ k_spec8(const __grid_constant__ SpecParams p, const __grid_constant__ CfaDev cfa
     const int qn = min(sm.qn, kQueueCap);
     if (qn >= kQueueCap - 1024 || (!have_next && qn > 0)) {
       if (!(p.dbg & 1))
-        for (int i = tid; i < qn; i += NT) fixup_entry(sm.sp, sm.cp, sm.spl, phase, g8_base, thr_base, sm.queue[i]);
+        for (int i = tid; i < qn; i += NT) fixup_entry(sm.sp, sm.cp, sm.spl, phase, pat, g8_base, thr_base, sm.queue[i]);
       __syncthreads();
       if (tid == 0) {
         if (p.stats) atomicAdd(p.stats, (unsigned long long)sm.qn);
@@ -674,7 +808,9 @@ __global__ void k_spec_probe(const __grid_constant__ SpecParams p, const __grid_
       float ex[3];
       float tp[9];
       taps_from_frame(p, x0 + j, y, tp);
-      exact_bayer_linear(p, P, spl, phase, x0 + j, y, tp, ex);
+      float er, eg, eb;
+      exact_rgb_bayer(p, phase, x0 + j, y, tp, er, eg, eb);
+      exact_chain(p, P, spl, er, eg, eb, ex);
       for (int c = 0; c < 3; c++) ex[c] = fminf(fmaxf(ex[c], 0.0f), 1.0f);  // gamma.rs:21 clamps before the table
       const float *l = (j & 1) ? l13 : l02;
       const int h = j >> 1;
@@ -738,16 +874,33 @@ bool make_raw_tmap(CUtensorMap *map, const uint16_t *raw, size_t pitch_elems, si
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-template <int NT, bool GF0, bool AR0>
+template <int NT, int MODE>
 cudaError_t launch_variant(cudaStream_t s, const SpecParams &p, const CfaDev &cfa, const ColorParams &P,
                            const CUtensorMap &tmap, int ntiles, int sm_count) {
   const size_t smem = sizeof(SmemSpec);
   const int ctas = sm_count * (NT == 512 ? 2 : 1);
   const int grid = ntiles < ctas ? ntiles : ctas;
-  cudaError_t e = cudaFuncSetAttribute(k_spec8<NT, GF0, AR0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = cudaFuncSetAttribute(k_spec8<NT, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  k_spec8<NT, GF0, AR0><<<grid, NT, smem, s>>>(p, cfa, P, tmap);
+  k_spec8<NT, MODE><<<grid, NT, smem, s>>>(p, cfa, P, tmap);
   return cudaGetLastError();
+}
+
+// RGB Bayer: 2 x 2, green on one diagonal, red and blue on the other
+bool is_rgb_bayer(const CfaDev &cfa) {
+  if (cfa.width != 2 || cfa.height != 2) return false;
+  const int c0 = cfa.pat[0], c1 = cfa.pat[1], c2_ = cfa.pat[48], c3 = cfa.pat[49];
+  return (c1 == 1 && c2_ == 1 && ((c0 == 0 && c3 == 2) || (c0 == 2 && c3 == 0))) ||
+         (c0 == 1 && c3 == 1 && ((c1 == 0 && c2_ == 2) || (c1 == 2 && c2_ == 0)));
+}
+// any other pattern of colours 0..2 with a period the tap-mask table holds (X-Trans 6 x 6, 2 x 8, 12 x 12 ...)
+bool is_rgb_generic(const CfaDev &cfa) {
+  if (cfa.width < 2 || cfa.height < 2 || cfa.width > 12 || cfa.height > 12) return false;
+  if (48 % cfa.width != 0 || 48 % cfa.height != 0) return false;  // the 48 x 48 table must tile without a seam
+  for (int r = 0; r < cfa.height; r++)
+    for (int c = 0; c < cfa.width; c++)
+      if (cfa.pat[r * 48 + c] > 2) return false;
+  return true;
 }
 
 }  // namespace
@@ -756,15 +909,12 @@ const char *spec_last_error() { return g_spec_err; }
 
 bool spec_supported(const FusedArgs &a, const CfaDev &cfa, const ColorParams &P) {
   if (a.out_kind != kOutU8 || P.linear || P.use_e) return false;
-  if (cfa.width != 2 || cfa.height != 2) return false;
-  const int c0 = cfa.pat[0], c1 = cfa.pat[1], c2_ = cfa.pat[48], c3 = cfa.pat[49];
-  const bool bayer = (c1 == 1 && c2_ == 1 && ((c0 == 0 && c3 == 2) || (c0 == 2 && c3 == 0))) ||
-                     (c0 == 1 && c3 == 1 && ((c1 == 0 && c2_ == 2) || (c1 == 2 && c2_ == 0)));
-  if (!bayer) return false;
+  if (!is_rgb_bayer(cfa) && !is_rgb_generic(cfa)) return false;
   if (!a.use_tma || (a.crop_x % 8) != 0) return false;
   if ((reinterpret_cast<uintptr_t>(a.raw) & 15) || ((a.raw_pitch * sizeof(uint16_t)) & 15)) return false;
   if (a.width < 8 || a.height < 4) return false;
   if (a.width >= 65536 || a.out_row1 - a.out_row0 >= 65536) return false;  // queue entries are row << 16 | column
+  if (a.height >= (1u << 24)) return false;  // n % period by multiplication (k_spec8, generic patterns)
   return true;
 }
 
@@ -800,18 +950,25 @@ cudaError_t launch_fused_spec8(cudaStream_t s, const FusedArgs &a, const CfaDev 
     return cudaErrorInvalidValue;
   }
   const int ntiles = p.tiles_x * p.tiles_y;
+  p.pw = cfa.width; p.ph = cfa.height;
+  p.rcp_pw = (uint32_t)(0x100000000ull / (unsigned long long)cfa.width) + 1u;
+  p.rcp_ph = (uint32_t)(0x100000000ull / (unsigned long long)cfa.height) + 1u;
+  if (!is_rgb_bayer(cfa)) {
+    if (threads == 1024) return launch_variant<1024, 4>(s, p, cfa, P, tmap, ntiles, sm_count);
+    return launch_variant<512, 4>(s, p, cfa, P, tmap, ntiles, sm_count);
+  }
   const bool gf0 = cfa.pat[0] == 1;
   const bool ar0 = (gf0 ? cfa.pat[1] : cfa.pat[0]) == 0;
   const int variant = (threads == 1024 ? 4 : 0) | (gf0 ? 2 : 0) | (ar0 ? 1 : 0);
   switch (variant) {
-    case 0: return launch_variant<512, false, false>(s, p, cfa, P, tmap, ntiles, sm_count);
-    case 1: return launch_variant<512, false, true>(s, p, cfa, P, tmap, ntiles, sm_count);
-    case 2: return launch_variant<512, true, false>(s, p, cfa, P, tmap, ntiles, sm_count);
-    case 3: return launch_variant<512, true, true>(s, p, cfa, P, tmap, ntiles, sm_count);
-    case 4: return launch_variant<1024, false, false>(s, p, cfa, P, tmap, ntiles, sm_count);
-    case 5: return launch_variant<1024, false, true>(s, p, cfa, P, tmap, ntiles, sm_count);
-    case 6: return launch_variant<1024, true, false>(s, p, cfa, P, tmap, ntiles, sm_count);
-    default: return launch_variant<1024, true, true>(s, p, cfa, P, tmap, ntiles, sm_count);
+    case 0: return launch_variant<512, 0>(s, p, cfa, P, tmap, ntiles, sm_count);
+    case 1: return launch_variant<512, 1>(s, p, cfa, P, tmap, ntiles, sm_count);
+    case 2: return launch_variant<512, 2>(s, p, cfa, P, tmap, ntiles, sm_count);
+    case 3: return launch_variant<512, 3>(s, p, cfa, P, tmap, ntiles, sm_count);
+    case 4: return launch_variant<1024, 0>(s, p, cfa, P, tmap, ntiles, sm_count);
+    case 5: return launch_variant<1024, 1>(s, p, cfa, P, tmap, ntiles, sm_count);
+    case 6: return launch_variant<1024, 2>(s, p, cfa, P, tmap, ntiles, sm_count);
+    default: return launch_variant<1024, 3>(s, p, cfa, P, tmap, ntiles, sm_count);
   }
 }
 
@@ -825,6 +982,12 @@ cudaError_t launch_spec_selftest(cudaStream_t s, unsigned int *out2) {
 
 cudaError_t launch_spec_probe(cudaStream_t s, const FusedArgs &a, const CfaDev &cfa, const ColorParams &P,
                               const SpecTables &T, int sm_count) {
+  // Bayer frames only: the cheap demosaic of every pattern is exact, so what the probe measures — the colour chain from
+  // the demosaiced values on — does not depend on the pattern
+  if (!is_rgb_bayer(cfa)) {
+    g_spec_err = "spec probe: RGB Bayer frames only";
+    return cudaErrorInvalidValue;
+  }
   SpecParams p = T.consts;
   p.raw = a.raw; p.raw_pitch = (long long)a.raw_pitch;
   p.src_row0 = (int)a.src_row0; p.src_rows = (int)a.src_rows;

@@ -24,6 +24,8 @@ struct SpecParams {
   int out_row0, out_row1;
   uint8_t *out;
   int tiles_x, tiles_y;
+  int pw, ph;                 // CFA period (generic-pattern variant)
+  uint32_t rcp_pw, rcp_ph;    // floor(2^32 / period) + 1: n % d = n - mulhi(n, rcp) * d while n * d < 2^32
   // ---- exact path (fix-ups)
   float black, range, range_rc;
   int exact_rc;

@@ -45,6 +45,68 @@ def test_against_oracle_all_phases(ip, orc, ctx, cfa, w, h):
         assert_bit_exact(out8(ip, ctx, data, params), want, f"{cfa} {w}x{h} {threads} threads")
 
 
+def _xtrans_12():
+    """X-Trans tiled to the 12 x 12 period rawloader also accepts (144 characters)."""
+    rows = [common.XTRANS[6 * r:6 * r + 6] for r in range(6)]
+    return "".join((rows[r % 6] * 2) for r in range(12))
+
+
+GENERIC = {"xtrans": common.XTRANS, "2x8": "RGGBBGGR" * 2, "12x12": _xtrans_12(), "GGGG": "GGGG", "RRGB": "RRGB"}
+
+
+@pytest.mark.parametrize("name", list(GENERIC))
+@pytest.mark.parametrize("w,h", [(640, 360), (403, 131), (128, 32), (12, 10), (257, 97)])
+def test_generic_patterns_against_oracle(ip, orc, ctx, name, w, h):
+    """Three-colour patterns other than RGB Bayer (X-Trans 6 x 6, 2 x 8, 12 x 12, degenerate 2 x 2) take k_spec8's
+    generic mode: per-position tap masks, exact means (demosaic.rs:77-116), the same cheap colour chain."""
+    data = common.synth_cfa(w, h, seed=11 + w)
+    params = common.raw_params(cfa=GENERIC[name])
+    want = orc.pipeline_output_8bit(orc.make_pipeline(data, "raw", params))
+    for threads in (512, 1024):
+        ctx.set_spec(0.0, threads)
+        ctx.spec_stats(reset=True)
+        assert_bit_exact(out8(ip, ctx, data, params), want, f"{name} {w}x{h} {threads} threads")
+        if w % 8 == 0:  # rows on 16-byte boundaries: the TMA precondition of k_spec8 (other widths take k_fused_full)
+            assert ctx.spec_stats()["fixups"] > 0, "the speculative kernel did not run"
+    assert_bit_exact(out8(ip, ctx, data, params, spec=False), want, f"{name} {w}x{h} exact kernel")
+
+
+@pytest.mark.parametrize("crops", [(0, 0, 0, 8), (3, 5, 2, 16), (7, 1, 0, 0)])
+def test_generic_pattern_crops_and_busy_queue(ip, orc, ctx, crops):
+    """Crops shift the pattern's phase (left crops in multiples of 8 keep the TMA precondition); delta at the cap keeps
+    the queue busy, a dark frame overflows it: the exact path of the generic mode (exact_rgb_generic) on every pixel."""
+    params = common.raw_params(cfa=common.XTRANS, crops=crops)
+    data = common.synth_cfa(1160, 300, seed=17)
+    want = orc.pipeline_output_8bit(orc.make_pipeline(data, "raw", params))
+    assert_bit_exact(out8(ip, ctx, data, params), want, f"crops {crops}")
+    ctx.set_spec(7.9e-5, 1024)
+    assert_bit_exact(out8(ip, ctx, data, params), want, f"crops {crops}, busy queue")
+    dark = np.random.default_rng(5).integers(0, 30, (300, 1160)).astype(np.uint16)
+    ctx.spec_stats(reset=True)
+    got = out8(ip, ctx, dark, params)
+    assert_bit_exact(got, orc.pipeline_output_8bit(orc.make_pipeline(dark, "raw", params)), "all pixels recomputed")
+    assert ctx.spec_stats()["fixups"] >= got.size // 3 * 0.9
+
+
+def test_full_size_xtrans_spec_equals_exact_kernel(ip, ctx):
+    """BASELINE config 3 at full size (8256 x 5504 X-Trans): speculative kernel == exact fused kernel, both CTA sizes."""
+    w, h = 8256, 5504
+    d_raw = ip.synth_cfa_u16(common.SEED + 2, w, 0, h, ctx=ctx)
+    src = ip.ImageSource.Raw(d_raw, w, h)
+    params = common.raw_params(cfa=common.XTRANS)
+    outs = []
+    for spec, threads in ((False, 512), (True, 512), (True, 1024)):
+        ctx.set_spec(0.0, threads)
+        p = ip.Pipeline.new_from_source(src, ctx=ctx)
+        common.fill_ipb_ops(p.ops, params)
+        p.set_speculative(spec)
+        ctx.spec_stats(reset=True)
+        outs.append(p.output_8bit().to_numpy())
+        if spec:
+            assert 0 < ctx.spec_stats()["fixups"] < w * h * 0.1
+    assert np.array_equal(outs[0], outs[1]) and np.array_equal(outs[0], outs[2])
+
+
 @pytest.mark.parametrize("delta", [1e-7, 1e-6, 7.9e-5])
 def test_forced_bounds_do_not_change_the_bytes_when_larger(ip, orc, ctx, delta):
     """A larger delta only recomputes more pixels.  (A smaller one than certified voids the guarantee: 1e-7 is here to
