@@ -15,10 +15,11 @@
 //                actual matrices and curve, ipb_host.cu spec_error_bound; measured by ipb_spec_probe).
 //   certificate  a channel whose cheap value is farther than delta from every threshold has, by monotonicity, exactly
 //                the reference's byte.  One add and one mask per channel produce byte and distance together.
-//   fix-up       pixels with a channel inside +-delta of a threshold (about 1 %), and the frame's border pixels, are
-//                queued in shared memory and recomputed by the bit-exact code of ipb_device.cuh (same arithmetic as
-//                the per-op kernels and k_fused_full) from the raw frame, all threads of the CTA working on queue
-//                entries, then their bytes are stored over the cheap ones.
+//   fix-up       pixels with a channel inside +-delta of a threshold (about 2 %), and the frame's border pixels, are
+//                queued in shared memory per tile and recomputed by the bit-exact code of ipb_device.cuh (same
+//                arithmetic as the per-op kernels and k_fused_full) from the tile's level-mapped samples, which are
+//                still in shared memory: after the tile's barrier the first ceil(n / 32) warps take the n entries,
+//                the other warps go on with the next tile; the exact bytes are stored over the cheap ones.
 //
 // Result: byte-identical to k_fused_full / the oracle by construction, at about a third of the instructions.
 // Tile pipeline as in k_fused_full: persistent CTAs, raw u16 boxes by TMA (cp.async.bulk.tensor.2d + mbarrier) one
@@ -56,13 +57,14 @@ struct SmemFront {
   alignas(8) unsigned long long mbar;
   alignas(8) unsigned long long mbar_tab;
   int conv_ctr[2];
-  int qn, pad;
+  int qn[2];                                    // queue length of the tile being computed / the tile being recomputed
 };
-constexpr int kQueueCap = (kG8Offset - (int)sizeof(SmemFront)) / 4;
+constexpr int kQueueCap = kTW * kTH;            // every pixel of a tile: the queue cannot overflow
+static_assert(kG8Offset - (int)sizeof(SmemFront) - kQueueCap * 2 >= 0, "front part of the shared window is full");
 
 struct SmemSpec : SmemFront {
-  uint32_t queue[kQueueCap];                    // uncertified pixels: row << 16 | column (row inside the launch's output rows)
-  unsigned char fill[kG8Offset - (int)sizeof(SmemFront) - kQueueCap * 4];
+  uint16_t queue[kQueueCap];                    // uncertified pixels of the current tile: row * kTW + column inside the tile
+  unsigned char fill[kG8Offset - (int)sizeof(SmemFront) - kQueueCap * 2];
   uint32_t g8a[kSpecG8Entries];                 // {byte, threshold} fixed-point gamma table; 32 KB aligned: its
                                                 // entries are addressed by (bits & 0x7ffc) | base, one LOP3
   float plane[2][kTileRows][2][kPS];            // [buffer][tile row][even / odd columns][column / 2]
@@ -358,30 +360,19 @@ __device__ __forceinline__ void taps_from_frame(const SpecParams &p, int x, int 
     }
 }
 
-// The same taps with two aligned 4-byte loads per row instead of three 2-byte ones: a recomputed pixel's loads are
-// scattered (every lane its own sector), and it is the number of load instructions that the load/store unit pays for.
-// Rows start on 16-byte boundaries (the kernel's TMA precondition), so an even sample index is a 4-byte boundary.
-__device__ __forceinline__ void taps_from_frame_wide(const SpecParams &p, int x, int y, float t[9]) {
-  const int cx = p.crop_x + x - 1;                                   // sensor column of the left tap
-  const int b = min(max(cx & ~1, 0), (int)p.raw_pitch - 4);          // four samples b .. b+3 inside the row
-  const int d = cx - b;                                              // the left tap is sample d of them (-1 .. 3)
+// The nine level-mapped taps of tile pixel (row r, column c) from the tile's f32 planes in shared memory — the very values
+// the cheap pass read (gofloat.rs:127 applied once per sample by convert_tile).  Tile row r + 1 is frame row ty0 + r, tile
+// column c + 8 is frame column tx0 + c.  ROWMAJOR: the generic-pattern layout; otherwise even / odd columns in two planes.
+template <bool ROWMAJOR>
+__device__ __forceinline__ void taps_from_tile(uint32_t tile_base, int r, int c, float t[9]) {
 #pragma unroll
-  for (int dy = -1; dy <= 1; dy++) {
-    const int yy = y + dy;
-    uint32_t w0 = 0, w1 = 0;
-    if (yy >= 0 && yy < p.height) {
-      const uint32_t *row = reinterpret_cast<const uint32_t *>(p.raw + (long long)(yy + p.crop_y - p.src_row0) * p.raw_pitch + b);
-      w0 = __ldg(row);
-      w1 = __ldg(row + 1);
-    }
-    const unsigned long long v = ((unsigned long long)w1 << 32) | w0;
+  for (int dy = 0; dy < 3; dy++)
 #pragma unroll
-    for (int k = 0; k < 3; k++) {
-      const int j = d + k;
-      const uint32_t sample = (j >= 0 && j < 4) ? (uint32_t)(v >> (16 * j)) & 0xffffu : 0u;  // out of the row: unused tap
-      t[(dy + 1) * 3 + k] = fminf(div_rc((float)sample - p.black, p.range, p.range_rc), 1.0f);
+    for (int dx = 0; dx < 3; dx++) {
+      const int tc = c + 7 + dx;
+      const int idx = ROWMAJOR ? (r + dy) * kTileStride + tc : (r + dy) * (2 * kPS) + (tc & 1) * kPS + (tc >> 1);
+      t[dy * 3 + dx] = lds32f(tile_base + (uint32_t)idx * 4u);
     }
-  }
 }
 
 // output8bit(apply_srgb_gamma(clamp(v))) (gamma.rs:21, color_conversions.rs:323-325) exactly, from shared memory only:
@@ -397,17 +388,23 @@ __device__ __forceinline__ uint32_t gamma8_exact(uint32_t g8_base, uint32_t thr_
   return lo + (vc >= t0 ? 1u : 0u) + (vc >= t1 ? 1u : 0u);
 }
 
-// queue entry: (row inside the launch's output rows) << 16 | column.  Out of line: the exact path keeps its registers
-// (and the instruction cache footprint of its ~450 instructions) to itself; p and P are the copies in shared memory.
+// queue entry: row * kTW + column inside the tile whose planes start at tile_base and whose first pixel is (tx0, ty0).
+// Out of line: the exact path keeps its registers (and the instruction cache footprint of its ~400 instructions) to
+// itself; p and P are the copies in shared memory.
 __device__ __noinline__ void fixup_entry(const SpecParams &p, const ColorParams &P, const float (*spl)[8], uint32_t phase,
-                                         const uint8_t *pat, uint32_t g8_base, uint32_t thr_base, uint32_t entry) {
-  const int row = (int)(entry >> 16), x = (int)(entry & 0xffffu), y = p.out_row0 + row;
-  float t[9], v[3], r, g, b;
-  taps_from_frame_wide(p, x, y, t);
-  if (pat) exact_rgb_generic(p, pat, x, y, t, r, g, b);   // uniform: one pattern kind per launch
-  else exact_rgb_bayer(p, phase, x, y, t, r, g, b);
-  exact_chain(p, P, spl, r, g, b, v);
-  uint8_t *o = p.out + ((size_t)row * (size_t)p.width + (size_t)x) * 3;
+                                         const uint8_t *pat, uint32_t g8_base, uint32_t thr_base, uint32_t tile_base, int tx0,
+                                         int ty0, uint32_t entry) {
+  const int r = (int)(entry / kTW), c = (int)(entry % kTW), x = tx0 + c, y = ty0 + r;
+  float t[9], v[3], cr, cg, cb;
+  if (pat) {   // uniform: one pattern kind per launch
+    taps_from_tile<true>(tile_base, r, c, t);
+    exact_rgb_generic(p, pat, x, y, t, cr, cg, cb);
+  } else {
+    taps_from_tile<false>(tile_base, r, c, t);
+    exact_rgb_bayer(p, phase, x, y, t, cr, cg, cb);
+  }
+  exact_chain(p, P, spl, cr, cg, cb, v);
+  uint8_t *o = p.out + ((size_t)(y - p.out_row0) * (size_t)p.width + (size_t)x) * 3;
   o[0] = (uint8_t)gamma8_exact(g8_base, thr_base, v[0]);
   o[1] = (uint8_t)gamma8_exact(g8_base, thr_base, v[1]);
   o[2] = (uint8_t)gamma8_exact(g8_base, thr_base, v[2]);
@@ -511,7 +508,6 @@ k_spec8(const __grid_constant__ SpecParams p, const __grid_constant__ CfaDev cfa
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int ntiles = p.tiles_x * p.tiles_y;
   const uint32_t bar = smem_u32(&sm.mbar), bar_tab = smem_u32(&sm.mbar_tab), raw_addr = smem_u32(sm.raw);
-  const uint32_t qn_addr = smem_u32(&sm.qn);
   const uint8_t *pat = BAYER ? nullptr : sm.pat;   // the exact path's pattern kind
 
   int tyi = (int)blockIdx.x / p.tiles_x, txi = (int)blockIdx.x - tyi * p.tiles_x;
@@ -524,7 +520,8 @@ k_spec8(const __grid_constant__ SpecParams p, const __grid_constant__ CfaDev cfa
   if (tid == 0) {
     sm.conv_ctr[0] = 0;
     sm.conv_ctr[1] = 0;
-    sm.qn = 0;
+    sm.qn[0] = 0;
+    sm.qn[1] = 0;
     mbar_init(bar, 1);
     mbar_init(bar_tab, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -626,26 +623,27 @@ k_spec8(const __grid_constant__ SpecParams p, const __grid_constant__ CfaDev cfa
   }
   mbar_wait(bar_tab, 0);
 
-  // queue the uncertified pixels of a task (entry = row << 16 | column of its first pixel); a full queue recomputes
-  // right away — the cheap bytes are already stored by this very thread, so the exact ones land on top
-  auto push = [&](uint32_t flags, uint32_t entry) {
-    int pos = atoms_add(qn_addr, __popc(flags));
+  // queue the uncertified pixels of a task (entry = row * kTW + column of its first pixel, inside the tile); the queue
+  // holds a whole tile, so it cannot overflow
+  auto push = [&](uint32_t qaddr, uint32_t flags, uint32_t entry) {
+    int pos = atoms_add(qaddr, __popc(flags));
     while (flags) {
       const int j = __ffs(flags) - 1;
       flags &= flags - 1u;
-      if (pos < kQueueCap) sm.queue[pos] = entry + j;
-      else fixup_entry(sm.sp, sm.cp, sm.spl, phase, pat, g8_base, thr_base, entry + j);
-      pos++;
+      sm.queue[pos++] = (uint16_t)(entry + j);
     }
   };
   // whole words can be stored when every row starts on a 4-byte boundary
   const bool rows_aligned = ((reinterpret_cast<uintptr_t>(p.out) & 3) == 0) && ((p.width & 3) == 0);
 
   int it = 0;
+  int fix_warps = 0;                 // warps that recomputed pixels of the previous tile at the top of this iteration
+  unsigned long long nfix = 0;       // thread 0: pixels recomputed by this CTA
   for (int t = blockIdx.x; t < ntiles; t += gridDim.x, it++) {
     const int ty0 = p.out_row0 + tyi * kTH, tx0 = txi * kTW;
     next_tile(txi, tyi);
     const uint32_t tile_base = smem_u32(&sm.plane[it & 1][0][0][0]);
+    const uint32_t qaddr = smem_u32(&sm.qn[it & 1]);
     // a tile is "inner" when all its pixels exist, are wanted, and have their nine taps inside the frame
     const bool inner = rows_aligned && ty0 >= 1 && ty0 + kTH <= p.height - 1 && ty0 + kTH <= p.out_row1 && tx0 >= 1 &&
                        tx0 + kTW <= p.width - 1;
@@ -699,7 +697,7 @@ k_spec8(const __grid_constant__ SpecParams p, const __grid_constant__ CfaDev cfa
       if (inner) {
         uint32_t *o4 = reinterpret_cast<uint32_t *>(p.out + (size_t)pix * 3);
         o4[0] = words[0]; o4[1] = words[1]; o4[2] = words[2];
-        if (flags && !(p.dbg & 2)) push(flags, ((uint32_t)(y - p.out_row0) << 16) | (uint32_t)(tx0 + 4 * lane));
+        if (flags && !(p.dbg & 2)) push(qaddr, flags, (uint32_t)(r * kTW + 4 * lane));
       } else {
         const int x0 = tx0 + 4 * lane;
         const bool live = y < p.out_row1 && x0 < p.width;
@@ -719,39 +717,50 @@ k_spec8(const __grid_constant__ SpecParams p, const __grid_constant__ CfaDev cfa
           if (x0 < 1) flags |= 1u;
           if (x0 + 3 > p.width - 2) flags |= 0xfu & ~((1u << max(p.width - 1 - x0, 0)) - 1u);
           flags &= (1u << npx) - 1u;
-          if (flags) push(flags, ((uint32_t)(y - p.out_row0) << 16) | (uint32_t)x0);
+          if (flags) push(qaddr, flags, (uint32_t)(r * kTW + 4 * lane));
         }
       }
     }
 
     const bool have_next = t + (int)gridDim.x < ntiles;
+    // The conversion below overwrites the planes of the previous tile, which the warps that recompute that tile's
+    // queued pixels are still reading: they arrive on barrier 1 when they are done, the other warps wait for them here
+    // (seldom for long: recomputing takes about as long as one row of the cheap pass, and a warp has at least two).
+    if (fix_warps > 0 && warp >= fix_warps) asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory");
     if (have_next) {
       mbar_wait(bar, (it + 1) & 1);
       convert_tile((it + 1) & 1, (it + 1) & 1);
     }
-    if (tid == 0) sm.conv_ctr[it & 1] = 0;
+    if (tid == 0) {
+      sm.conv_ctr[it & 1] = 0;
+      sm.qn[(it + 1) & 1] = 0;   // the next tile's queue length; its last readers passed the second barrier of the previous iteration
+    }
     __syncthreads();
     if (tid == 0 && t + 2 * (int)gridDim.x < ntiles) {
       int ntx = txi, nty = tyi;
       next_tile(ntx, nty);
       issue_tile(p, &tmap, raw_addr, bar, ntx, nty);
     }
-    // Uncertified pixels are recomputed exactly when the queue is nearly full and after the last tile, densely: every
-    // thread takes entries, all lanes busy.  What bounds this step is the number of scattered load / store
-    // instructions (each lane its own sector), which is why the exact path loads its taps as six words, reads its
-    // gamma thresholds from shared memory, and runs rarely.  The barrier above ordered every push before this read.
-    const int qn = min(sm.qn, kQueueCap);
-    if (qn >= kQueueCap - 1024 || (!have_next && qn > 0)) {
-      if (!(p.dbg & 1))
-        for (int i = tid; i < qn; i += NT) fixup_entry(sm.sp, sm.cp, sm.spl, phase, pat, g8_base, thr_base, sm.queue[i]);
-      __syncthreads();
-      if (tid == 0) {
-        if (p.stats) atomicAdd(p.stats, (unsigned long long)sm.qn);
-        sm.qn = 0;
-      }
-      __syncthreads();
+    // Uncertified pixels of this tile are recomputed exactly from the tile's planes, densely: entry i goes to thread i, so
+    // the first ceil(n / 32) warps do the work with all lanes busy while the others start the next tile.  The barrier
+    // above ordered every push before these reads; the one below frees the queue for the next tile's pushes.
+    const int qn = sm.qn[it & 1];
+    const bool recompute = !(p.dbg & 1);
+    if (qn > NT && recompute)   // more than one entry per thread (dark frames, the bound at its cap): all threads, right here
+      for (int i = NT + tid; i < qn; i += NT)
+        fixup_entry(sm.sp, sm.cp, sm.spl, phase, pat, g8_base, thr_base, tile_base, tx0, ty0, sm.queue[i]);
+    const uint32_t mine = tid < qn ? (uint32_t)sm.queue[tid] : 0xffffffffu;
+    __syncthreads();
+    if (tid == 0) nfix += (unsigned long long)qn;
+    fix_warps = min((qn + 31) >> 5, NT / 32);
+    if (warp < fix_warps) {
+      if (mine != 0xffffffffu && recompute)
+        fixup_entry(sm.sp, sm.cp, sm.spl, phase, pat, g8_base, thr_base, tile_base, tx0, ty0, mine);
+      if (have_next) asm volatile("bar.arrive 1, %0;" ::"n"(NT) : "memory");
     }
+    if (!have_next) fix_warps = 0;
   }
+  if (tid == 0 && p.stats && nfix) atomicAdd(p.stats, nfix);
 }
 
 // ---------------------------------------------------------------- probe: cheap vs exact linear values
