@@ -61,7 +61,7 @@ def select_workload(name):
         OUT_W, OUT_H = 1500, 1000
         WORKLOAD_NAME = ("C4: 6000x4000 RGGB Bayer -> 1500x1000 8-bit sRGB (4x down-scale inside the demosaic op, "
                          "scaled_demosaic), frames round-robin over the GPUs")
-        KERNEL_NAME, TRAFFIC_KEY = "k_fused_scaled<u8>", "k_fused_scaled<u8> C4 6000x4000->1500x1000"
+        KERNEL_NAME, TRAFFIC_KEY = "k_spec8_scaled (speculative 8-bit kernel behind scaled_demosaic)", "k_spec8_scaled C4 6000x4000->1500x1000"
         ALGO_BYTES_PER_PX = 2 + 3.0 * OUT_W * OUT_H / (W * H)  # per INPUT pixel: 2.1875
     MP = W * H / 1e6
 

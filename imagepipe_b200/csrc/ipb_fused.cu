@@ -28,7 +28,12 @@
 // reference's f32 arithmetic (tests/test_gpu_fused*.py compare against the CPU oracle bit for bit).
 #include <cuda.h>  // CUtensorMap (types only; cuTensorMapEncodeTiled is resolved at run time, no libcuda link)
 
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
 #include "ipb_internal.h"
+#include "ipb_scaled.cuh"
 
 namespace ipb {
 
@@ -741,27 +746,6 @@ k_fused_full(const __grid_constant__ FullParams p, const __grid_constant__ CfaDe
   }
 }
 
-// ---------------------------------------------------------------------------------------- scaled demosaic
-
-struct ScaledParams {
-  const uint16_t *raw;
-  long long raw_pitch;
-  int src_row0, src_rows;
-  int crop_x, crop_y;
-  int width, height;            // cropped source frame
-  int nwidth, nheight;          // output frame
-  int out_row0, out_row1;
-  void *out;
-  float black, range, range_rc;
-  int exact_rc;
-  const float2 *lut_lab, *lut_gamma;
-  float skip_x, skip_y;         // skip_x_x, skip_y_y of scaling.rs:69-72 (skip_x_y == skip_y_x == 0 here)
-  int bayer;                    // 2x2 pattern with green on one diagonal and red / blue on the other
-};
-
-constexpr int kPatStride = 56;   // pattern row: 48 columns + the first 8 again, so that x % 48 + k needs no wrap
-constexpr int kMaxCols = 8;      // widest window the register-resident fast path handles (scale < 7)
-
 struct SmemScaled {
   float2 lut_lab[kLutEntries];
   float2 lut_gamma[kLutEntries];
@@ -770,110 +754,6 @@ struct SmemScaled {
 };
 
 constexpr int kNTScaled = 1024;
-
-__device__ __forceinline__ int f2i_sat(float f) {  // Rust `f as usize` for the values met here (>= 0, < 2^31)
-  return (int)min(__float2uint_rz(f), 0x7fffffffu);
-}
-
-// sums[c] += vf; counts[c] += f when cond, as two predicated scalar adds (a predicated packed add is lowered to an
-// unpredicated FFMA2 plus two selects, which costs more issue slots than this)
-__device__ __forceinline__ void add_if(F2 &acc, float vf, float f, bool cond) {
-  asm("{ .reg .pred q; setp.ne.s32 q, %2, 0; @q add.rn.f32 %0, %0, %3; @q add.rn.f32 %1, %1, %4; }"
-      : "+f"(acc.x), "+f"(acc.y) : "r"((int)cond), "f"(vf), "f"(f));
-}
-
-// u16 -> f32 without the conversion unit: 0x4B000000 | v is the float 2^23 + v, and subtracting 2^23 is exact
-__device__ __forceinline__ float u16_to_float(uint32_t v) { return __uint_as_float(0x4B000000u | v) - 8388608.0f; }
-
-// The taps of one output pixel whose window is at most NX columns wide (scaling.rs:91-118, CFA mode).  Columns k >= nx
-// of a narrower window (frame edge, or a lane whose window is narrower than its warp's) get weight 0 and re-read the
-// window's last column: they add (+-0, 0) to the accumulators, which changes neither a sum nor a count (neither is
-// ever -0.0: both start at +0.0).
-template <int NX, bool UNIFORM, int NC>
-__device__ __forceinline__ void window_taps(const ScaledParams &p, const uint8_t *pat, float one, int from_x, int nx,
-                                            int from_y, int to_y, float center_x, float center_y, F2 acc[4]) {
-  const float black = p.black, range = p.range, rc = p.range_rc, skip_x = p.skip_x, skip_y = p.skip_y;
-  float ax[NX];  // 1.0 - delta_x*delta_x of window column k
-#pragma unroll
-  for (int k = 0; k < NX; k++) {
-    const float delta_x = __fdiv_rn((float)(from_x + k) - center_x, skip_x);
-    ax[k] = 1.0f - (delta_x * delta_x);
-  }
-  int ym = from_y % 48;
-  const uint8_t *pcol = pat + from_x % 48;
-  const uint16_t *rowp = p.raw + (long long)(from_y + p.crop_y - p.src_row0) * p.raw_pitch + p.crop_x + from_x;
-  for (int y = from_y; y <= to_y; y++, rowp += p.raw_pitch) {
-    const float delta_y = __fdiv_rn((float)y - center_y, skip_y);
-    const float dy2 = delta_y * delta_y;
-    const uint8_t *prow = pcol + ym * kPatStride;
-    ym = ym == 47 ? 0 : ym + 1;
-#pragma unroll
-    for (int k = 0; k < NX; k++) {
-      const bool valid = UNIFORM || k < nx;
-      float factor = ax[k] - dy2;
-      factor = factor < 0.0f ? 0.0f : factor;
-      if (!UNIFORM) factor = valid ? factor : 0.0f;
-      const int kk = UNIFORM ? k : min(k, nx - 1);
-      const int c = prow[kk];
-      const float v = fminf(div_rc(u16_to_float(__ldg(rowp + kk)) - black, range, rc), 1.0f);  // gofloat.rs:127
-      const float vf = v * factor;
-#pragma unroll
-      for (int j = 0; j < NC; j++) add_if(acc[j], vf, factor, c == j);
-    }
-  }
-}
-
-// One window row of an RGB Bayer frame.  RP = parity of the row relative to the window's first row.  In a Bayer mosaic
-// green sits on one diagonal, so whether window column k of this row is green depends only on (RP + k) & 1 and on
-// one per-lane bit — is the window's top-left sample green (g00) — and the row's other colour is the same for the
-// whole row.  Green taps go to `g`, the others to `xacc` (the caller keeps one per relative row parity and maps the
-// two to red / blue at the end): no colour look-up, no comparisons, four predicated adds per tap.  Each colour still
-// receives its taps in raster order, like the reference's sums[c] / counts[c].
-template <int NX, bool UNIFORM, int RP>
-__device__ __forceinline__ void bayer_row(const uint16_t *rowp, const float ax[NX], float dy2, int nx, bool g00, float black,
-                                          float range, float rc, F2 &g, F2 &xacc) {
-#pragma unroll
-  for (int k = 0; k < NX; k++) {
-    float factor = ax[k] - dy2;
-    factor = factor < 0.0f ? 0.0f : factor;
-    if (!UNIFORM) factor = k < nx ? factor : 0.0f;
-    const int kk = UNIFORM ? k : min(k, nx - 1);
-    const float v = fminf(div_rc(u16_to_float(__ldg(rowp + kk)) - black, range, rc), 1.0f);  // gofloat.rs:127
-    const float vf = v * factor;
-    const bool green = ((RP + k) & 1) ? !g00 : g00;
-    add_if(g, vf, factor, green);
-    add_if(xacc, vf, factor, !green);
-  }
-}
-
-template <int NX, bool UNIFORM>
-__device__ __forceinline__ void window_taps_bayer(const ScaledParams &p, const CfaDev &cfa, int from_x, int nx, int from_y,
-                                                  int to_y, float center_x, float center_y, F2 acc[4]) {
-  const float black = p.black, range = p.range, rc = p.range_rc, skip_x = p.skip_x, skip_y = p.skip_y;
-  float ax[NX];
-#pragma unroll
-  for (int k = 0; k < NX; k++) {
-    const float delta_x = __fdiv_rn((float)(from_x + k) - center_x, skip_x);
-    ax[k] = 1.0f - (delta_x * delta_x);
-  }
-  const int py = from_y & 1, pxb = from_x & 1;
-  const bool g00 = cfa.pat[py * 48 + pxb] == 1;
-  F2 g{0.f, 0.f}, x0{0.f, 0.f}, x1{0.f, 0.f};
-  const uint16_t *rowp = p.raw + (long long)(from_y + p.crop_y - p.src_row0) * p.raw_pitch + p.crop_x + from_x;
-  for (int y = from_y; y <= to_y; y += 2, rowp += 2 * p.raw_pitch) {
-    float delta_y = __fdiv_rn((float)y - center_y, skip_y);
-    bayer_row<NX, UNIFORM, 0>(rowp, ax, delta_y * delta_y, nx, g00, black, range, rc, g, x0);
-    if (y + 1 <= to_y) {
-      delta_y = __fdiv_rn((float)(y + 1) - center_y, skip_y);
-      bayer_row<NX, UNIFORM, 1>(rowp + p.raw_pitch, ax, delta_y * delta_y, nx, g00, black, range, rc, g, x1);
-    }
-  }
-  // the non-green colour of the window's first row (0 = red or 2 = blue); the second row holds the other one
-  const int c0 = g00 ? cfa.pat[py * 48 + (pxb ^ 1)] : cfa.pat[py * 48 + pxb];
-  acc[1] = g;
-  acc[0] = c0 == 0 ? x0 : x1;
-  acc[2] = c0 == 0 ? x1 : x0;
-}
 
 // k_fused_scaled: one output pixel per thread (scaling.rs:76-127 with the CFA binning of :109-112), then the colour
 // chain.  The reference's per-tap arithmetic is kept expression by expression; what is shared between taps is
@@ -920,31 +800,22 @@ k_fused_scaled(const __grid_constant__ ScaledParams p, const __grid_constant__ C
     const bool live = idx < npix;
     const long long id = live ? idx : npix - 1;
     const int row = p.out_row0 + (int)(id / p.nwidth), col = (int)(id % p.nwidth);
-    const float frow = (float)row, frow1 = (float)(row + 1), fcol = (float)col, fcol1 = (float)(col + 1);
-    // scaling.rs:77-89 with topleft = (0,0), skip_x_y = skip_y_x = 0
-    const float rfrom_x = 0.0f + 0.0f * frow;
-    const float rto_x = 0.0f + 0.0f * frow1;
-    const float rfrom_y = 0.0f + p.skip_y * frow;
-    const float rto_y = 0.0f + p.skip_y * frow1;
-    const float rcenter_x = 0.0f + (0.0f * frow) + __fdiv_rn(0.0f, 2.0f) - 0.5f;
-    const float rcenter_y = 0.0f + (p.skip_y * frow) + __fdiv_rn(p.skip_y, 2.0f) - 0.5f;
-    const int from_x = min(p.width - 1, f2i_sat(floorf(rfrom_x + (p.skip_x * fcol))));
-    const int to_x = min(p.width - 1, f2i_sat(floorf(rto_x + (p.skip_x * fcol1))));
-    const int from_y = min(p.height - 1, f2i_sat(floorf(rfrom_y + (0.0f * fcol))));
-    const int to_y = min(p.height - 1, f2i_sat(floorf(rto_y + (0.0f * fcol1))));
-    const float center_x = rcenter_x + (p.skip_x * fcol) + __fdiv_rn(p.skip_x, 2.0f);
-    const float center_y = rcenter_y + (0.0f * fcol) + __fdiv_rn(0.0f, 2.0f);
+    const ScaledWindow win = scaled_window(p, row, col);
+    const int from_x = win.from_x, to_x = win.to_x, from_y = win.from_y, to_y = win.to_y;
+    const float center_x = win.center_x, center_y = win.center_y;
     const int nx = to_x - from_x + 1;
 
     F2 acc[4] = {F2{0.f, 0.f}, F2{0.f, 0.f}, F2{0.f, 0.f}, F2{0.f, 0.f}};  // {sums[c], counts[c]}
     const int nx_max = __reduce_max_sync(kFull, nx), nx_min = __reduce_min_sync(kFull, nx);
     if (nx_max <= kMaxCols && p.exact_rc && p.bayer) {
-      if (nx_max == 5 && nx_min == 5)
-        window_taps_bayer<5, true>(p, cfa, from_x, nx, from_y, to_y, center_x, center_y, acc);
-      else if (nx_max <= 6)
-        window_taps_bayer<6, false>(p, cfa, from_x, nx, from_y, to_y, center_x, center_y, acc);
-      else
-        window_taps_bayer<kMaxCols, false>(p, cfa, from_x, nx, from_y, to_y, center_x, center_y, acc);
+      if (nx_max == 5 && nx_min == 5) {
+        if (p.skip_rc_exact) window_taps_bayer<5, true, true>(p, cfa, from_x, nx, from_y, to_y, center_x, center_y, acc);
+        else window_taps_bayer<5, true, false>(p, cfa, from_x, nx, from_y, to_y, center_x, center_y, acc);
+      } else if (nx_max <= 6) {
+        window_taps_bayer<6, false, false>(p, cfa, from_x, nx, from_y, to_y, center_x, center_y, acc);
+      } else {
+        window_taps_bayer<kMaxCols, false, false>(p, cfa, from_x, nx, from_y, to_y, center_x, center_y, acc);
+      }
     } else if (nx_max <= kMaxCols && p.exact_rc && !four) {
       if (nx_max == 5 && nx_min == 5)
         window_taps<5, true, 3>(p, sm.pat, P.one, from_x, nx, from_y, to_y, center_x, center_y, acc);
@@ -1136,9 +1007,39 @@ cudaError_t launch_fused_full(cudaStream_t s, const FusedArgs &a, const CfaDev &
   }
 }
 
-cudaError_t launch_fused_scaled(cudaStream_t s, const FusedArgs &a, const CfaDev &cfa, const ColorParams &P,
-                                int sm_count) {
-  if (a.out_row1 <= a.out_row0 || a.out_width == 0) return cudaSuccess;
+// Does the three-instruction reciprocal form of (coordinate - centre) / skip give the IEEE quotient for every tap of every
+// window of this frame?  The kernel's coordinate arithmetic (k_fused_scaled, scaling.rs:77-89,94-98) is repeated here in
+// the same f32 expressions, column by column and row by row.  A few ten thousand divisions per distinct frame geometry.
+static bool scaled_skip_rc_exact(int width, int height, int nwidth, int nheight, float skip_x, float skip_y) {
+  const float rcx = 1.0f / skip_x, rcy = 1.0f / skip_y;
+  if (!std::isnormal(skip_x) || !std::isnormal(skip_y) || !std::isnormal(rcx) || !std::isnormal(rcy)) return false;
+  auto sat = [](float f) { return f >= 2147483648.0f ? 0x7fffffff : (f > 0.0f ? (int)f : 0); };
+  auto same = [](float num, float d, float rc) {
+    const float q = num * rc, r = fmaf(-q, d, num), q2 = fmaf(r, rc, q), ref = num / d;
+    return memcmp(&q2, &ref, 4) == 0;
+  };
+  for (int col = 0; col < nwidth; col++) {
+    const float fcol = (float)col, fcol1 = (float)(col + 1);
+    const float rcenter_x = 0.0f + (0.0f * 0.0f) + (0.0f / 2.0f) - 0.5f;
+    const int from_x = std::min(width - 1, sat(floorf(0.0f + (skip_x * fcol))));
+    const int to_x = std::min(width - 1, sat(floorf(0.0f + (skip_x * fcol1))));
+    const float center_x = rcenter_x + (skip_x * fcol) + (skip_x / 2.0f);
+    for (int x = from_x; x <= to_x; x++)
+      if (!same((float)x - center_x, skip_x, rcx)) return false;
+  }
+  for (int row = 0; row < nheight; row++) {
+    const float frow = (float)row, frow1 = (float)(row + 1);
+    const float rcenter_y = 0.0f + (skip_y * frow) + (skip_y / 2.0f) - 0.5f;
+    const int from_y = std::min(height - 1, sat(floorf((0.0f + skip_y * frow) + 0.0f)));
+    const int to_y = std::min(height - 1, sat(floorf((0.0f + skip_y * frow1) + 0.0f)));
+    const float center_y = rcenter_y + 0.0f + (0.0f / 2.0f);
+    for (int y = from_y; y <= to_y; y++)
+      if (!same((float)y - center_y, skip_y, rcy)) return false;
+  }
+  return true;
+}
+
+void fill_scaled_params(const FusedArgs &a, const CfaDev &cfa, ScaledParams *out) {
   ScaledParams p;
   p.raw = a.raw; p.raw_pitch = (long long)a.raw_pitch;
   p.src_row0 = (int)a.src_row0; p.src_rows = (int)a.src_rows;
@@ -1153,6 +1054,31 @@ cudaError_t launch_fused_scaled(cudaStream_t s, const FusedArgs &a, const CfaDev
   p.skip_x = ((float)((long)a.width - 1) - 0.0f) / (float)(a.out_width - 1);
   p.skip_y = ((float)((long)a.height - 1) - 0.0f) / (float)(a.out_height - 1);
   p.bayer = is_rgb_bayer(cfa) ? 1 : 0;
+  p.skip_x_rc = 1.0f / p.skip_x;
+  p.skip_y_rc = 1.0f / p.skip_y;
+  {
+    // the check depends on the frame geometry only: remembered for the last one (frames of a batch share it)
+    struct Memo { int w, h, nw, nh, ok; };
+    thread_local Memo memo = {0, 0, 0, 0, 0};
+    if (memo.w != p.width || memo.h != p.height || memo.nw != p.nwidth || memo.nh != p.nheight) {
+      memo = {p.width, p.height, p.nwidth, p.nheight,
+              scaled_skip_rc_exact(p.width, p.height, p.nwidth, p.nheight, p.skip_x, p.skip_y) ? 1 : 0};
+    }
+    p.skip_rc_exact = memo.ok;
+  }
+  {
+    const bool integral = a.black >= 0.0f && a.black < 4194304.0f && a.black == floorf(a.black);
+    p.sub_a = integral ? -(8388608.0f + a.black) : -8388608.0f;
+    p.sub_b = integral ? 0.0f : -a.black;
+  }
+  *out = p;
+}
+
+cudaError_t launch_fused_scaled(cudaStream_t s, const FusedArgs &a, const CfaDev &cfa, const ColorParams &P,
+                                int sm_count) {
+  if (a.out_row1 <= a.out_row0 || a.out_width == 0) return cudaSuccess;
+  ScaledParams p;
+  fill_scaled_params(a, cfa, &p);
   const long long npix = (long long)(p.out_row1 - p.out_row0) * p.nwidth;
   long long blocks = (npix + kNTScaled - 1) / kNTScaled;
   const int grid = (int)(blocks < sm_count ? blocks : sm_count);

@@ -1629,7 +1629,8 @@ static int launch_fused_rows(ipb_pipeline *p, const FusedPlan &plan, const Color
   a.lut_lab = ctx->lut_lab;
   a.lut_gamma = ctx->lut_gamma;
   a.lut_gamma8 = ctx->lut_gamma8;
-  if (plan.mode == kFusedFull) IPB_TRY(ensure_cbrt_table(ctx));
+  const bool scaled_spec = plan.mode == kFusedScaled && p->spec && out_kind == kOutU8;
+  if (plan.mode == kFusedFull || scaled_spec) IPB_TRY(ensure_cbrt_table(ctx));
   a.cbrt_tab = ctx->cbrt_tab;
   a.use_tma = p->use_tma;
   // 8-bit output of a full-resolution RGB Bayer frame: the speculative kernel (byte-identical, about a third of the
@@ -1640,6 +1641,17 @@ static int launch_fused_rows(ipb_pipeline *p, const FusedPlan &plan, const Color
     if (use) {
       cudaError_t es = launch_fused_spec8(ctx->stream, a, plan.cfa, P, ctx->spec_tab, ctx->sm_count, ctx->spec_threads);
       if (es != cudaSuccess) return fail(ctx, IPB_ERR_CUDA, "speculative kernel: %s %s", cudaGetErrorString(es), spec_last_error());
+      ctx->launches++;
+      return IPB_OK;
+    }
+  }
+  // ... and of a down-scaled one: the same chain behind scaled_demosaic's window phase
+  if (scaled_spec && spec_scaled_supported(a, plan.cfa, P)) {
+    bool use = false;
+    IPB_TRY(ensure_spec_tables(ctx, P, a.black, a.range, &use));
+    if (use) {
+      cudaError_t es = launch_scaled_spec8(ctx->stream, a, plan.cfa, P, ctx->spec_tab, ctx->sm_count);
+      if (es != cudaSuccess) return fail(ctx, IPB_ERR_CUDA, "speculative scaled kernel: %s %s", cudaGetErrorString(es), spec_last_error());
       ctx->launches++;
       return IPB_OK;
     }

@@ -29,6 +29,7 @@
 #include <cuda.h>
 
 #include "ipb_internal.h"
+#include "ipb_scaled.cuh"
 #include "ipb_spec.h"
 
 namespace ipb {
@@ -388,17 +389,42 @@ __device__ __forceinline__ uint32_t gamma8_exact(uint32_t g8_base, uint32_t thr_
   return lo + (vc >= t0 ? 1u : 0u) + (vc >= t1 ? 1u : 0u);
 }
 
+// {1/n rounded to nearest, n} for tap counts n = 0..9 (entry 0 divides the empty sum by 1: +0.0)
+__constant__ float2 kTapRcpS[10] = {{0.0f, 1.0f}, {1.0f, 1.0f}, {0.5f, 2.0f}, {1.0f / 3.0f, 3.0f}, {0.25f, 4.0f},
+                                    {1.0f / 5.0f, 5.0f}, {1.0f / 6.0f, 6.0f}, {1.0f / 7.0f, 7.0f}, {0.125f, 8.0f},
+                                    {1.0f / 9.0f, 9.0f}};
+// One colour of demosaic::full for an interior pixel of any pattern, exactly as the reference rounds it: the selected taps
+// summed in raster order (predicated adds), s / n through the three-instruction reciprocal form, which equals IEEE
+// division for every divisor 1..9 (tools/verify_constdiv.c) — the scheme of k_fused_full (ipb_fused.cu bin_mean_rc).
+__device__ __forceinline__ float bin_mean_exact(uint32_t m, const float v[9]) {
+  float s = 0.0f;
+#pragma unroll
+  for (int i = 0; i < 9; i++)
+    if ((m >> i) & 1u) s = s + v[i];
+  const float2 e = kTapRcpS[__popc(m)];
+  return div_rc(s, e.y, e.x);
+}
+
 // queue entry: row * kTW + column inside the tile whose planes start at tile_base and whose first pixel is (tx0, ty0).
 // Out of line: the exact path keeps its registers (and the instruction cache footprint of its ~400 instructions) to
 // itself; p and P are the copies in shared memory.
 __device__ __noinline__ void fixup_entry(const SpecParams &p, const ColorParams &P, const float (*spl)[8], uint32_t phase,
-                                         const uint8_t *pat, uint32_t g8_base, uint32_t thr_base, uint32_t tile_base, int tx0,
+                                         const uint8_t *pat, const uint2 *taps, uint32_t g8_base, uint32_t thr_base, uint32_t tile_base, int tx0,
                                          int ty0, uint32_t entry) {
   const int r = (int)(entry / kTW), c = (int)(entry % kTW), x = tx0 + c, y = ty0 + r;
   float t[9], v[3], cr, cg, cb;
   if (pat) {   // uniform: one pattern kind per launch
     taps_from_tile<true>(tile_base, r, c, t);
-    exact_rgb_generic(p, pat, x, y, t, cr, cg, cb);
+    if (x >= 1 && x <= p.width - 2 && y >= 1 && y <= p.height - 2) {
+      // all nine taps exist: the tap masks of the pixel's pattern position and the exact means of the cheap pass
+      const int pr = y - (int)__umulhi((uint32_t)y, p.rcp_ph) * p.ph, pc = x - (int)__umulhi((uint32_t)x, p.rcp_pw) * p.pw;
+      const uint2 m = taps[pr * p.pw + pc];
+      cr = bin_mean_exact(m.x & 0xffffu, t);
+      cg = bin_mean_exact(m.x >> 16, t);
+      cb = bin_mean_exact(m.y & 0xffffu, t);
+    } else {
+      exact_rgb_generic(p, pat, x, y, t, cr, cg, cb);
+    }
   } else {
     taps_from_tile<false>(tile_base, r, c, t);
     exact_rgb_bayer(p, phase, x, y, t, cr, cg, cb);
@@ -450,22 +476,6 @@ __device__ __forceinline__ uint32_t cheap_task(const SpecParams &p, uint32_t g8_
   // s[2c + h]: channel c of the pair's pixel h: px0 = s02[*][0], px1 = s13[*][0], px2 = s02[*][1], px3 = s13[*][1]
   const uint32_t c[12] = {s02[0], s02[2], s02[4], s13[0], s13[2], s13[4], s02[1], s02[3], s02[5], s13[1], s13[3], s13[5]};
   return pack_and_certify(p, c, y02, y13, 5u, 10u, words);
-}
-
-// {1/n rounded to nearest, n} for tap counts n = 0..9 (entry 0 divides the empty sum by 1: +0.0)
-__constant__ float2 kTapRcpS[10] = {{0.0f, 1.0f}, {1.0f, 1.0f}, {0.5f, 2.0f}, {1.0f / 3.0f, 3.0f}, {0.25f, 4.0f},
-                                    {1.0f / 5.0f, 5.0f}, {1.0f / 6.0f, 6.0f}, {1.0f / 7.0f, 7.0f}, {0.125f, 8.0f},
-                                    {1.0f / 9.0f, 9.0f}};
-// One colour of demosaic::full for an interior pixel of any pattern, exactly as the reference rounds it: the selected taps
-// summed in raster order (predicated adds), s / n through the three-instruction reciprocal form, which equals IEEE
-// division for every divisor 1..9 (tools/verify_constdiv.c) — the scheme of k_fused_full (ipb_fused.cu bin_mean_rc).
-__device__ __forceinline__ float bin_mean_exact(uint32_t m, const float v[9]) {
-  float s = 0.0f;
-#pragma unroll
-  for (int i = 0; i < 9; i++)
-    if ((m >> i) & 1u) s = s + v[i];
-  const float2 e = kTapRcpS[__popc(m)];
-  return div_rc(s, e.y, e.x);
 }
 
 // the same task for any three-colour pattern: w = the 3 x 6 window (rows y-1 .. y+1, columns x0-1 .. x0+4), mm[j] = the
@@ -748,19 +758,144 @@ k_spec8(const __grid_constant__ SpecParams p, const __grid_constant__ CfaDev cfa
     const bool recompute = !(p.dbg & 1);
     if (qn > NT && recompute)   // more than one entry per thread (dark frames, the bound at its cap): all threads, right here
       for (int i = NT + tid; i < qn; i += NT)
-        fixup_entry(sm.sp, sm.cp, sm.spl, phase, pat, g8_base, thr_base, tile_base, tx0, ty0, sm.queue[i]);
+        fixup_entry(sm.sp, sm.cp, sm.spl, phase, pat, sm.taps, g8_base, thr_base, tile_base, tx0, ty0, sm.queue[i]);
     const uint32_t mine = tid < qn ? (uint32_t)sm.queue[tid] : 0xffffffffu;
     __syncthreads();
     if (tid == 0) nfix += (unsigned long long)qn;
     fix_warps = min((qn + 31) >> 5, NT / 32);
     if (warp < fix_warps) {
       if (mine != 0xffffffffu && recompute)
-        fixup_entry(sm.sp, sm.cp, sm.spl, phase, pat, g8_base, thr_base, tile_base, tx0, ty0, mine);
+        fixup_entry(sm.sp, sm.cp, sm.spl, phase, pat, sm.taps, g8_base, thr_base, tile_base, tx0, ty0, mine);
       if (have_next) asm volatile("bar.arrive 1, %0;" ::"n"(NT) : "memory");
     }
     if (!have_next) fix_warps = 0;
   }
   if (tid == 0 && p.stats && nfix) atomicAdd(p.stats, nfix);
+}
+
+// ---------------------------------------------------------------- speculative scaled kernel (BASELINE config 4)
+// scaled_demosaic (scaling.rs:51-145) + the same cheap colour chain / certificate / exact recomputation for the 8-bit
+// output of a down-scaled RGB Bayer frame.  The window phase is k_fused_scaled's (ipb_scaled.cuh: the reference's f32
+// expressions, so cheap and exact chains start from identical demosaiced values); a thread takes two output pixels so
+// that the chain runs on packed pairs.  Uncertified pixels go, with their demosaiced values, to a queue of the warp in
+// shared memory; whenever it holds 32 the warp recomputes them exactly with all lanes busy (warp-synchronous, no CTA
+// barrier), the rest after the last pixel.
+constexpr int kScNT = 512;
+constexpr int kWQCap = 96;   // 31 left over + up to 64 new entries per iteration
+
+struct SmemScaledSpec : SmemFront {
+  unsigned char fill[kG8Offset - (int)sizeof(SmemFront)];
+  uint32_t g8a[kSpecG8Entries];
+  float4 wq[kScNT / 32][kWQCap];                // {pixel index (bits), demosaiced r, g, b}
+};
+static_assert(offsetof(SmemScaledSpec, g8a) == kG8Offset, "gamma table must sit on a 32 KB boundary of the shared window");
+
+__device__ __noinline__ void fixup_scaled(const SpecParams &p, const ColorParams &P, const float (*spl)[8], uint32_t g8_base,
+                                          uint32_t thr_base, float4 e) {
+  float v[3];
+  exact_chain(p, P, spl, e.y, e.z, e.w, v);
+  uint8_t *o = p.out + (size_t)__float_as_uint(e.x) * 3;
+  o[0] = (uint8_t)gamma8_exact(g8_base, thr_base, v[0]);
+  o[1] = (uint8_t)gamma8_exact(g8_base, thr_base, v[1]);
+  o[2] = (uint8_t)gamma8_exact(g8_base, thr_base, v[2]);
+}
+
+__global__ void __launch_bounds__(kScNT, 2)
+k_spec8_scaled(const __grid_constant__ SpecParams p, const __grid_constant__ ScaledParams g, const __grid_constant__ CfaDev cfa,
+               const __grid_constant__ ColorParams P) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  SmemScaledSpec &sm = *reinterpret_cast<SmemScaledSpec *>(smem_raw);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t bar_tab = smem_u32(&sm.mbar_tab);
+  if (tid == 0) {
+    mbar_init(bar_tab, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    constexpr uint32_t kG8Bytes = kSpecG8Entries * 4u, kSTabBytes = kSpecSTabEntries * 8u;
+    mbar_expect_tx(bar_tab, kG8Bytes + kSTabBytes);
+    bulk_load(smem_u32(sm.g8a), p.g8a, kG8Bytes, bar_tab);
+    bulk_load(smem_u32(sm.stab), p.stab, kSTabBytes, bar_tab);
+  }
+  const uint32_t g8_base = smem_u32(sm.g8a);
+  if ((g8_base & 0x7fffu) != 0u) {  // cannot happen: ipb_ctx_create probed the shared window base (kSpecSmemBase)
+    if (tid == 0 && p.stats) p.stats[4] = 1ull;
+    return;
+  }
+  const uint32_t stab_bias = smem_u32(sm.stab) - p.bias58, thr_base = smem_u32(sm.thr);
+  for (int i = tid; i < kSplRows; i += kScNT) {
+    float e[5] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
+    if (i == 0) e[1] = P.sp.y_first;
+    else if (i >= P.sp.n) e[1] = P.sp.y_last;
+    else { e[0] = P.sp.x[i - 1]; e[1] = P.sp.y[i - 1]; e[2] = P.sp.c1[i - 1]; e[3] = P.sp.c2[i - 1]; e[4] = P.sp.c3[i - 1]; }
+#pragma unroll
+    for (int k = 0; k < 5; k++) sm.spl[i][k] = e[k];
+  }
+  for (int i = tid; i < 260; i += kScNT) sm.thr[i] = i < 255 ? __ldg(p.thr8 + i) : __int_as_float(0x7f800000);
+  for (int i = tid; i < (int)(sizeof(SpecParams) / 4); i += kScNT) reinterpret_cast<uint32_t *>(&sm.sp)[i] = reinterpret_cast<const uint32_t *>(&p)[i];
+  for (int i = tid; i < (int)(sizeof(ColorParams) / 4); i += kScNT) reinterpret_cast<uint32_t *>(&sm.cp)[i] = reinterpret_cast<const uint32_t *>(&P)[i];
+  __syncthreads();
+
+  float4 *wq = sm.wq[warp];
+  int qn = 0;                        // warp-uniform: entries in this warp's queue
+  unsigned long long nfix = 0;
+  bool tables_in = false;
+  const bool recompute = !(p.dbg & 1);
+  const long long npix = (long long)(g.out_row1 - g.out_row0) * g.nwidth;
+  const long long npairs = (npix + 1) / 2, npairs_pad = (npairs + 31) / 32 * 32;  // whole warps stay in the loop
+  const bool out_even = (reinterpret_cast<uintptr_t>(p.out) & 1) == 0;
+  for (long long pi = (long long)blockIdx.x * kScNT + tid; pi < npairs_pad; pi += (long long)gridDim.x * kScNT) {
+    const bool live = pi < npairs;
+    const long long id0 = 2 * (live ? pi : npairs - 1);
+    const bool have1 = live && id0 + 1 < npix;
+    const long long id1 = id0 + 1 < npix ? id0 + 1 : id0;
+    float pa[3], pb[3];
+    scaled_pixel_bayer(g, cfa, g.out_row0 + (int)(id0 / g.nwidth), (int)(id0 % g.nwidth), pa);
+    scaled_pixel_bayer(g, cfa, g.out_row0 + (int)(id1 / g.nwidth), (int)(id1 % g.nwidth), pb);
+    if (!tables_in) {
+      mbar_wait(bar_tab, 0);
+      tables_in = true;
+    }
+    // a weighted mean of samples <= 1 can round an ulp above 1, where the reference clips green (mul[1] == 1); the cheap
+    // chain assumes green <= 1
+    uint32_t s[6];
+    const float ymin = chain_pair<false>(p, g8_base, stab_bias, F2{pa[0], pb[0]}, F2{fminf(pa[1], 1.0f), fminf(pb[1], 1.0f)},
+                                         F2{pa[2], pb[2]}, s, nullptr);
+    const uint32_t wr = p.wmul[0], wg = p.wmul[1], wb = p.wmul[2], T = p.amb_t;
+    const uint32_t d0 = min(min(s[0] * wr, s[2] * wg), s[4] * wb), d1 = min(min(s[1] * wr, s[3] * wg), s[5] * wb);
+    const bool dark = ymin < p.y_min;   // outside the certified domain: both pixels exactly
+    const bool f0 = live && (d0 <= T || dark) && !(p.dbg & 2), f1 = have1 && (d1 <= T || dark) && !(p.dbg & 2);
+    if (live) {
+      uint8_t *o = p.out + (size_t)id0 * 3;
+      const uint32_t w01 = __byte_perm(s[0], s[2], 0x0073), w2 = s[4] >> 24;          // pixel 0: r, g | b
+      const uint32_t w34 = __byte_perm(s[3], s[5], 0x0073), w3 = s[1] >> 24;          // pixel 1: r | g, b
+      if (have1 && out_even) {
+        uint16_t *o2 = reinterpret_cast<uint16_t *>(o);
+        o2[0] = (uint16_t)w01; o2[1] = (uint16_t)(w2 | (w3 << 8)); o2[2] = (uint16_t)w34;
+      } else {
+        o[0] = (uint8_t)w01; o[1] = (uint8_t)(w01 >> 8); o[2] = (uint8_t)w2;
+        if (have1) { o[3] = (uint8_t)w3; o[4] = (uint8_t)w34; o[5] = (uint8_t)(w34 >> 8); }
+      }
+    }
+    // queue the uncertified pixels with their demosaiced values (ballot compaction: qn stays warp-uniform)
+    const uint32_t m0 = __ballot_sync(kFull, f0), m1 = __ballot_sync(kFull, f1), lt = (1u << lane) - 1u;
+    if (f0) wq[qn + __popc(m0 & lt)] = make_float4(__uint_as_float((uint32_t)id0), pa[0], pa[1], pa[2]);
+    qn += __popc(m0);
+    if (f1) wq[qn + __popc(m1 & lt)] = make_float4(__uint_as_float((uint32_t)id1), pb[0], pb[1], pb[2]);
+    qn += __popc(m1);
+    __syncwarp();   // orders the cheap stores and the queue writes before the recomputation by other lanes
+    while (qn >= 32) {
+      qn -= 32;
+      const float4 e = wq[qn + lane];
+      if (recompute) fixup_scaled(sm.sp, sm.cp, sm.spl, g8_base, thr_base, e);
+      nfix += 32;
+      __syncwarp();
+    }
+  }
+  if (qn > 0) {
+    if (lane < qn && recompute) fixup_scaled(sm.sp, sm.cp, sm.spl, g8_base, thr_base, wq[lane]);
+    nfix += (unsigned long long)qn;
+  }
+  if (lane == 0 && p.stats && nfix) atomicAdd(p.stats, nfix);
 }
 
 // ---------------------------------------------------------------- probe: cheap vs exact linear values
@@ -979,6 +1114,42 @@ cudaError_t launch_fused_spec8(cudaStream_t s, const FusedArgs &a, const CfaDev 
     case 6: return launch_variant<1024, 2>(s, p, cfa, P, tmap, ntiles, sm_count);
     default: return launch_variant<1024, 3>(s, p, cfa, P, tmap, ntiles, sm_count);
   }
+}
+
+bool spec_scaled_supported(const FusedArgs &a, const CfaDev &cfa, const ColorParams &P) {
+  if (a.out_kind != kOutU8 || P.linear || P.use_e || !a.exact_rc) return false;
+  if (!is_rgb_bayer(cfa)) return false;
+  if (a.out_width < 2 || a.out_height < 2 || a.width < 2 || a.height < 2) return false;
+  // windows of at most kMaxCols columns (scaling.rs:84-87: floor(skip * (col + 1)) - floor(skip * col) + 1 <= ceil(skip) + 1)
+  const float skip_x = (float)((long)a.width - 1) / (float)(a.out_width - 1);
+  if (!(skip_x >= 1.0f) || ceilf(skip_x) + 1.0f > (float)kMaxCols) return false;
+  if ((unsigned long long)a.out_width * (unsigned long long)(a.out_row1 - a.out_row0) >= (1ull << 31)) return false;
+  return true;
+}
+
+cudaError_t launch_scaled_spec8(cudaStream_t s, const FusedArgs &a, const CfaDev &cfa, const ColorParams &P,
+                                const SpecTables &T, int sm_count) {
+  if (a.out_row1 <= a.out_row0 || a.out_width == 0) return cudaSuccess;
+  SpecParams p = T.consts;
+  p.out = (uint8_t *)a.out;
+  p.black = a.black; p.range = a.range; p.range_rc = a.range_rc; p.exact_rc = a.exact_rc;
+  p.bias58 = 0x58000000u;
+  {
+    static const int dbg = getenv("IPB_SPEC_DBG") ? atoi(getenv("IPB_SPEC_DBG")) : 0;
+    p.dbg = dbg;
+  }
+  p.lut_lab = a.lut_lab; p.lut_gamma = a.lut_gamma; p.cbrt_tab = a.cbrt_tab;
+  p.g8a = T.g8a; p.stab = T.stab; p.thr8 = T.thr8; p.stats = T.stats;
+  ScaledParams g;
+  fill_scaled_params(a, cfa, &g);
+  const long long npairs = ((long long)(g.out_row1 - g.out_row0) * g.nwidth + 1) / 2;
+  const long long blocks = (npairs + kScNT - 1) / kScNT;
+  const int grid = (int)(blocks < 2ll * sm_count ? blocks : 2ll * sm_count);
+  const size_t smem = sizeof(SmemScaledSpec);
+  cudaError_t e = cudaFuncSetAttribute(k_spec8_scaled, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  k_spec8_scaled<<<grid, kScNT, smem, s>>>(p, g, cfa, P);
+  return cudaGetLastError();
 }
 
 cudaError_t launch_spec_selftest(cudaStream_t s, unsigned int *out2) {

@@ -73,6 +73,10 @@ bool spec_build(const ColorParams &P, float black, float range, float mufu_rel_e
 bool spec_supported(const FusedArgs &a, const CfaDev &cfa, const ColorParams &P);
 cudaError_t launch_fused_spec8(cudaStream_t s, const FusedArgs &a, const CfaDev &cfa, const ColorParams &P,
                                const SpecTables &T, int sm_count, int threads);
+// the same for a down-scaled RGB Bayer frame (scaled_demosaic): k_spec8_scaled
+bool spec_scaled_supported(const FusedArgs &a, const CfaDev &cfa, const ColorParams &P);
+cudaError_t launch_scaled_spec8(cudaStream_t s, const FusedArgs &a, const CfaDev &cfa, const ColorParams &P,
+                                const SpecTables &T, int sm_count);
 cudaError_t launch_spec_probe(cudaStream_t s, const FusedArgs &a, const CfaDev &cfa, const ColorParams &P,
                               const SpecTables &T, int sm_count);
 cudaError_t launch_spec_selftest(cudaStream_t s, unsigned int *out2);

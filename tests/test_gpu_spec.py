@@ -223,3 +223,82 @@ def test_full_size_frames_spec_equals_exact_kernel(ip, ctx, w, h, seed):
     common.fill_ipb_ops(p.ops, params)
     mx, mean, delta = p.spec_probe()
     assert mx <= delta / 1.5, (mx, delta)   # measured margin on 24 / 102 million pixels of white noise
+
+
+# ---------------------------------------------------------------- k_spec8_scaled: down-scaled RGB Bayer frames
+
+def out8_scaled(ip, ctx, data, params, st, spec=True):
+    p = common.make_ipb_pipeline(ip, data, "raw", params, st, ctx=ctx)
+    p.set_speculative(spec)
+    return p.output_8bit().to_numpy()
+
+
+@pytest.mark.parametrize("cfa", ["RGGB", "BGGR", "GRBG", "GBRG"])
+@pytest.mark.parametrize("w,h,maxw,maxh", [(640, 360, 160, 90), (403, 131, 100, 0), (1200, 800, 300, 200), (257, 97, 0, 40),
+                                           (600, 400, 299, 0), (1500, 1000, 250, 0)])
+def test_scaled_against_oracle(ip, orc, ctx, cfa, w, h, maxw, maxh):
+    """scaled_demosaic (2x .. 6x, window widths 3 .. 8) + speculative chain == oracle == exact fused kernel; the
+    speculative kernel is the one that ran (its counter moves)."""
+    data = common.synth_cfa(w, h, seed=5 + w)
+    params = common.raw_params(cfa=cfa)
+    st = {"maxwidth": maxw, "maxheight": maxh}
+    want = orc.pipeline_output_8bit(orc.make_pipeline(data, "raw", params, st))
+    ctx.spec_stats(reset=True)
+    assert_bit_exact(out8_scaled(ip, ctx, data, params, st), want, f"{cfa} {w}x{h} -> {maxw}x{maxh}")
+    assert ctx.spec_stats()["fixups"] > 0, "the speculative kernel did not run"
+    ctx.spec_stats(reset=True)
+    assert_bit_exact(out8_scaled(ip, ctx, data, params, st, spec=False), want, f"{cfa} {w}x{h} exact kernel")
+    assert ctx.spec_stats()["fixups"] == 0
+
+
+@pytest.mark.parametrize("name,kw", PARAMS, ids=[p[0] for p in PARAMS])
+def test_scaled_parameter_sets(ip, orc, ctx, name, kw):
+    data = common.synth_cfa(1031, 277, seed=33)
+    if "black" in kw and kw["white"] < 5000:
+        data = (data >> 2).astype(np.uint16)
+    params = common.raw_params(**kw)
+    st = {"maxwidth": 257, "maxheight": 0}
+    want = orc.pipeline_output_8bit(orc.make_pipeline(data, "raw", params, st))
+    assert_bit_exact(out8_scaled(ip, ctx, data, params, st), want, name)
+
+
+@pytest.mark.parametrize("kind", list(FRAMES))
+def test_scaled_frame_kinds_and_busy_queue(ip, orc, ctx, kind):
+    """Every kind of frame at the certified bound and with the bound forced to its cap (warp queues flush often); a
+    frame below the black level leaves the certified domain everywhere: every pixel is recomputed."""
+    data = FRAMES[kind](1152, 320)
+    params = common.raw_params()
+    st = {"maxwidth": 288, "maxheight": 0}
+    want = orc.pipeline_output_8bit(orc.make_pipeline(data, "raw", params, st))
+    assert_bit_exact(out8_scaled(ip, ctx, data, params, st), want, kind)
+    ctx.set_spec(7.9e-5, 512)
+    assert_bit_exact(out8_scaled(ip, ctx, data, params, st), want, kind + ", bound at its cap")
+
+
+def test_scaled_dark_frame_recomputes_everything(ip, orc, ctx):
+    params = common.raw_params()
+    dark = np.random.default_rng(5).integers(0, 30, (256, 1280)).astype(np.uint16)
+    st = {"maxwidth": 320, "maxheight": 0}
+    ctx.spec_stats(reset=True)
+    got = out8_scaled(ip, ctx, dark, params, st)
+    assert ctx.spec_stats()["fixups"] >= got.size // 3 * 0.9
+    assert_bit_exact(got, orc.pipeline_output_8bit(orc.make_pipeline(dark, "raw", params, st)), "all pixels recomputed")
+
+
+def test_scaled_full_size_spec_equals_exact_kernel(ip, ctx):
+    """BASELINE config 4 at full size (6000x4000 -> 1500x1000): speculative scaled kernel == k_fused_scaled (which the
+    other suites pin to the oracle at this size)."""
+    w, h = 6000, 4000
+    d_raw = ip.synth_cfa_u16(common.SEED + 1, w, 0, h, ctx=ctx)
+    src = ip.ImageSource.Raw(d_raw, w, h)
+    outs = []
+    for spec in (False, True):
+        p = ip.Pipeline.new_from_source(src, ctx=ctx)
+        common.fill_ipb_ops(p.ops, common.raw_params())
+        p.globals.settings.maxwidth, p.globals.settings.maxheight = 1500, 1000
+        p.set_speculative(spec)
+        ctx.spec_stats(reset=True)
+        outs.append(p.output_8bit().to_numpy())
+        if spec:
+            assert 0 < ctx.spec_stats()["fixups"] < 1500 * 1000 * 0.1
+    assert outs[0].shape == (1000, 1500, 3) and np.array_equal(outs[0], outs[1])
