@@ -221,25 +221,53 @@ bool spec_build(const ColorParams &P, float black, float range, float mufu_rel_e
         const double e_sE = (100.0 * (spl * e_l + e_sp) + U * (100.0 * fabs(sv) + 116.0 * fabs(Sy))) / 116.0 + U * fabs(Sy);
         const double e_fyp = e_sE + e_stab;
         const double D = Sy - fy;
-        double EXp[3], Xp[3];
+        // Error of the three cube-root-domain values t = (fx + D, fy', fz + D), cheap minus reference:
+        //   dt_x = dfx + ind_x + cS + (S' - 1) dfy,   dt_y = cS + S' dfy,   dt_z = dfz + ind_z + cS + (S' - 1) dfy
+        // dfx, dfy, dfz: the transfer-function errors (|.| <= ef); ind: the roundings of the a / b legs; cS: the error of the
+        // basecurve step itself (|cS| <= e_fyp) — ONE number for all three, because both computations add the same fy'
+        // to the a / b differences; S': a secant slope of S near fy (between the two one-sided slopes).  The common terms
+        // reach an output channel through the SIGNED sum of its matrix row times g'(t), which is much smaller than the
+        // sum of magnitudes (the rows of the XYZ -> RGB matrix sum to about 1 but hold entries up to 3.2).
+        double EXp[3], Xp[3], gpm[3], gpc[3], dev[3], eind[3], tj[3];
         for (int i = 0; i < 3; i++) {
-          double et, t;
+          double et;
           if (i == 1) {
             et = spl * ef[1] + e_fyp;
-            t = Sy;
+            tj[i] = Sy;
+            eind[i] = 0.0;
           } else {
             const double e_ab = U * (2.0 + 7.1 * fabs(f[i] - fy)) + 1.5 * U;
-            et = ef[i] + ls * ef[1] + e_fyp + e_ab + 2.0 * U * (fabs(f[i]) + fabs(D));
-            t = f[i] + D;
+            eind[i] = ef[i] + e_ab + 2.0 * U * (fabs(f[i]) + fabs(D));
+            et = eind[i] + ls * ef[1] + e_fyp;
+            tj[i] = f[i] + D;
           }
-          const double gp = std::max(lab_gp(t + et), lab_gp(t - et));
-          EXp[i] = gp * et + 4.0 * U * fabs(lab_g(t)) + 4.0 * U * 16.0 / kK;
-          Xp[i] = fabs(lab_g(t)) + EXp[i];
+          gpc[i] = lab_gp(tj[i]);
+          gpm[i] = std::max(lab_gp(tj[i] + et), lab_gp(tj[i] - et));
+          dev[i] = std::max(fabs(lab_gp(tj[i] + et) - gpc[i]), fabs(lab_gp(tj[i] - et) - gpc[i]));
+          EXp[i] = gpm[i] * et + 4.0 * U * fabs(lab_g(tj[i])) + 4.0 * U * 16.0 / kK;   // magnitude bound (sum of everything)
+          Xp[i] = fabs(lab_g(tj[i])) + EXp[i];
           worst_ex[i] = std::max(worst_ex[i], EXp[i]);
         }
+        const double slopes[2] = {sp.n ? sl1 : 1.0, sp.n ? sl2 : 1.0};
         for (int ch = 0; ch < 3; ch++) {
-          double d = 0.0;
-          for (int j = 0; j < 3; j++) d += fabs(RO[ch][j]) * (EXp[j] + 9.0 * U * Xp[j]);
+          double d = 0.0, sum_c = 0.0, sum_dev = 0.0;
+          for (int j = 0; j < 3; j++) {
+            d += fabs(RO[ch][j]) * (gpm[j] * eind[j] + 4.0 * U * fabs(lab_g(tj[j])) + 4.0 * U * 16.0 / kK + 9.0 * U * Xp[j]);
+            sum_c += RO[ch][j] * gpc[j];
+            sum_dev += fabs(RO[ch][j]) * dev[j];
+          }
+          d += e_fyp * (fabs(sum_c) + sum_dev);
+          double worst_y = 0.0;
+          for (double sl : slopes) {
+            const double k[3] = {sl - 1.0, sl, sl - 1.0};
+            double sk = 0.0, skd = 0.0;
+            for (int j = 0; j < 3; j++) {
+              sk += RO[ch][j] * gpc[j] * k[j];
+              skd += fabs(RO[ch][j]) * dev[j] * fabs(k[j]);
+            }
+            worst_y = std::max(worst_y, fabs(sk) + skd);
+          }
+          d += ef[1] * worst_y;
           if (d > delta && getenv("IPB_SPEC_DEBUG2"))
             fprintf(stderr, "  ch %d c (%.4f %.4f %.4f) x (%.4f %.4f %.4f) ef %.1f %.1f %.1f u e_sE %.1f e_stab %.1f ls %.3f spl %.3f D %.3f EX %.1f %.1f %.1f u X' %.3f %.3f %.3f d %.3g\n",
                     ch, ca, cb, cc, x[0], x[1], x[2], ef[0] / U, ef[1] / U, ef[2] / U, e_sE / U, e_stab / U, ls, spl, D, EXp[0] / U, EXp[1] / U, EXp[2] / U, Xp[0], Xp[1], Xp[2], d);
