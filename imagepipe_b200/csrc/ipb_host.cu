@@ -44,6 +44,9 @@ struct ipb_ctx {
   // milliseconds to map again).  Like the reference's allocator, it holds on to what a pipeline run needed.
   cudaMemPool_t pool = nullptr;
   // speculative 8-bit kernel (ipb_spec.cu): self-test results, device tables, the parameter set they were built for
+  bool rc_cached = false;           // ranges_rc_exact: result for the last (black, range) pair
+  float rc_black = 0.0f, rc_range = 0.0f;
+  int rc_exact = 0;
   int spec_ok = 0;                  // the shared window starts where the gamma table's addressing assumes it does
   float mufu_cbrt_err = 1.0f;       // measured max relative error of the XU-pipe cube root (every float in [2^-8, 4])
   int spec_threads = 512;           // CTA size of k_spec8 (512: two CTAs per SM, 1024: one)
@@ -824,6 +827,17 @@ void *ipb_buffer_device_ptr(const ipb_buffer *buf) { return buf ? buf->dptr : nu
 
 // ------------------------------------------------------------------------------------------------ ImageOp::run
 
+// golevel_rc_exact for the context's last (black, range) pair (the check walks all 65536 samples)
+static bool ranges_rc_exact(ipb_ctx *ctx, float black, float range) {
+  if (!ctx->rc_cached || memcmp(&ctx->rc_black, &black, 4) != 0 || memcmp(&ctx->rc_range, &range, 4) != 0) {
+    ctx->rc_exact = golevel_rc_exact(black, range, 1.0f / range) ? 1 : 0;
+    ctx->rc_black = black;
+    ctx->rc_range = range;
+    ctx->rc_cached = true;
+  }
+  return ctx->rc_exact != 0;
+}
+
 int ipb_gofloat_run(ipb_ctx *ctx, const ipb_gofloat *op, const ipb_source *image, ipb_buffer **out) {
   IPB_TRY(enter(ctx));
   if (!op || !image || !out) return fail(ctx, IPB_ERR_INVALID, "null pointer");
@@ -852,7 +866,8 @@ int ipb_gofloat_run(ipb_ctx *ctx, const ipb_gofloat *op, const ipb_source *image
     if (rc == IPB_OK) {
       cudaError_t e = launch_gofloat_raw(ctx->stream, image->kind == IPB_SRC_RAW_F32, src.ptr,
                                          image->width * image->height * image->cpp, image->width, x, y, width, height,
-                                         image->cpp, mode, mins, ranges, b->dptr);
+                                         image->cpp, mode, mins, ranges,
+                                         mode == 2 && ranges_rc_exact(ctx, mins[0], ranges[0]) ? 1 : 0, b->dptr);
       if (e != cudaSuccess) rc = fail(ctx, IPB_ERR_CUDA, "gofloat kernel: %s", cudaGetErrorString(e));
       else ctx->launches++;
     }
@@ -962,20 +977,28 @@ int ipb_rotatecrop_run(ipb_ctx *ctx, const ipb_rotatecrop *op, ipb_buffer *in, i
   return IPB_OK;
 }
 
-int ipb_tolab_run(ipb_ctx *ctx, const ipb_tolab *op, ipb_buffer *in, ipb_buffer **out) {
-  IPB_TRY(enter(ctx));
-  if (!op || !in || !out) return fail(ctx, IPB_ERR_INVALID, "null pointer");
+static bool spline_counting_ok(const SplineDev &sp);
+// to_lab, optionally with the basecurve applied in the same pass (sp != null, sp->n > 0)
+static int tolab_launch(ipb_ctx *ctx, const ipb_tolab *op, const SplineDev *sp, ipb_buffer *in, ipb_buffer **out) {
   if (in->colors != 4) return fail(ctx, IPB_ERR_BAD_COLORS, "to_lab: expected 4 channels, got %zu", in->colors);
   ColorParams P;
   memset(&P, 0, sizeof(P));
   fill_tolab(&P, op, in->monochrome);
+  if (sp) P.sp = *sp;
   ipb_buffer *b;
   IPB_TRY(new_buffer(ctx, in->width, in->height, 3, in->monochrome, false, &b));
-  cudaError_t e = launch_tolab(ctx->stream, P, ctx->lut_lab, in->dptr, in->width * in->height, b->dptr);
+  const int curve = sp ? (spline_counting_ok(*sp) ? 2 : 1) : 0;
+  cudaError_t e = launch_tolab(ctx->stream, P, ctx->lut_lab, ctx->cbrt_tab, curve, in->dptr, in->width * in->height, b->dptr);
   if (e != cudaSuccess) { ipb_buffer_release(b); return fail(ctx, IPB_ERR_CUDA, "to_lab kernel: %s", cudaGetErrorString(e)); }
   ctx->launches++;
   *out = b;
   return IPB_OK;
+}
+
+int ipb_tolab_run(ipb_ctx *ctx, const ipb_tolab *op, ipb_buffer *in, ipb_buffer **out) {
+  IPB_TRY(enter(ctx));
+  if (!op || !in || !out) return fail(ctx, IPB_ERR_INVALID, "null pointer");
+  return tolab_launch(ctx, op, nullptr, in, out);
 }
 
 int ipb_basecurve_run(ipb_ctx *ctx, const ipb_basecurve *op, ipb_buffer *in, ipb_buffer **out) {
@@ -999,20 +1022,25 @@ int ipb_basecurve_run(ipb_ctx *ctx, const ipb_basecurve *op, ipb_buffer *in, ipb
   return IPB_OK;
 }
 
-int ipb_fromlab_run(ipb_ctx *ctx, ipb_buffer *in, ipb_buffer **out) {
-  IPB_TRY(enter(ctx));
-  if (!in || !out) return fail(ctx, IPB_ERR_INVALID, "null pointer");
-  if (in->colors != 3) return fail(ctx, IPB_ERR_BAD_COLORS, "from_lab: expected 3 channels, got %zu", in->colors);
+// from_lab, optionally with OpGamma applied in the same pass
+static int fromlab_launch(ipb_ctx *ctx, bool with_gamma, ipb_buffer *in, ipb_buffer **out) {
   ColorParams P;
   memset(&P, 0, sizeof(P));
   memcpy(P.rgbm, tables().xyz_d65_33, sizeof(P.rgbm));
   ipb_buffer *b;
   IPB_TRY(new_buffer(ctx, in->width, in->height, 3, in->monochrome, false, &b));
-  cudaError_t e = launch_fromlab(ctx->stream, P, in->dptr, in->width * in->height, b->dptr);
+  cudaError_t e = launch_fromlab(ctx->stream, P, with_gamma ? ctx->lut_gamma : nullptr, in->dptr, in->width * in->height, b->dptr);
   if (e != cudaSuccess) { ipb_buffer_release(b); return fail(ctx, IPB_ERR_CUDA, "from_lab kernel: %s", cudaGetErrorString(e)); }
   ctx->launches++;
   *out = b;
   return IPB_OK;
+}
+
+int ipb_fromlab_run(ipb_ctx *ctx, ipb_buffer *in, ipb_buffer **out) {
+  IPB_TRY(enter(ctx));
+  if (!in || !out) return fail(ctx, IPB_ERR_INVALID, "null pointer");
+  if (in->colors != 3) return fail(ctx, IPB_ERR_BAD_COLORS, "from_lab: expected 3 channels, got %zu", in->colors);
+  return fromlab_launch(ctx, false, in, out);
 }
 
 int ipb_gamma_run(ipb_ctx *ctx, const ipb_settings *settings, ipb_buffer *in, ipb_buffer **out) {
@@ -1410,6 +1438,22 @@ struct FusedPlan {
 // These bounds keep every dividend of the chain in that range for any u16 sample: levels within the u16 range and
 // at least one code value apart, white-balance multipliers and matrix entries zero or between 2^-20 and 64 in
 // magnitude.  Real camera metadata is far inside them; anything else runs op by op with IEEE division.
+// Can the spline be evaluated by counting the knots at or below the value (k_fused_*, k_spec8, k_tolab<2>)?  Knots must be
+// finite and increase strictly; the coefficients must be finite: on a knot the counting form returns y + 0 * c, which is
+// NaN for an infinite c (tiny knot spacing overflows 1/dx) where the reference's early return gives y; and the end values
+// must not be -0.0 (they are returned through y + 0 * d sums).
+static bool spline_counting_ok(const SplineDev &sp) {
+  for (int i = 0; i < sp.n; i++)
+    if (!std::isfinite(sp.x[i]) || !std::isfinite(sp.y[i])) return false;
+  for (int i = 0; i + 1 < sp.n; i++)
+    if (!(sp.x[i] < sp.x[i + 1])) return false;
+  for (int i = 0; i < sp.nseg; i++)
+    if (!std::isfinite(sp.c1[i]) || !std::isfinite(sp.c2[i]) || !std::isfinite(sp.c3[i])) return false;
+  if (sp.n > 0 && (std::signbit(sp.y_first) && sp.y_first == 0.0f)) return false;
+  if (sp.n > 0 && (std::signbit(sp.y_last) && sp.y_last == 0.0f)) return false;
+  return true;
+}
+
 static bool fused_params_bounded(const ipb_pipeline *p) {
   const ipb_gofloat &g = p->ops.gofloat;
   const float black = g.blacklevels[0], range = g.whitelevels[0] - g.blacklevels[0];
@@ -1435,15 +1479,7 @@ static bool fused_params_bounded(const ipb_pipeline *p) {
   // values must not be -0.0 (they are returned through y + 0*d sums)
   SplineDev sp;
   if (!build_spline(&c, &sp)) return false;
-  for (int i = 0; i + 1 < sp.n; i++)
-    if (!(sp.x[i] < sp.x[i + 1])) return false;
-  // ... and finite coefficients: on a knot the fused evaluation returns y + 0 * c, which is NaN for an infinite c
-  // (tiny knot spacing overflows 1/dx) where the reference's early return gives y
-  for (int i = 0; i < sp.nseg; i++)
-    if (!std::isfinite(sp.c1[i]) || !std::isfinite(sp.c2[i]) || !std::isfinite(sp.c3[i])) return false;
-  if (sp.n > 0 && (std::signbit(sp.y_first) && sp.y_first == 0.0f)) return false;
-  if (sp.n > 0 && (std::signbit(sp.y_last) && sp.y_last == 0.0f)) return false;
-  return true;
+  return spline_counting_ok(sp);
 }
 
 static int plan_fused(ipb_pipeline *p, FusedPlan *plan) {
@@ -1825,10 +1861,27 @@ static int run_unfused(ipb_pipeline *p, ipb_buffer **out) {
   } while (0)
   STEP(ipb_demosaic_run(ctx, &p->ops.demosaic, &p->settings, cur, &next));
   STEP(ipb_rotatecrop_run(ctx, &p->ops.rotatecrop, cur, &next));
-  STEP(ipb_tolab_run(ctx, &p->ops.tolab, cur, &next));
-  STEP(ipb_basecurve_run(ctx, &p->ops.basecurve, cur, &next));
-  STEP(ipb_fromlab_run(ctx, cur, &next));
-  STEP(ipb_gamma_run(ctx, &p->settings, cur, &next));
+  // Nobody sees the buffers between to_lab and basecurve or between from_lab and gamma here (Pipeline::run without a
+  // cache), so each pair runs as one pass with the same per-pixel arithmetic: two buffers fewer through HBM.  Anything
+  // unusual (a curve the per-op entry point rejects or passes through, wrong channel counts, linear output) takes the
+  // separate ops, which report it exactly as before.
+  {
+    SplineDev sp;
+    const bool pair = p->ops.basecurve.npoints <= IPB_MAX_CURVE_POINTS && build_spline(&p->ops.basecurve, &sp) && sp.n > 0 &&
+                      cur->colors == 4;
+    if (pair) {
+      STEP(tolab_launch(ctx, &p->ops.tolab, &sp, cur, &next));
+    } else {
+      STEP(ipb_tolab_run(ctx, &p->ops.tolab, cur, &next));
+      STEP(ipb_basecurve_run(ctx, &p->ops.basecurve, cur, &next));
+    }
+  }
+  if (!p->settings.linear && cur->colors == 3) {
+    STEP(fromlab_launch(ctx, true, cur, &next));
+  } else {
+    STEP(ipb_fromlab_run(ctx, cur, &next));
+    STEP(ipb_gamma_run(ctx, &p->settings, cur, &next));
+  }
   STEP(ipb_transform_run(ctx, &p->ops.transform, cur, &next));
 #undef STEP
   *out = cur;

@@ -50,7 +50,7 @@ struct FusedArgs {
 // ---- ipb_ops.cu
 cudaError_t launch_gofloat_raw(cudaStream_t s, int is_f32, const void *src, size_t total_elems, size_t owidth,
                                size_t x, size_t y, size_t width, size_t height, size_t cpp, int mode,
-                               const float mins[4], const float ranges[4], float *out);
+                               const float mins[4], const float ranges[4], int rc_exact, float *out);
 bool gofloat_rows_cover(size_t total, size_t owidth, size_t x, size_t y, size_t width, size_t height, size_t cpp);
 cudaError_t launch_gofloat_other(cudaStream_t s, int is16, const void *src, size_t owidth, size_t x, size_t y,
                                  size_t width, size_t height, const float2 *lut_rev, float *out);
@@ -58,10 +58,14 @@ cudaError_t launch_demosaic_full(cudaStream_t s, const CfaDev &cfa, const float 
 cudaError_t launch_transform_f32(cudaStream_t s, const XformGeom &g, const CfaDev *cfa, const float *src, float *out);
 cudaError_t launch_transform_u8(cudaStream_t s, const XformGeom &g, const uint8_t *src, uint8_t *out);
 cudaError_t launch_transform_u16(cudaStream_t s, const XformGeom &g, const uint16_t *src, uint16_t *out);
-cudaError_t launch_tolab(cudaStream_t s, const ColorParams &P, const float2 *lut_lab, const float *in, size_t npix,
-                         float *out);
+// curve != 0: P.sp is applied to L before the store (to_lab + basecurve in one pass); 1 = the reference's binary search,
+// 2 = the counting form for finite, strictly increasing knots with finite coefficients.  cbrt_tab may be null.
+cudaError_t launch_tolab(cudaStream_t s, const ColorParams &P, const float2 *lut_lab, const float *cbrt_tab, int curve,
+                         const float *in, size_t npix, float *out);
 cudaError_t launch_basecurve(cudaStream_t s, const SplineDev &sp, const float *in, size_t npix, float *out);
-cudaError_t launch_fromlab(cudaStream_t s, const ColorParams &P, const float *in, size_t npix, float *out);
+// lut_gamma != null: OpGamma is applied before the store (from_lab + gamma in one pass)
+cudaError_t launch_fromlab(cudaStream_t s, const ColorParams &P, const float2 *lut_gamma, const float *in, size_t npix,
+                           float *out);
 cudaError_t launch_gamma(cudaStream_t s, const float2 *lut_gamma, const float *in, size_t nelem, float *out);
 cudaError_t launch_pack8(cudaStream_t s, const float *in, size_t nelem, uint8_t *out);
 cudaError_t launch_pack16(cudaStream_t s, const float *in, size_t nelem, uint16_t *out);

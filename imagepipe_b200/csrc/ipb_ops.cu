@@ -64,14 +64,51 @@ k_gofloat_rows(const T *__restrict__ src, size_t owidth, size_t x, size_t y, uns
   out[row * linelen + c] = fminf(__fdiv_rn(v - m0, r0), 1.0f);
 }
 
+// The same for u16 sources whose rows start on 16-byte boundaries: eight samples per thread (one 16-byte load, two
+// 16-byte stores), u16 -> f32 through the exact 2^23 + v identity, and — when the host has verified it for every
+// possible sample (golevel_rc_exact) — the three-instruction reciprocal form of the division, else IEEE division.
+template <bool RC>
+__global__ void __launch_bounds__(256)
+k_gofloat_rows8(const uint16_t *__restrict__ src, size_t owidth, size_t x, size_t y, unsigned linelen, float m0, float r0,
+                float rc, float *__restrict__ out) {
+  const unsigned c = (blockIdx.y * 256u + threadIdx.x) * 8u;
+  if (c >= linelen) return;
+  const size_t row = blockIdx.x;
+  const uint4 pk = __ldg(reinterpret_cast<const uint4 *>(src + owidth * (row + y) + x + c));
+  const uint32_t w[4] = {pk.x, pk.y, pk.z, pk.w};
+  float v[8];
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    const float lo = __uint_as_float(0x4B000000u | (w[k] & 0xffffu)) - 8388608.0f;
+    const float hi = __uint_as_float(0x4B000000u | (w[k] >> 16)) - 8388608.0f;
+    v[2 * k] = fminf(RC ? div_rc(lo - m0, r0, rc) : __fdiv_rn(lo - m0, r0), 1.0f);
+    v[2 * k + 1] = fminf(RC ? div_rc(hi - m0, r0, rc) : __fdiv_rn(hi - m0, r0), 1.0f);
+  }
+  float4 *o = reinterpret_cast<float4 *>(out + row * linelen + c);
+  o[0] = make_float4(v[0], v[1], v[2], v[3]);
+  o[1] = make_float4(v[4], v[5], v[6], v[7]);
+}
+
 cudaError_t launch_gofloat_raw(cudaStream_t s, int is_f32, const void *src, size_t total, size_t owidth, size_t x,
                                size_t y, size_t width, size_t height, size_t cpp, int mode, const float mins[4],
-                               const float ranges[4], float *out) {
+                               const float ranges[4], int rc_exact, float *out) {
   size_t n = mode == 2 ? width * cpp * height : width * height;
   if (n == 0) return cudaSuccess;
   const size_t linelen = width * cpp;
   if (mode == 2 && gofloat_rows_cover(total, owidth, x, y, width, height, cpp) && (linelen + 255) / 256 <= 65535 &&
       height < (1ull << 31)) {
+    const bool vec8 = !is_f32 && (linelen % 8) == 0 && (owidth % 8) == 0 && (x % 8) == 0 &&
+                      (reinterpret_cast<uintptr_t>(src) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0;
+    if (vec8) {
+      dim3 grid((unsigned)height, (unsigned)((linelen / 8 + 255) / 256));
+      if (rc_exact)
+        k_gofloat_rows8<true><<<grid, 256, 0, s>>>((const uint16_t *)src, owidth, x, y, (unsigned)linelen, mins[0], ranges[0],
+                                                   1.0f / ranges[0], out);
+      else
+        k_gofloat_rows8<false><<<grid, 256, 0, s>>>((const uint16_t *)src, owidth, x, y, (unsigned)linelen, mins[0], ranges[0],
+                                                    0.0f, out);
+      return cudaGetLastError();
+    }
     dim3 grid((unsigned)height, (unsigned)((linelen + 255) / 256));
     if (is_f32)
       k_gofloat_rows<float><<<grid, 256, 0, s>>>((const float *)src, owidth, x, y, (unsigned)linelen, mins[0], ranges[0], out);
@@ -338,17 +375,73 @@ struct LutSmemPtr {
   __device__ __forceinline__ float2 at(int key) const { return t[key]; }
 };
 
+// Lab transfer table in shared memory plus the context's table of the host libm's cbrtf over (1, 1.5] — the ratios that
+// clipped highlights produce — so that only values beyond it (and -0.0 / NaN) take the double-precision restatement
+struct LutSmemCbrt {
+  const float2 *t;
+  const float *cbrt_tab;
+  __device__ __forceinline__ float2 at(int key) const { return t[key]; }
+};
+__device__ __forceinline__ float lab_f(const LutSmemCbrt &lut, float v) {
+  if (v < 0.0f || v > 1.0f) {   // the same split as lab_f<Lut> (ipb_device.cuh)
+    const uint32_t u = __float_as_uint(v), first = 0x3f800001u, size = 1u << 22;
+    if (lut.cbrt_tab && u - first < size) return __ldg(lut.cbrt_tab + (u - first));
+    return lab_f_slow(v);
+  }
+  return lut_lerp(lut, v);
+}
+
+// SplineFunc::interpolate (curves.rs:126-157) for finite, strictly increasing knots and finite coefficients (checked on
+// the host: spline_counting_ok): the number of knots <= val names the piece — 0: below the first knot (its y), n: at or
+// above the last (its y), else segment idx - 1, where a value on the knot itself gives y + 0 * c = y like the reference's
+// early return.  NaN fails every comparison of the reference's binary search, which then returns y[(nseg - 1) / 2]
+// (idx == 0 for NaN, so the NaN test comes first).
+__device__ __forceinline__ float spline_sorted(const float (*spl)[8], const SplineDev &sp, float val) {
+  int idx = 0;
+  for (int j = 0; j < sp.n; j++) idx += val >= sp.x[j] ? 1 : 0;
+  const float4 c = *reinterpret_cast<const float4 *>(spl[idx]);
+  const float c3 = spl[idx][4];
+  const float diff = val - c.x;
+  const float r = c.y + c.z * diff + c.w * diff * diff + c3 * diff * diff * diff;
+  // the end pieces return their y as it is (curves.rs:128-135): 0 * diff would be NaN for an infinite value, which these
+  // kernels, unlike the fused ones, can meet
+  if (val != val) return sp.y_nan;
+  if (idx == 0 || idx == sp.n) return c.y;
+  return r;
+}
+
+// CURVE != 0: OpBaseCurve (curves.rs:38-47: the spline on L, a and b untouched) applied to the pixel before it is
+// stored — the two ops as one pass when nobody asked for the buffer between them (Pipeline::run without a cache).
+// 1: the reference's binary search (any knots); 2: sorted knots, piece table in shared memory.
+template <int CURVE>
 __global__ void __launch_bounds__(kLutThreads)
-k_tolab(const __grid_constant__ ColorParams P, const float2 *__restrict__ lut_lab, const float *__restrict__ in,
-        size_t npix, float *__restrict__ out) {
+k_tolab(const __grid_constant__ ColorParams P, const float2 *__restrict__ lut_lab, const float *__restrict__ cbrt_tab,
+        const float *__restrict__ in, size_t npix, float *__restrict__ out) {
   extern __shared__ __align__(16) unsigned char lut_smem[];
   float2 *tab = reinterpret_cast<float2 *>(lut_smem);
+  float (*spl)[8] = reinterpret_cast<float (*)[8]>(lut_smem + kLutEntries * sizeof(float2));
+  if (CURVE == 2) {
+    for (int i = threadIdx.x; i <= P.sp.n; i += kLutThreads) {
+      float e[5] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
+      if (i == 0) e[1] = P.sp.y_first;
+      else if (i >= P.sp.n) e[1] = P.sp.y_last;
+      else { e[0] = P.sp.x[i - 1]; e[1] = P.sp.y[i - 1]; e[2] = P.sp.c1[i - 1]; e[3] = P.sp.c2[i - 1]; e[4] = P.sp.c3[i - 1]; }
+      for (int k = 0; k < 5; k++) spl[i][k] = e[k];
+    }
+  }
   load_lut_smem(tab, lut_lab);
-  const LutSmemPtr lab{tab};
-  for (size_t idx = (size_t)blockIdx.x * kLutThreads + threadIdx.x; idx < npix; idx += (size_t)gridDim.x * kLutThreads) {
-    const float4 px = __ldg(reinterpret_cast<const float4 *>(in) + idx);
+  const LutSmemCbrt lab{tab, cbrt_tab};
+  // the next pixel is requested before this one is worked on (a pixel is ~230 instructions behind one 16-byte load)
+  const size_t step = (size_t)gridDim.x * kLutThreads;
+  size_t idx = (size_t)blockIdx.x * kLutThreads + threadIdx.x;
+  float4 nxt = idx < npix ? __ldg(reinterpret_cast<const float4 *>(in) + idx) : make_float4(0.f, 0.f, 0.f, 0.f);
+  for (; idx < npix; idx += step) {
+    const float4 px = nxt;
+    if (idx + step < npix) nxt = __ldg(reinterpret_cast<const float4 *>(in) + idx + step);
     float l, a, b;
     camera_to_lab<false>(P, lab, px.x, px.y, px.z, px.w, l, a, b);
+    if (CURVE == 1) l = spline_eval(P.sp, l);
+    if (CURVE == 2) l = spline_sorted(spl, P.sp, l);
     out[idx * 3 + 0] = l;
     out[idx * 3 + 1] = a;
     out[idx * 3 + 2] = b;
@@ -362,14 +455,21 @@ static int lut_grid(size_t work_items) {
   const size_t cap = (size_t)sms * 3;
   return (int)(blocks < cap ? (blocks ? blocks : 1) : cap);
 }
-cudaError_t launch_tolab(cudaStream_t s, const ColorParams &P, const float2 *lut_lab, const float *in, size_t npix,
-                         float *out) {
-  if (npix == 0) return cudaSuccess;
-  const size_t smem = kLutEntries * sizeof(float2);
-  cudaError_t e = cudaFuncSetAttribute(k_tolab, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+template <int CURVE>
+static cudaError_t launch_tolab_kind(cudaStream_t s, const ColorParams &P, const float2 *lut_lab, const float *cbrt_tab,
+                                     const float *in, size_t npix, float *out) {
+  const size_t smem = kLutEntries * sizeof(float2) + (kMaxSplinePts + 2) * 8 * sizeof(float);
+  cudaError_t e = cudaFuncSetAttribute(k_tolab<CURVE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  k_tolab<<<lut_grid(npix), kLutThreads, smem, s>>>(P, lut_lab, in, npix, out);
+  k_tolab<CURVE><<<lut_grid(npix), kLutThreads, smem, s>>>(P, lut_lab, cbrt_tab, in, npix, out);
   return cudaGetLastError();
+}
+cudaError_t launch_tolab(cudaStream_t s, const ColorParams &P, const float2 *lut_lab, const float *cbrt_tab, int curve,
+                         const float *in, size_t npix, float *out) {
+  if (npix == 0) return cudaSuccess;
+  if (curve == 2) return launch_tolab_kind<2>(s, P, lut_lab, cbrt_tab, in, npix, out);
+  if (curve == 1) return launch_tolab_kind<1>(s, P, lut_lab, cbrt_tab, in, npix, out);
+  return launch_tolab_kind<0>(s, P, lut_lab, cbrt_tab, in, npix, out);
 }
 
 // ------------------------------------------------------------------ K5 basecurve (curves.rs:33-49)
@@ -411,9 +511,39 @@ __global__ void k_fromlab(const __grid_constant__ ColorParams P, const float *__
   out[idx * 3 + 1] = g;
   out[idx * 3 + 2] = b;
 }
-cudaError_t launch_fromlab(cudaStream_t s, const ColorParams &P, const float *in, size_t npix, float *out) {
+// from_lab and OpGamma (gamma.rs:21) as one pass when nobody asked for the buffer between them
+__global__ void __launch_bounds__(kLutThreads)
+k_fromlab_gamma(const __grid_constant__ ColorParams P, const float2 *__restrict__ lut_gamma, const float *__restrict__ in,
+                size_t npix, float *__restrict__ out) {
+  extern __shared__ __align__(16) unsigned char lut_smem[];
+  float2 *tab = reinterpret_cast<float2 *>(lut_smem);
+  load_lut_smem(tab, lut_gamma);
+  const LutSmemPtr gam{tab};
+  const size_t step = (size_t)gridDim.x * kLutThreads;
+  size_t idx = (size_t)blockIdx.x * kLutThreads + threadIdx.x;
+  float n0 = 0.f, n1 = 0.f, n2 = 0.f;
+  if (idx < npix) { n0 = in[idx * 3 + 0]; n1 = in[idx * 3 + 1]; n2 = in[idx * 3 + 2]; }
+  for (; idx < npix; idx += step) {
+    const float l = n0, a = n1, bb = n2;
+    if (idx + step < npix) { n0 = in[(idx + step) * 3 + 0]; n1 = in[(idx + step) * 3 + 1]; n2 = in[(idx + step) * 3 + 2]; }
+    float r, g, b;
+    lab_to_rgb<false>(P, l, a, bb, r, g, b);
+    out[idx * 3 + 0] = gamma_elem(gam, r);
+    out[idx * 3 + 1] = gamma_elem(gam, g);
+    out[idx * 3 + 2] = gamma_elem(gam, b);
+  }
+}
+cudaError_t launch_fromlab(cudaStream_t s, const ColorParams &P, const float2 *lut_gamma, const float *in, size_t npix,
+                           float *out) {
   if (npix == 0) return cudaSuccess;
-  k_fromlab<<<grid_for(npix, 256), 256, 0, s>>>(P, in, npix, out);
+  if (lut_gamma) {
+    const size_t smem = kLutEntries * sizeof(float2);
+    cudaError_t e = cudaFuncSetAttribute(k_fromlab_gamma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    k_fromlab_gamma<<<lut_grid(npix), kLutThreads, smem, s>>>(P, lut_gamma, in, npix, out);
+  } else {
+    k_fromlab<<<grid_for(npix, 256), 256, 0, s>>>(P, in, npix, out);
+  }
   return cudaGetLastError();
 }
 

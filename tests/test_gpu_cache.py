@@ -131,3 +131,28 @@ def test_stripe_rows_query_leaves_settings_alone(ip, ctx):
     assert p.globals.settings.linear == 1          # sticky state of the last output call (pipeline.rs:452)
     p.stripe_rows(0, 64)
     assert p.globals.settings.linear == 1
+
+
+CURVE_CASES = [((0.5, 0.6),), ((0.3, 0.2), (0.7, 0.9)), ((0.6, 0.5), (0.3, 0.4)), (), ((0.2, 0.6), (0.5, 0.3), (0.8, 0.7))]
+
+
+@pytest.mark.parametrize("points", CURVE_CASES, ids=["default", "two knots", "unsorted", "passthrough", "non-monotone"])
+@pytest.mark.parametrize("matrix_scale", [1.0, 3e37])
+def test_paired_ops_equal_the_separate_ops(ip, ctx, points, matrix_scale):
+    """Pipeline::run without a cache runs to_lab + basecurve and from_lab + gamma as one kernel each (k_tolab<1|2>,
+    k_fromlab_gamma); with a cache every op runs on its own (k_tolab<0>, k_basecurve, k_fromlab, k_gamma) because each
+    result is kept.  Same bits either way: sorted and unsorted knots, a pass-through curve, finite and overflowing
+    (inf / NaN) pixel values."""
+    data = common.synth_cfa(333, 91, seed=77)
+    params = common.raw_params(points=points, matrix=common.CAM_TO_XYZ * np.float32(matrix_scale))
+    p = common.make_ipb_pipeline(ip, data, "raw", params, ctx=ctx)
+    p.set_fused(False)
+    n0 = ctx.launch_count
+    paired = p.run().to_numpy()
+    n_paired = ctx.launch_count - n0
+    cache = ip.Pipeline.new_cache(1 << 28, ctx)
+    n0 = ctx.launch_count
+    separate = p.run(cache).to_numpy()
+    n_separate = ctx.launch_count - n0
+    assert n_paired < n_separate, (n_paired, n_separate)
+    assert_bit_exact(paired, separate, f"paired vs separate, curve {points}, matrix x {matrix_scale}")

@@ -55,7 +55,7 @@ def test_fused_equals_unfused_on_gpu(ip, ctx):
     n0 = ctx.launch_count
     pg.set_fused(False)
     unfused = pg.run().to_numpy()
-    assert ctx.launch_count - n0 >= 6  # gofloat, demosaic, to_lab, basecurve, from_lab, gamma
+    assert ctx.launch_count - n0 >= 4  # gofloat, demosaic, to_lab + basecurve, from_lab + gamma (paired without a cache)
     assert_bit_exact(fused, unfused, "fused vs op-by-op")
 
 
@@ -223,5 +223,5 @@ def test_unbounded_parameters_run_op_by_op(ip, orc, ctx, matrix_scale, wb):
     po, pg = both(ip, orc, ctx, data, params)
     n0 = ctx.launch_count
     got = pg.run().to_numpy()
-    assert ctx.launch_count - n0 >= 6
+    assert ctx.launch_count - n0 >= 4   # gofloat, demosaic, to_lab + basecurve, from_lab + gamma
     assert_bit_exact(got, orc.pipeline_run(po), "op-by-op fallback")

@@ -20,7 +20,7 @@ def test_roundtrip_8bit_all_colors(ip, ctx, fast):
     out = p.output_8bit().to_numpy()
     assert_bit_exact(out, img, f"8-bit round trip, fastpath={fast}")
     if not fast:
-        assert ctx.launch_count - n0 >= 5  # really went through the ops
+        assert ctx.launch_count - n0 >= 4  # really went through the ops (gofloat, to_lab + basecurve, from_lab + gamma, pack)
 
 
 @pytest.mark.parametrize("fast", [True, False])
