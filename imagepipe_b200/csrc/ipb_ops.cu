@@ -178,7 +178,10 @@ __device__ __forceinline__ float dem_bin(uint32_t m, const float v[9]) {
 #pragma unroll
   for (int i = 0; i < 9; i++)
     if ((m >> i) & 1u) s = s + v[i];
-  return __fdiv_rn(s, (float)__popc(m));
+  const int n = __popc(m);
+  // s / 2^k == s * 2^-k for every float (an exact scaling, rounded once either way): Bayer frames never divide
+  if ((n & (n - 1)) == 0) return s * __int_as_float((127 - (31 - __clz(n))) << 23);
+  return __fdiv_rn(s, (float)n);
 }
 
 __global__ void __launch_bounds__(256)
@@ -201,6 +204,15 @@ k_demosaic_full(const __grid_constant__ CfaDev cfa, const float *__restrict__ in
   __syncthreads();
   const int col = blockIdx.x * 256 + threadIdx.x;
   if (col >= w) return;
+  // RGB Bayer (2 x 2, green on one diagonal, red and blue on the other): the colours of positions (row & 1, col & 1) in
+  // bits 2 * (2 * (row & 1) + (col & 1)), plus bit 8 so that the word is non-zero; 0 for every other pattern
+  uint32_t bayer_phase = 0u;
+  if (pw == 2 && ph == 2) {
+    const int c0 = cfa.pat[0], c1 = cfa.pat[1], c2 = cfa.pat[48], c3 = cfa.pat[49];
+    const bool ok = (c1 == 1 && c2 == 1 && ((c0 == 0 && c3 == 2) || (c0 == 2 && c3 == 0))) ||
+                    (c0 == 1 && c3 == 1 && ((c1 == 0 && c2 == 2) || (c1 == 2 && c2 == 0)));
+    if (ok) bayer_phase = 0x100u | (uint32_t)c0 | ((uint32_t)c1 << 2) | ((uint32_t)c2 << 4) | ((uint32_t)c3 << 6);
+  }
   const int row0 = blockIdx.y * kDemRows, row1 = min(h, row0 + kDemRows);
   const int pc = col % pw;
   int pr = row0 % ph;
@@ -228,10 +240,25 @@ k_demosaic_full(const __grid_constant__ CfaDev cfa, const float *__restrict__ in
     const uint2 mm = taps[pr * pw + pc];
     pr = pr + 1 == ph ? 0 : pr + 1;
     float4 o;
-    o.x = dem_bin(mm.x & 0xffffu & valid, v);
-    o.y = dem_bin((mm.x >> 16) & valid, v);
-    o.z = dem_bin(mm.y & 0xffffu & valid, v);
-    o.w = dem_bin((mm.y >> 16) & valid, v);
+    if (bayer_phase != 0u && valid == 0x1ffu) {
+      // RGB Bayer, all nine taps inside the frame: the four means a site can need, then selects (both kinds of site run
+      // the same instructions).  Sums start at +0.0 and add in raster order like the reference's (demosaic.rs:96-114;
+      // 0.0 + x also turns a -0.0 sample into the +0.0 the reference's sum holds); / 4, / 2 and / 1 are exact scalings.
+      const float mg = ((((0.0f + v[1]) + v[3]) + v[5]) + v[7]) * 0.25f;
+      const float md = ((((0.0f + v[0]) + v[2]) + v[6]) + v[8]) * 0.25f;
+      const float mh = ((0.0f + v[3]) + v[5]) * 0.5f, mv = ((0.0f + v[1]) + v[7]) * 0.5f, own = 0.0f + v[4];
+      const int sh = 2 * (2 * (row & 1) + (col & 1));
+      const int c = (bayer_phase >> sh) & 3, ch = (bayer_phase >> (sh ^ 2)) & 3;  // this site's colour, its row neighbours'
+      const bool gsite = c == 1;
+      const int first = gsite ? ch : c;  // the colour (0 or 2) that receives a0
+      const float a0 = gsite ? mh : own, a1 = gsite ? mv : md;
+      o = make_float4(first == 0 ? a0 : a1, gsite ? own : mg, first == 0 ? a1 : a0, 0.0f);
+    } else {
+      o.x = dem_bin(mm.x & 0xffffu & valid, v);
+      o.y = dem_bin((mm.x >> 16) & valid, v);
+      o.z = dem_bin(mm.y & 0xffffu & valid, v);
+      o.w = dem_bin((mm.y >> 16) & valid, v);
+    }
     reinterpret_cast<float4 *>(out)[(size_t)row * w + col] = o;
 #pragma unroll
     for (int i = 0; i < 6; i++) v[i] = v[i + 3];
