@@ -166,6 +166,7 @@ def lib():
         "ipb_stripe_plan": (i, [vp, vp, sz, sz, sz, sz, szp, szp, szp, szp]),
         "ipb_pipeline_set_stripe_source": (i, [vp, vp, vp]),
         "ipb_pipeline_output_8bit_stripe": (i, [vp, vp, sz, i, szp, szp]),
+        "ipb_pipeline_output_8bit_batch": (i, [vp, sz, sz, vp, sz, sz, szp, szp]),
         "ipb_pipeline_set_tma": (i, [vp, i]),
         "ipb_pipeline_set_band_mb": (i, [vp, i]),
         "ipb_pipeline_set_speculative": (i, [vp, i]),

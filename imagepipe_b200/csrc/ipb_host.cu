@@ -82,6 +82,10 @@ struct ipb_pipeline {
   int use_tma = 1;
   unsigned long long source_gen = 0;  // bumped by set_source: part of the cache key (a refilled buffer is a new image)
   int spec = 1;      // 8-bit output of RGB Bayer frames through the speculative kernel (results identical; 0: k_fused_full)
+  // ipb_pipeline_output_8bit_batch in flight: frames of the batch, source rows / output bytes from one to the next, and
+  // whether the launch took them all (else the caller runs them one by one)
+  size_t batch_n = 0, batch_src_rows = 0, batch_out_bytes = 0;
+  bool batch_done = false;
   int band_mb = 16;  // host<->device paths: band size of the overlapped H2D / kernel / D2H schedule (0 = no bands)
   // golevel_rc_exact() result for the last (black, range) pair: the check walks all 65536 samples
   bool rc_cached = false;
@@ -1671,6 +1675,7 @@ static int launch_fused_rows(ipb_pipeline *p, const FusedPlan &plan, const Color
   a.use_tma = p->use_tma;
   // 8-bit output of a full-resolution RGB Bayer frame: the speculative kernel (byte-identical, about a third of the
   // instructions), when its preconditions hold
+  if (p->batch_n > 1) { a.batch_n = p->batch_n; a.batch_src_rows = p->batch_src_rows; a.batch_out_bytes = p->batch_out_bytes; }
   if (plan.mode == kFusedFull && p->spec && a.exact_rc && spec_supported(a, plan.cfa, P)) {
     bool use = false;
     IPB_TRY(ensure_spec_tables(ctx, P, a.black, a.range, &use));
@@ -1678,9 +1683,11 @@ static int launch_fused_rows(ipb_pipeline *p, const FusedPlan &plan, const Color
       cudaError_t es = launch_fused_spec8(ctx->stream, a, plan.cfa, P, ctx->spec_tab, ctx->sm_count, ctx->spec_threads);
       if (es != cudaSuccess) return fail(ctx, IPB_ERR_CUDA, "speculative kernel: %s %s", cudaGetErrorString(es), spec_last_error());
       ctx->launches++;
+      if (p->batch_n > 1) p->batch_done = true;
       return IPB_OK;
     }
   }
+  if (p->batch_n > 1) return IPB_ERR_UNSUPPORTED;   // only k_spec8 takes a batch: the caller runs the frames one by one
   // ... and of a down-scaled one: the same chain behind scaled_demosaic's window phase
   if (scaled_spec && spec_scaled_supported(a, plan.cfa, P)) {
     bool use = false;
@@ -2284,6 +2291,60 @@ int ipb_pipeline_output_8bit_stripe(ipb_pipeline *p, uint8_t *dst, size_t dst_ca
   if (width) *width = plan.out_width;
   if (rows) *rows = r1 - r0;
   return IPB_OK;
+}
+
+// A batch of frames of identical geometry and parameters, device resident, frame k's source rows src_stride_rows * k rows
+// after the pipeline's source (whole image or stripe rows) and its result dst_stride_bytes * k bytes after dst: the same
+// bytes as nframes calls of output_8bit / output_8bit_stripe on shifted pointers.  One launch when the speculative
+// full-resolution kernel applies (its tables, start-up and tail are paid once per batch), else one launch per frame.
+int ipb_pipeline_output_8bit_batch(ipb_pipeline *p, size_t nframes, size_t src_stride_rows, uint8_t *dst, size_t dst_stride_bytes,
+                                   size_t dst_capacity, size_t *width, size_t *rows) {
+  if (!p || !dst) return IPB_ERR_INVALID;
+  ipb_ctx *ctx = p->ctx;
+  IPB_TRY(enter(ctx));
+  ipb_source &src = p->has_stripe ? p->stripe_rows : p->image;
+  if (!src.on_device) return fail(ctx, IPB_ERR_UNSUPPORTED, "output_8bit_batch: device-resident sources only");
+  if (src_stride_rows < src.height) return fail(ctx, IPB_ERR_INVALID, "output_8bit_batch: frames overlap (%zu < %zu rows)", src_stride_rows, src.height);
+  FusedPlan plan;
+  size_t r0, r1;
+  if (p->has_stripe) {
+    IPB_TRY(stripe_plan(p, &plan));
+    r0 = p->stripe.out_row0; r1 = p->stripe.out_row1;
+    if (r0 >= r1 || r1 > plan.out_height) return fail(ctx, IPB_ERR_INVALID, "stripe output rows [%zu,%zu) outside the %zu-row result", r0, r1, plan.out_height);
+  } else {
+    if (p->image.width < 10 || p->image.height < 10) return fail(ctx, IPB_ERR_INVALID, "source smaller than 10x10");
+    p->settings.linear = 0;  // pipeline.rs:405
+    negotiate(p, nullptr, nullptr);
+    IPB_TRY(plan_fused(p, &plan));
+    int flips[3];
+    orientation_flips(&p->ops.transform, flips);
+    if (plan.mode == kNotFused || flips[0] || flips[1] || flips[2])
+      return fail(ctx, IPB_ERR_UNSUPPORTED, "output_8bit_batch: only the fused raw CFA path with Normal orientation (use output_8bit per frame)");
+    r0 = 0; r1 = plan.out_height;
+  }
+  const size_t n = (r1 - r0) * plan.out_width * 3;
+  if (nframes > 0 && (dst_stride_bytes < n || (nframes - 1) * dst_stride_bytes + n > dst_capacity))
+    return fail(ctx, IPB_ERR_INVALID, "output_8bit_batch: destination too small or strides overlap");
+  if (width) *width = plan.out_width;
+  if (rows) *rows = r1 - r0;
+  if (nframes == 0) return IPB_OK;
+  if (nframes > 1) {
+    p->batch_n = nframes; p->batch_src_rows = src_stride_rows; p->batch_out_bytes = dst_stride_bytes; p->batch_done = false;
+    const int rc = run_fused(p, plan, kOutU8, r0, r1, dst);
+    const bool done = p->batch_done;
+    p->batch_n = 0; p->batch_done = false;
+    if (rc == IPB_OK && done) return IPB_OK;
+    if (rc != IPB_OK && rc != IPB_ERR_UNSUPPORTED) return rc;
+  }
+  // frame by frame on shifted pointers
+  const void *base = src.data;
+  int rc = IPB_OK;
+  for (size_t k = 0; k < nframes && rc == IPB_OK; k++) {
+    src.data = (const uint8_t *)base + k * src_stride_rows * src.width * sizeof(uint16_t);
+    rc = run_fused(p, plan, kOutU8, r0, r1, dst + k * dst_stride_bytes);
+  }
+  src.data = base;
+  return rc;
 }
 
 int ipb_pipeline_set_band_mb(ipb_pipeline *p, int megabytes) {

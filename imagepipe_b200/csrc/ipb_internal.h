@@ -45,6 +45,9 @@ struct FusedArgs {
   const float2 *lut_gamma8;  // 8-bit output: {threshold, base} per table segment (ipb_host.cu build_gamma8)
   const float *cbrt_tab;     // full-res kernel: host cbrtf of every float in (1.0, 1.5] (ipb_host.cu ensure_cbrt_table)
   int use_tma;             // full-res kernel: stage tiles with TMA (needs 16B-aligned base and pitch)
+  // a batch of frames with this geometry in one launch (k_spec8 only): frame k's source rows start batch_src_rows * k
+  // rows after raw, its output batch_out_bytes * k bytes after out.  batch_n <= 1: a single frame.
+  size_t batch_n, batch_src_rows, batch_out_bytes;
 };
 
 // ---- ipb_ops.cu

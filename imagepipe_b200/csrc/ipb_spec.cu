@@ -410,7 +410,7 @@ __device__ __forceinline__ float bin_mean_exact(uint32_t m, const float v[9]) {
 // itself; p and P are the copies in shared memory.
 __device__ __noinline__ void fixup_entry(const SpecParams &p, const ColorParams &P, const float (*spl)[8], uint32_t phase,
                                          const uint8_t *pat, const uint2 *taps, uint32_t g8_base, uint32_t thr_base, uint32_t tile_base, int tx0,
-                                         int ty0, uint32_t entry) {
+                                         int ty0, uint8_t *out_f, uint32_t entry) {
   const int r = (int)(entry / kTW), c = (int)(entry % kTW), x = tx0 + c, y = ty0 + r;
   float t[9], v[3], cr, cg, cb;
   if (pat) {   // uniform: one pattern kind per launch
@@ -430,16 +430,28 @@ __device__ __noinline__ void fixup_entry(const SpecParams &p, const ColorParams 
     exact_rgb_bayer(p, phase, x, y, t, cr, cg, cb);
   }
   exact_chain(p, P, spl, cr, cg, cb, v);
-  uint8_t *o = p.out + ((size_t)(y - p.out_row0) * (size_t)p.width + (size_t)x) * 3;
+  uint8_t *o = out_f + ((size_t)(y - p.out_row0) * (size_t)p.width + (size_t)x) * 3;
   o[0] = (uint8_t)gamma8_exact(g8_base, thr_base, v[0]);
   o[1] = (uint8_t)gamma8_exact(g8_base, thr_base, v[1]);
   o[2] = (uint8_t)gamma8_exact(g8_base, thr_base, v[2]);
 }
 
+// tile number t of the launch -> frame of the batch, tile row and column inside the frame
+struct TilePos { int f, tyi, txi; };
+__device__ __forceinline__ TilePos tile_pos(const SpecParams &p, int t) {
+  const int per_frame = p.tiles_x * p.tiles_y;
+  TilePos q;
+  q.f = t / per_frame;
+  const int r = t - q.f * per_frame;
+  q.tyi = r / p.tiles_x;
+  q.txi = r - q.tyi * p.tiles_x;
+  return q;
+}
 __device__ __forceinline__ void issue_tile(const SpecParams &p, const CUtensorMap *tmap, uint32_t raw_stage, uint32_t bar,
-                                           int txi, int tyi) {
-  const int x = txi * kTW - 8 + p.crop_x;
-  const int y = p.out_row0 + tyi * kTH - 1 + p.crop_y - p.src_row0;
+                                           int t) {
+  const TilePos q = tile_pos(p, t);
+  const int x = q.txi * kTW - 8 + p.crop_x;
+  const int y = p.out_row0 + q.tyi * kTH - 1 + p.crop_y - p.src_row0 + q.f * p.frame_src_rows;
   mbar_expect_tx(bar, kTileElems * (uint32_t)sizeof(uint16_t));
   tma_load_2d(raw_stage, tmap, x, y, bar);
 }
@@ -516,16 +528,9 @@ k_spec8(const __grid_constant__ SpecParams p, const __grid_constant__ CfaDev cfa
   SmemSpec &sm = *reinterpret_cast<SmemSpec *>(smem_raw);
   constexpr bool BAYER = MODE < 4, GF0 = (MODE & 2) != 0, AR0 = (MODE & 1) != 0;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int ntiles = p.tiles_x * p.tiles_y;
+  const int ntiles = p.tiles_x * p.tiles_y * p.nframes;   // the frames of a batch are one sequence of tiles
   const uint32_t bar = smem_u32(&sm.mbar), bar_tab = smem_u32(&sm.mbar_tab), raw_addr = smem_u32(sm.raw);
   const uint8_t *pat = BAYER ? nullptr : sm.pat;   // the exact path's pattern kind
-
-  int tyi = (int)blockIdx.x / p.tiles_x, txi = (int)blockIdx.x - tyi * p.tiles_x;
-  const int step_y = (int)gridDim.x / p.tiles_x, step_x = (int)gridDim.x - step_y * p.tiles_x;
-  auto next_tile = [&](int &tx, int &ty) {
-    tx += step_x; ty += step_y;
-    if (tx >= p.tiles_x) { tx -= p.tiles_x; ty++; }
-  };
 
   if (tid == 0) {
     sm.conv_ctr[0] = 0;
@@ -536,7 +541,7 @@ k_spec8(const __grid_constant__ SpecParams p, const __grid_constant__ CfaDev cfa
     mbar_init(bar_tab, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    issue_tile(p, &tmap, raw_addr, bar, txi, tyi);
+    issue_tile(p, &tmap, raw_addr, bar, (int)blockIdx.x);
     constexpr uint32_t kG8Bytes = kSpecG8Entries * 4u, kSTabBytes = kSpecSTabEntries * 8u;
     mbar_expect_tx(bar_tab, kG8Bytes + kSTabBytes);
     bulk_load(smem_u32(sm.g8a), p.g8a, kG8Bytes, bar_tab);
@@ -626,11 +631,7 @@ k_spec8(const __grid_constant__ SpecParams p, const __grid_constant__ CfaDev cfa
   mbar_wait(bar, 0);
   convert_tile(0, 0);
   __syncthreads();
-  {
-    int ntx = txi, nty = tyi;
-    next_tile(ntx, nty);
-    if (tid == 0 && (int)(blockIdx.x + gridDim.x) < ntiles) issue_tile(p, &tmap, raw_addr, bar, ntx, nty);
-  }
+  if (tid == 0 && (int)(blockIdx.x + gridDim.x) < ntiles) issue_tile(p, &tmap, raw_addr, bar, (int)(blockIdx.x + gridDim.x));
   mbar_wait(bar_tab, 0);
 
   // queue the uncertified pixels of a task (entry = row * kTW + column of its first pixel, inside the tile); the queue
@@ -644,14 +645,15 @@ k_spec8(const __grid_constant__ SpecParams p, const __grid_constant__ CfaDev cfa
     }
   };
   // whole words can be stored when every row starts on a 4-byte boundary
-  const bool rows_aligned = ((reinterpret_cast<uintptr_t>(p.out) & 3) == 0) && ((p.width & 3) == 0);
+  const bool rows_aligned = ((reinterpret_cast<uintptr_t>(p.out) & 3) == 0) && ((p.width & 3) == 0) && ((p.frame_out_bytes & 3) == 0);
 
   int it = 0;
   int fix_warps = 0;                 // warps that recomputed pixels of the previous tile at the top of this iteration
   unsigned long long nfix = 0;       // thread 0: pixels recomputed by this CTA
   for (int t = blockIdx.x; t < ntiles; t += gridDim.x, it++) {
-    const int ty0 = p.out_row0 + tyi * kTH, tx0 = txi * kTW;
-    next_tile(txi, tyi);
+    const TilePos tp = tile_pos(p, t);
+    const int ty0 = p.out_row0 + tp.tyi * kTH, tx0 = tp.txi * kTW;
+    uint8_t *const out_f = p.out + (size_t)tp.f * (size_t)p.frame_out_bytes;   // this tile's frame of the batch
     const uint32_t tile_base = smem_u32(&sm.plane[it & 1][0][0][0]);
     const uint32_t qaddr = smem_u32(&sm.qn[it & 1]);
     // a tile is "inner" when all its pixels exist, are wanted, and have their nine taps inside the frame
@@ -705,7 +707,7 @@ k_spec8(const __grid_constant__ SpecParams p, const __grid_constant__ CfaDev cfa
       }
       const uint32_t pix = pix0 + (uint32_t)r * (uint32_t)p.width;
       if (inner) {
-        uint32_t *o4 = reinterpret_cast<uint32_t *>(p.out + (size_t)pix * 3);
+        uint32_t *o4 = reinterpret_cast<uint32_t *>(out_f + (size_t)pix * 3);
         o4[0] = words[0]; o4[1] = words[1]; o4[2] = words[2];
         if (flags && !(p.dbg & 2)) push(qaddr, flags, (uint32_t)(r * kTW + 4 * lane));
       } else {
@@ -713,7 +715,7 @@ k_spec8(const __grid_constant__ SpecParams p, const __grid_constant__ CfaDev cfa
         const bool live = y < p.out_row1 && x0 < p.width;
         if (live) {
           const int npx = min(4, p.width - x0);
-          uint8_t *o = p.out + (size_t)pix * 3;
+          uint8_t *o = out_f + (size_t)pix * 3;
           if (npx == 4 && ((reinterpret_cast<uintptr_t>(o) & 3) == 0)) {
             uint32_t *o4 = reinterpret_cast<uint32_t *>(o);
             o4[0] = words[0]; o4[1] = words[1]; o4[2] = words[2];
@@ -746,11 +748,7 @@ k_spec8(const __grid_constant__ SpecParams p, const __grid_constant__ CfaDev cfa
       sm.qn[(it + 1) & 1] = 0;   // the next tile's queue length; its last readers passed the second barrier of the previous iteration
     }
     __syncthreads();
-    if (tid == 0 && t + 2 * (int)gridDim.x < ntiles) {
-      int ntx = txi, nty = tyi;
-      next_tile(ntx, nty);
-      issue_tile(p, &tmap, raw_addr, bar, ntx, nty);
-    }
+    if (tid == 0 && t + 2 * (int)gridDim.x < ntiles) issue_tile(p, &tmap, raw_addr, bar, t + 2 * (int)gridDim.x);
     // Uncertified pixels of this tile are recomputed exactly from the tile's planes, densely: entry i goes to thread i, so
     // the first ceil(n / 32) warps do the work with all lanes busy while the others start the next tile.  The barrier
     // above ordered every push before these reads; the one below frees the queue for the next tile's pushes.
@@ -758,14 +756,14 @@ k_spec8(const __grid_constant__ SpecParams p, const __grid_constant__ CfaDev cfa
     const bool recompute = !(p.dbg & 1);
     if (qn > NT && recompute)   // more than one entry per thread (dark frames, the bound at its cap): all threads, right here
       for (int i = NT + tid; i < qn; i += NT)
-        fixup_entry(sm.sp, sm.cp, sm.spl, phase, pat, sm.taps, g8_base, thr_base, tile_base, tx0, ty0, sm.queue[i]);
+        fixup_entry(sm.sp, sm.cp, sm.spl, phase, pat, sm.taps, g8_base, thr_base, tile_base, tx0, ty0, out_f, sm.queue[i]);
     const uint32_t mine = tid < qn ? (uint32_t)sm.queue[tid] : 0xffffffffu;
     __syncthreads();
     if (tid == 0) nfix += (unsigned long long)qn;
     fix_warps = min((qn + 31) >> 5, NT / 32);
     if (warp < fix_warps) {
       if (mine != 0xffffffffu && recompute)
-        fixup_entry(sm.sp, sm.cp, sm.spl, phase, pat, sm.taps, g8_base, thr_base, tile_base, tx0, ty0, mine);
+        fixup_entry(sm.sp, sm.cp, sm.spl, phase, pat, sm.taps, g8_base, thr_base, tile_base, tx0, ty0, out_f, mine);
       if (have_next) asm volatile("bar.arrive 1, %0;" ::"n"(NT) : "memory");
     }
     if (!have_next) fix_warps = 0;
@@ -1059,6 +1057,11 @@ bool spec_supported(const FusedArgs &a, const CfaDev &cfa, const ColorParams &P)
   if (a.width < 8 || a.height < 4) return false;
   if (a.width >= 65536 || a.out_row1 - a.out_row0 >= 65536) return false;  // queue entries are row << 16 | column
   if (a.height >= (1u << 24)) return false;  // n % period by multiplication (k_spec8, generic patterns)
+  if (a.batch_n > 1) {   // tile numbers and tensor-map rows of the whole batch stay inside 31 bits
+    const unsigned long long tiles = (unsigned long long)((a.width + kTW - 1) / kTW) * ((a.out_row1 - a.out_row0 + kTH - 1) / kTH);
+    if (tiles * a.batch_n >= (1ull << 30) || (unsigned long long)a.batch_src_rows * a.batch_n >= (1ull << 30)) return false;
+    if (a.batch_src_rows < a.src_rows) return false;   // frames must not overlap
+  }
   return true;
 }
 
@@ -1087,13 +1090,18 @@ cudaError_t launch_fused_spec8(cudaStream_t s, const FusedArgs &a, const CfaDev 
   p.g8a = T.g8a; p.stab = T.stab; p.thr8 = T.thr8; p.stats = T.stats;
   p.tiles_x = (p.width + kTW - 1) / kTW;
   p.tiles_y = (p.out_row1 - p.out_row0 + kTH - 1) / kTH;
+  p.nframes = a.batch_n > 1 ? (int)a.batch_n : 1;
+  p.frame_src_rows = p.nframes > 1 ? (int)a.batch_src_rows : 0;
+  p.frame_out_bytes = p.nframes > 1 ? (long long)a.batch_out_bytes : 0;
+  // one tensor map over the rows of all frames: a box that reaches into the neighbouring frame (or past the last one:
+  // zero fill) only fetches taps that the frame-border logic never uses
   CUtensorMap tmap;
   memset(&tmap, 0, sizeof(tmap));
-  if (!make_raw_tmap(&tmap, a.raw, a.raw_pitch, a.src_rows)) {
+  if (!make_raw_tmap(&tmap, a.raw, a.raw_pitch, (size_t)(p.nframes - 1) * (size_t)p.frame_src_rows + a.src_rows)) {
     g_spec_err = "spec8: tensor map";
     return cudaErrorInvalidValue;
   }
-  const int ntiles = p.tiles_x * p.tiles_y;
+  const int ntiles = p.tiles_x * p.tiles_y * p.nframes;
   p.pw = cfa.width; p.ph = cfa.height;
   p.rcp_pw = (uint32_t)(0x100000000ull / (unsigned long long)cfa.width) + 1u;
   p.rcp_ph = (uint32_t)(0x100000000ull / (unsigned long long)cfa.height) + 1u;
@@ -1175,6 +1183,7 @@ cudaError_t launch_spec_probe(cudaStream_t s, const FusedArgs &a, const CfaDev &
   p.width = (int)a.width; p.height = (int)a.height;
   p.out_row0 = 0; p.out_row1 = (int)a.height;
   p.out = nullptr;
+  p.nframes = 1; p.frame_src_rows = 0; p.frame_out_bytes = 0;
   p.black = a.black; p.range = a.range; p.range_rc = a.range_rc; p.exact_rc = a.exact_rc;
   {
     const bool integral = a.black >= 0.0f && a.black < 4194304.0f && a.black == floorf(a.black);

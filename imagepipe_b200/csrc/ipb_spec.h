@@ -24,6 +24,9 @@ struct SpecParams {
   int out_row0, out_row1;
   uint8_t *out;
   int tiles_x, tiles_y;
+  int nframes;                // frames of identical geometry in this launch (a batch), >= 1
+  int frame_src_rows;         // ... source rows from one frame to the next
+  long long frame_out_bytes;  // ... output bytes from one frame to the next
   int pw, ph;                 // CFA period (generic-pattern variant)
   uint32_t rcp_pw, rcp_ph;    // floor(2^32 / period) + 1: n % d = n - mulhi(n, rcp) * d while n * d < 2^32
   // ---- exact path (fix-ups)

@@ -575,6 +575,15 @@ class Pipeline:
             host = host[: ow.value * orows.value * 3]
         return SRGBImage(ow.value, orows.value, host)
 
+    def output_8bit_batch(self, nframes, src_stride_rows, dst, dst_stride_bytes):
+        """ipb_pipeline_output_8bit_batch: nframes device-resident frames of this pipeline's geometry, frame k's source
+        rows src_stride_rows * k rows after the pipeline's source (image or stripe rows), its result dst_stride_bytes * k
+        bytes into the DeviceArray dst.  Returns (width, rows) of one result."""
+        ow, orows = C.c_size_t(), C.c_size_t()
+        _capi.check(self.ctx.handle, lib().ipb_pipeline_output_8bit_batch(self.handle, nframes, src_stride_rows, dst.ptr,
+                                                                       dst_stride_bytes, dst.nbytes, C.byref(ow), C.byref(orows)))
+        return ow.value, orows.value
+
     def close(self):
         if self.handle and self.ctx.handle:
             lib().ipb_pipeline_destroy(self.handle)

@@ -329,6 +329,15 @@ int ipb_stripe_plan(const ipb_ops *ops, const ipb_settings *settings, size_t wid
 int ipb_pipeline_set_stripe_source(ipb_pipeline *p, const ipb_source *rows, const ipb_stripe *stripe);
 int ipb_pipeline_output_8bit_stripe(ipb_pipeline *p, uint8_t *dst, size_t dst_capacity, int dst_on_device,
                                     size_t *width, size_t *rows);
+/* A batch of frames in one call (extension: the reference's Pipeline::output_8bit, pipeline.rs:377-422, takes one image;
+ * a caller that converts many frames of one camera — BASELINE config 4, or the stripes of several frames in flight —
+ * pays kernel start-up and tail once per batch instead of once per frame).  nframes frames of identical geometry and
+ * parameters, all on the device: frame k's source rows begin src_stride_rows * k rows after the pipeline's source
+ * (the whole image, or the stripe rows given to ipb_pipeline_set_stripe_source), its result dst_stride_bytes * k bytes
+ * after dst.  Same bytes as nframes calls of ipb_pipeline_output_8bit / _stripe on shifted pointers.  Only for the
+ * fused raw CFA path with Normal orientation (IPB_ERR_UNSUPPORTED otherwise). */
+int ipb_pipeline_output_8bit_batch(ipb_pipeline *p, size_t nframes, size_t src_stride_rows, uint8_t *dst,
+                                   size_t dst_stride_bytes, size_t dst_capacity, size_t *width, size_t *rows);
 
 /* Halo exchange between stripe neighbours: the only collective of the path.  One process per
  * GPU; rank r holds stripe r.  NCCL is resolved at run time (dlopen of libnccl.so.2): the library links neither NCCL

@@ -221,6 +221,7 @@ extern "C" {
     pub fn ipb_stripe_plan(ops: *const ipb_ops, settings: *const ipb_settings, width: usize, height: usize, out_row0: usize, out_row1: usize, src_row0: *mut usize, src_row1: *mut usize, out_width: *mut usize, out_height: *mut usize) -> c_int;
     pub fn ipb_pipeline_set_stripe_source(p: *mut ipb_pipeline, rows: *const ipb_source, stripe: *const ipb_stripe) -> c_int;
     pub fn ipb_pipeline_output_8bit_stripe(p: *mut ipb_pipeline, dst: *mut u8, dst_capacity: usize, dst_on_device: c_int, width: *mut usize, rows: *mut usize) -> c_int;
+    pub fn ipb_pipeline_output_8bit_batch(p: *mut ipb_pipeline, nframes: usize, src_stride_rows: usize, dst: *mut u8, dst_stride_bytes: usize, dst_capacity: usize, width: *mut usize, rows: *mut usize) -> c_int;
     pub fn ipb_comm_unique_id(id: *mut u8) -> c_int;
     pub fn ipb_comm_create(device: c_int, stream: *mut c_void, id: *const u8, rank: c_int, nranks: c_int, out: *mut *mut ipb_comm) -> c_int;
     pub fn ipb_comm_destroy(comm: *mut ipb_comm);

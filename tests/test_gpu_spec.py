@@ -302,3 +302,71 @@ def test_scaled_full_size_spec_equals_exact_kernel(ip, ctx):
         if spec:
             assert 0 < ctx.spec_stats()["fixups"] < 1500 * 1000 * 0.1
     assert outs[0].shape == (1000, 1500, 3) and np.array_equal(outs[0], outs[1])
+
+
+# ---------------------------------------------------------------- batches of frames in one launch
+
+@pytest.mark.parametrize("case", ["bayer", "xtrans", "gap rows", "odd height", "plain width (frame by frame)",
+                                  "scaled (frame by frame)"])
+def test_batch_equals_single_frames(ip, orc, ctx, case):
+    """ipb_pipeline_output_8bit_batch: several frames stacked in one device buffer, one k_spec8 launch over all of them
+    (tiles of consecutive frames form one sequence; a tile's halo may reach into the neighbouring frame, which only
+    feeds taps the frame-border logic ignores) == each frame through output_8bit == the oracle."""
+    w, h, n, gap = 1024, 192, 3, 0
+    cfa, st = "GRBG", {}
+    if case == "xtrans":
+        cfa = common.XTRANS
+    elif case == "gap rows":
+        gap = 5
+    elif case == "odd height":
+        h = 203
+    elif case.startswith("plain width"):
+        w = 1030            # rows not on 16-byte boundaries: no TMA, the batch runs frame by frame through k_fused_full
+    elif case.startswith("scaled"):
+        st = {"maxwidth": 256, "maxheight": 0}
+    params = common.raw_params(cfa=cfa)
+    stride = h + gap
+    stack = np.full((n * stride, w), 60000, np.uint16)      # gap rows hold a value no frame contains
+    frames = [common.synth_cfa(w, h, seed=90 + k) for k in range(n)]
+    for k, fr in enumerate(frames):
+        stack[k * stride:k * stride + h] = fr
+    d = ip.DeviceArray.from_numpy(stack, ctx)
+    p = ip.Pipeline.new_from_source(ip.ImageSource.Raw(d, w, h), ctx=ctx)
+    common.fill_ipb_ops(p.ops, params)
+    for k_, v in st.items():
+        setattr(p.globals.settings, k_, int(v))
+    ow, oh = (256, 48) if st else (w, h)
+    nbytes = ow * oh * 3
+    dstride = nbytes + 64                                    # results need not be packed either
+    dst = ip.DeviceArray(n * dstride, ctx)
+    n0 = ctx.launch_count
+    got_w, got_h = p.output_8bit_batch(n, stride, dst, dstride)
+    launches = ctx.launch_count - n0
+    assert (got_w, got_h) == (ow, oh)
+    assert launches == (n if "frame by frame" in case else 1), launches
+    out = dst.to_numpy(np.uint8)
+    for k, fr in enumerate(frames):
+        want = orc.pipeline_output_8bit(orc.make_pipeline(fr, "raw", params, st))
+        assert_bit_exact(out[k * dstride:k * dstride + nbytes].reshape(oh, ow, 3), want, f"{case}: frame {k} of the batch")
+
+
+def test_batch_of_stripes(ip, ctx):
+    """The stripe form: three frames' rows [r0-1, r1+1) stacked, one launch, each == the stripe run alone."""
+    w, h, n, r0, r1 = 768, 300, 3, 96, 211
+    frames = [common.synth_cfa(w, h, seed=70 + k) for k in range(n)]
+    params = common.raw_params()
+    p = common.make_ipb_pipeline(ip, frames[0], "raw", params, ctx=ctx)
+    s0, s1 = p.stripe_rows(r0, r1)
+    rows = s1 - s0
+    stack = np.concatenate([fr[s0:s1] for fr in frames], 0)
+    d = ip.DeviceArray.from_numpy(stack, ctx)
+    p.set_stripe_source(ip.ImageSource.Raw(d, w, rows), s0, r0, r1)
+    nbytes = (r1 - r0) * w * 3
+    dst = ip.DeviceArray(n * nbytes, ctx)
+    n0 = ctx.launch_count
+    assert p.output_8bit_batch(n, rows, dst, nbytes) == (w, r1 - r0)
+    assert ctx.launch_count - n0 == 1
+    out = dst.to_numpy(np.uint8).reshape(n, r1 - r0, w, 3)
+    for k, fr in enumerate(frames):
+        whole = common.make_ipb_pipeline(ip, fr, "raw", params, ctx=ctx).output_8bit().to_numpy()
+        assert_bit_exact(out[k], whole[r0:r1], f"stripe of frame {k}")
