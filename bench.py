@@ -241,7 +241,8 @@ def strong_leg(args, ip, common, torch, dist, ctx, stream, barrier, rank, world,
     rank runs one fused launch on its stripe.  Returns the dict of the JSON line's "strong" key (rank 0) — with
     `parity`: every rank's stripe equals, byte for byte, the same rows of a single-launch run of the whole frame."""
     from imagepipe_b200 import _capi
-    from imagepipe_b200.sharded import Comm, DevicePtr, exchange_halos_nccl, halo_plan, plan_stripes, run_stripe_8bit
+    from imagepipe_b200.sharded import (Comm, DevicePtr, exchange_halos_nccl, halo_plan, plan_stripes, run_stripe_8bit,
+                                        run_stripes_8bit_batch)
     W5, H5 = 11648, 8736
     mp5 = W5 * H5 / 1e6
     dummy = ip.DeviceArray(64, ctx)
@@ -257,15 +258,21 @@ def strong_leg(args, ip, common, torch, dist, ctx, stream, barrier, rank, world,
         box = [Comm.unique_id() if rank == 0 else None]
         dist.broadcast_object_list(box, src=0)
         comm = Comm(box[0], rank, world, local_rank, stream.cuda_stream)
-    bufs, outs = [], []
+    src_rows_me = me.src_row1 - me.src_row0
     with torch.cuda.stream(stream):
+        # the stripes of the nsets frames in flight sit one after the other in one allocation (so do their results): they
+        # can be converted by one batched launch after one grouped exchange
+        in_block = torch.zeros((nsets, src_rows_me, W5), dtype=torch.int16, device="cuda")
+        out_block = torch.empty((nsets, rows_out, W5, 3), dtype=torch.uint8, device="cuda")
+        bufs = [in_block[i] for i in range(nsets)]
+        outs = [out_block[i] for i in range(nsets)]
         for i in range(nsets):
-            b = torch.zeros((me.src_row1 - me.src_row0, W5), dtype=torch.int16, device="cuda")
-            own = b[me.own_row0 - me.src_row0: me.own_row1 - me.src_row0]
+            own = bufs[i][me.own_row0 - me.src_row0: me.own_row1 - me.src_row0]
             ip.lib().ipb_synth_cfa_u16(ctx.handle, common.SEED + i, W5, me.own_row0, me.own_row1 - me.own_row0, own.data_ptr())
-            bufs.append(b)
-            outs.append(torch.empty((rows_out, W5, 3), dtype=torch.uint8, device="cuda"))
     ptrs = [b.data_ptr() for b in bufs]
+    # measured (profiles/r02e_batch.txt): behind the grouped exchange, inside a CUDA graph, one launch per stripe is as fast
+    # (2 GPUs) or faster (8 GPUs: 80 against 85 us per stripe) than one batched launch per step, so that is the default here
+    batched = args.strong_batch
     hp = halo_plan(lays, rank, W5 * 2)
     halo_bytes = hp.send_up_bytes + hp.send_down_bytes + hp.recv_up_bytes + hp.recv_down_bytes
 
@@ -274,11 +281,16 @@ def strong_leg(args, ip, common, torch, dist, ctx, stream, barrier, rank, world,
     # (tens of microseconds, against < 0.1 ms of compute per stripe at 8 GPUs) is paid once per step.
     F = nsets
 
+    out_all = DevicePtr(out_block.data_ptr(), out_block.numel())
+
     def step():
         if comm is not None:
             exchange_halos_nccl(comm, ptrs, lays, W5 * 2)
-        for j in range(F):
-            run_stripe_8bit(p, ptrs[j], me, DevicePtr(outs[j].data_ptr(), outs[j].numel()))
+        if batched:   # the F stripes in one launch (ipb_pipeline_output_8bit_batch on the stripe source)
+            run_stripes_8bit_batch(p, ptrs[0], F, me, out_all)
+        else:
+            for j in range(F):
+                run_stripe_8bit(p, ptrs[j], me, DevicePtr(outs[j].data_ptr(), outs[j].numel()))
 
     with torch.cuda.stream(stream):
         for _ in range(Wm):
@@ -371,11 +383,12 @@ def strong_leg(args, ip, common, torch, dist, ctx, stream, barrier, rank, world,
     launch_ms = total_ms / (K * F)
     return {
         "workload": "C5: 11648x8736 RGGB Bayer -> 8-bit sRGB, one frame cut into row stripes (one per GPU), halo rows "
-                    "by ipb_halo_exchange (NCCL send/recv), one fused launch per stripe",
+                    "by ipb_halo_exchange (NCCL send/recv), " +
+                    ("the stripes of the step's frames in one batched launch" if batched else "one fused launch per stripe"),
         "value": value, "unit": "MP/s", "scaling": "strong", "steps": K, "frames_per_step": F,
         "ms_per_step": total_ms / K, "ms_per_frame": launch_ms, "stripe_rows": rows_out,
         "halo_rows": (me.own_row0 - me.src_row0) + (me.src_row1 - me.own_row1), "halo_bytes": int(halo_bytes),
-        "launch": mode, "nccl": Comm.nccl_version() if world > 1 else None,
+        "launch": mode, "launches_per_step": 1 if batched else F, "nccl": Comm.nccl_version() if world > 1 else None,
         "buffer_sets": nsets, "set_mb": set_bytes / 1e6,
         "achieved_gbs": ALGO_BYTES_PER_PX * rows_out * W5 / (launch_ms / 1e3) / 1e9,
         "e2e": {"value": e2e_value, "unit": "MP/s", "h2d_bytes_per_frame": src_rows * W5 * 2,
@@ -409,7 +422,7 @@ def run_c5(args, ip, common, torch, dist, ctx, stream, barrier, rank, world, loc
                          "algorithmic_bytes_per_launch": ALGO_BYTES_PER_PX * st["stripe_rows"] * 11648},
             "e2e": {"value": st["e2e"]["value"], "unit": "MP/s", "h2d_bytes_per_step": st["e2e"]["h2d_bytes_per_frame"],
                     "d2h_bytes_per_step": st["e2e"]["d2h_bytes_per_frame"], "matches_device_path": st["e2e"]["matches_device_path"]},
-            "gpu_launches": int(K * st["frames_per_step"]), "clocks": clocks, "parity": st["parity"],
+            "gpu_launches": int(K * st["launches_per_step"]), "clocks": clocks, "parity": st["parity"],
         }
         print(json.dumps(line), flush=True)
 
@@ -423,6 +436,10 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--frames-per-step", type=int, default=None)
     ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling (C5 stripes) leg of the default line")
+    ap.add_argument("--strong-batch", action="store_true",
+                    help="strong-scaling leg: the stripes of a step's frames in one batched launch instead of one launch each")
+    ap.add_argument("--no-batch", action="store_true",
+                    help="one output_8bit call (one launch) per frame instead of ipb_pipeline_output_8bit_batch over the buffer sets")
     ap.add_argument("--no-graph", action="store_true", help="c5: launch every frame from Python instead of replaying a CUDA graph")
     ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c4", "c5"],
                     help="c2 (default, the contract's line): 24 MP frames, replicas; c3: 45 MP X-Trans frames; c4: 24 MP frames "
@@ -470,12 +487,18 @@ def main():
         if world > 1:
             dist.destroy_process_group()
         return
-    # NSETS distinct synthetic frames, generated on the device, and NSETS output buffers
-    frames = [ip.synth_cfa_u16(common.SEED + rank * 1000 + i, W, 0, H, ctx=ctx) for i in range(NSETS)]
-    outs = [ip.DeviceArray(OUT_W * OUT_H * 3, ctx) for _ in range(NSETS)]
+    # NSETS distinct synthetic frames, generated on the device, and NSETS output buffers, each kind in
+    # one allocation so that the sets can also be handed over as one batch
+    from imagepipe_b200.sharded import DevicePtr
+    frame_bytes, out_bytes = W * H * 2, OUT_W * OUT_H * 3
+    frames_block = ip.DeviceArray(NSETS * frame_bytes, ctx)
+    outs_block = ip.DeviceArray(NSETS * out_bytes, ctx)
+    for i in range(NSETS):
+        ip.lib().ipb_synth_cfa_u16(ctx.handle, common.SEED + rank * 1000 + i, W, 0, H, frames_block.ptr + i * frame_bytes)
+    outs = [DevicePtr(outs_block.ptr + i * out_bytes, out_bytes, keep=outs_block) for i in range(NSETS)]
     pipes = []
     for i in range(NSETS):
-        src = ip.ImageSource.Raw(frames[i], width=W, height=H, cpp=1)
+        src = ip.ImageSource(ip._capi.SRC_RAW_U16, W, H, 1, frames_block.ptr + i * frame_bytes, keep=frames_block)
         p = ip.Pipeline.new_from_source(src, ctx=ctx)
         common.fill_ipb_ops(p.ops, params)
         for k, v in SETTINGS.items():
@@ -483,9 +506,21 @@ def main():
         assert p.output_size() == (OUT_W, OUT_H)
         pipes.append(p)
 
-    def step():
+    # A step is F frames.  Per frame: one Pipeline.output_8bit call (the reference's API shape), one launch.  Batched
+    # (default): ipb_pipeline_output_8bit_batch over the NSETS frames at a time — one launch per batch where the
+    # full-resolution speculative kernel applies (start-up and tail once per batch), the same per-frame launches inside
+    # the C call elsewhere (C4).
+    batched = not args.no_batch and F % NSETS == 0
+
+    def step_frames():
         for j in range(F):
             pipes[j % NSETS].output_8bit(dst=outs[j % NSETS])
+
+    def step_batches():
+        for _ in range(F // NSETS):
+            pipes[0].output_8bit_batch(NSETS, H, outs_block, out_bytes)
+
+    step = step_batches if batched else step_frames
 
     for _ in range(Wm):
         step()
@@ -506,10 +541,24 @@ def main():
     st = ctx.spec_stats()
     # pixels recomputed exactly per launch, as a fraction of the pixels a launch produces (every workload runs a
     # speculative kernel now: k_spec8 on C2 / C3, k_spec8_scaled on C4)
-    spec_stats = {"recomputed_fraction": st["fixups"] / max(1, launches) / (OUT_W * OUT_H), "certified_delta": st["delta"],
+    spec_stats = {"recomputed_fraction": st["fixups"] / max(1, K * F) / (OUT_W * OUT_H), "certified_delta": st["delta"],
                   "xu_cbrt_rel_err": st["mufu_err"]}
     total_ms = ev[0].elapsed_time(ev[K])
     step_ms = [ev[k].elapsed_time(ev[k + 1]) for k in range(K)]
+    per_frame_calls = None
+    if batched:   # the same frames through one output_8bit call each (device resident), for comparison
+        kk = max(2, min(K, 5))
+        step_frames()
+        pe = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        with torch.cuda.stream(stream):
+            pe[0].record(stream)
+            for _ in range(kk):
+                step_frames()
+            pe[1].record(stream)
+        pe[1].synchronize()
+        pms = pe[0].elapsed_time(pe[1]) / (kk * F)
+        per_frame_calls = {"ms_per_frame": pms, "value_per_gpu": MP / (pms / 1e3), "unit": "MP/s",
+                           "what": "one Pipeline.output_8bit call (one launch) per frame, device resident, this rank"}
     t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -522,7 +571,7 @@ def main():
     #  — so that one frame's D2H overlaps the next frame's H2D; whole-frame copies (band_mb 0) use the
     # PCIe link best in that regime (tools/pcie_dep_probe.py).  The latency of a single banded call is reported too.
     e2e_frames, e2e_steps = 4, max(5, K // 5)
-    frame0 = frames[0].to_numpy()
+    frame0 = frames_block.to_numpy(np.uint16)[: W * H].reshape(H, W)
     workers = []
     for t in range(E2E_THREADS):
         wctx = ctx if t == 0 else ip.Context(local_rank)
@@ -567,7 +616,7 @@ def main():
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = world * per_thread * E2E_THREADS * MP / float(te.item())
     # result check on the last e2e frame: the device-resident path produced the same bytes
-    same = all(bool(np.array_equal(w[3], outs[0].to_numpy(np.uint8, (OUT_H, OUT_W, 3)))) for w in workers)
+    same = all(bool(np.array_equal(w[3], outs_block.to_numpy(np.uint8)[:out_bytes].reshape(OUT_H, OUT_W, 3))) for w in workers)
     # the box's copy ceiling for this traffic at N GPUs: every rank moves one frame's bytes (48 MB in, 72 MB out, pinned,
     # both directions at once on the two copy streams) with nothing else, all ranks at once
     ceil_in = torch.empty(W * H * 2, dtype=torch.uint8, device="cuda")
@@ -602,17 +651,23 @@ def main():
 
     if rank == 0:
         peak, peak_kind = measured_peak()
-        kernel_ms = float(np.mean(step_ms)) / F  # one fused launch per frame, nothing else in the step
-        achieved = ALGO_BYTES_PER_PX * W * H / (kernel_ms / 1e3) / 1e9
+        # the step contains nothing but its launches: launches / K of them, each over frames_per_launch frames
+        per_step = max(1, int(launches) // K)
+        frames_per_launch = F / per_step
+        kernel_ms = float(np.mean(step_ms)) / per_step
+        achieved = ALGO_BYTES_PER_PX * W * H * frames_per_launch / (kernel_ms / 1e3) / 1e9
         line = {
             "metric": METRIC, "value": value, "unit": "MP/s", "n_gpus": world, "steps": K, "warmup": Wm,
             "ms_per_step": total_ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": workload_config(world, F),
+            "config": dict(workload_config(world, F),
+                           launches=("ipb_pipeline_output_8bit_batch over %d frames at a time" % NSETS) if batched
+                           else "one Pipeline.output_8bit call per frame"),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": measured_traffic(TRAFFIC_KEY), "kernel": KERNEL_NAME,
+                         "traffic": (measured_traffic(TRAFFIC_KEY) or 0) * frames_per_launch or None, "kernel": KERNEL_NAME,
                          "kernel_ms": kernel_ms, "peak_kind": peak_kind,
-                         "algorithmic_bytes_per_launch": ALGO_BYTES_PER_PX * W * H,
+                         "algorithmic_bytes_per_launch": ALGO_BYTES_PER_PX * W * H * frames_per_launch,
+                         "frames_per_launch": frames_per_launch, "kernel_ms_per_frame": kernel_ms / frames_per_launch,
                          "issue": measured_issue(TRAFFIC_KEY), "spec": spec_stats},
             "e2e": {"value": e2e_value, "unit": "MP/s", "h2d_bytes_per_step": e2e_frames * W * H * 2,
                     "d2h_bytes_per_step": e2e_frames * OUT_W * OUT_H * 3, "steps": e2e_steps, "frames_per_step": e2e_frames,
@@ -624,6 +679,8 @@ def main():
             "gpu_launches": int(launches),
             "clocks": clocks,
         }
+        if per_frame_calls is not None:
+            line["per_frame_calls"] = per_frame_calls
         if strong is not None:
             line["strong"] = strong
         if not args.no_cpu_baseline and world == 1:

@@ -436,20 +436,10 @@ __device__ __noinline__ void fixup_entry(const SpecParams &p, const ColorParams 
   o[2] = (uint8_t)gamma8_exact(g8_base, thr_base, v[2]);
 }
 
-// tile number t of the launch -> frame of the batch, tile row and column inside the frame
+// position of a tile: frame of the batch, tile row and column inside the frame
 struct TilePos { int f, tyi, txi; };
-__device__ __forceinline__ TilePos tile_pos(const SpecParams &p, int t) {
-  const int per_frame = p.tiles_x * p.tiles_y;
-  TilePos q;
-  q.f = t / per_frame;
-  const int r = t - q.f * per_frame;
-  q.tyi = r / p.tiles_x;
-  q.txi = r - q.tyi * p.tiles_x;
-  return q;
-}
 __device__ __forceinline__ void issue_tile(const SpecParams &p, const CUtensorMap *tmap, uint32_t raw_stage, uint32_t bar,
-                                           int t) {
-  const TilePos q = tile_pos(p, t);
+                                           const TilePos &q) {
   const int x = q.txi * kTW - 8 + p.crop_x;
   const int y = p.out_row0 + q.tyi * kTH - 1 + p.crop_y - p.src_row0 + q.f * p.frame_src_rows;
   mbar_expect_tx(bar, kTileElems * (uint32_t)sizeof(uint16_t));
@@ -532,6 +522,21 @@ k_spec8(const __grid_constant__ SpecParams p, const __grid_constant__ CfaDev cfa
   const uint32_t bar = smem_u32(&sm.mbar), bar_tab = smem_u32(&sm.mbar_tab), raw_addr = smem_u32(sm.raw);
   const uint8_t *pat = BAYER ? nullptr : sm.pat;   // the exact path's pattern kind
 
+  // this CTA's tiles are blockIdx.x, + gridDim.x, ...: their positions by stepping (no division per tile)
+  TilePos cur;
+  {
+    const int row = (int)blockIdx.x / p.tiles_x;
+    cur.txi = (int)blockIdx.x - row * p.tiles_x;
+    cur.f = row / p.tiles_y;
+    cur.tyi = row - cur.f * p.tiles_y;
+  }
+  const int step_y = (int)gridDim.x / p.tiles_x, step_x = (int)gridDim.x - step_y * p.tiles_x;
+  auto advance = [&](TilePos &q) {
+    q.txi += step_x; q.tyi += step_y;
+    if (q.txi >= p.tiles_x) { q.txi -= p.tiles_x; q.tyi++; }
+    while (q.tyi >= p.tiles_y) { q.tyi -= p.tiles_y; q.f++; }
+  };
+
   if (tid == 0) {
     sm.conv_ctr[0] = 0;
     sm.conv_ctr[1] = 0;
@@ -541,7 +546,7 @@ k_spec8(const __grid_constant__ SpecParams p, const __grid_constant__ CfaDev cfa
     mbar_init(bar_tab, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    issue_tile(p, &tmap, raw_addr, bar, (int)blockIdx.x);
+    issue_tile(p, &tmap, raw_addr, bar, cur);
     constexpr uint32_t kG8Bytes = kSpecG8Entries * 4u, kSTabBytes = kSpecSTabEntries * 8u;
     mbar_expect_tx(bar_tab, kG8Bytes + kSTabBytes);
     bulk_load(smem_u32(sm.g8a), p.g8a, kG8Bytes, bar_tab);
@@ -631,7 +636,11 @@ k_spec8(const __grid_constant__ SpecParams p, const __grid_constant__ CfaDev cfa
   mbar_wait(bar, 0);
   convert_tile(0, 0);
   __syncthreads();
-  if (tid == 0 && (int)(blockIdx.x + gridDim.x) < ntiles) issue_tile(p, &tmap, raw_addr, bar, (int)(blockIdx.x + gridDim.x));
+  if (tid == 0 && (int)(blockIdx.x + gridDim.x) < ntiles) {
+    TilePos nx = cur;
+    advance(nx);
+    issue_tile(p, &tmap, raw_addr, bar, nx);
+  }
   mbar_wait(bar_tab, 0);
 
   // queue the uncertified pixels of a task (entry = row * kTW + column of its first pixel, inside the tile); the queue
@@ -651,7 +660,8 @@ k_spec8(const __grid_constant__ SpecParams p, const __grid_constant__ CfaDev cfa
   int fix_warps = 0;                 // warps that recomputed pixels of the previous tile at the top of this iteration
   unsigned long long nfix = 0;       // thread 0: pixels recomputed by this CTA
   for (int t = blockIdx.x; t < ntiles; t += gridDim.x, it++) {
-    const TilePos tp = tile_pos(p, t);
+    const TilePos tp = cur;
+    advance(cur);
     const int ty0 = p.out_row0 + tp.tyi * kTH, tx0 = tp.txi * kTW;
     uint8_t *const out_f = p.out + (size_t)tp.f * (size_t)p.frame_out_bytes;   // this tile's frame of the batch
     const uint32_t tile_base = smem_u32(&sm.plane[it & 1][0][0][0]);
@@ -748,7 +758,11 @@ k_spec8(const __grid_constant__ SpecParams p, const __grid_constant__ CfaDev cfa
       sm.qn[(it + 1) & 1] = 0;   // the next tile's queue length; its last readers passed the second barrier of the previous iteration
     }
     __syncthreads();
-    if (tid == 0 && t + 2 * (int)gridDim.x < ntiles) issue_tile(p, &tmap, raw_addr, bar, t + 2 * (int)gridDim.x);
+    if (tid == 0 && t + 2 * (int)gridDim.x < ntiles) {
+      TilePos nx = cur;   // already the next tile: one more step
+      advance(nx);
+      issue_tile(p, &tmap, raw_addr, bar, nx);
+    }
     // Uncertified pixels of this tile are recomputed exactly from the tile's planes, densely: entry i goes to thread i, so
     // the first ceil(n / 32) warps do the work with all lanes busy while the others start the next tile.  The barrier
     // above ordered every push before these reads; the one below frees the queue for the next tile's pushes.

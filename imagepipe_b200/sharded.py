@@ -211,3 +211,15 @@ def run_stripe_8bit(pipeline, rows, layout, dst):
     src = ImageSource(_capi.SRC_RAW_U16, img.width, layout.src_row1 - layout.src_row0, 1, data)
     pipeline.set_stripe_source(src, layout.src_row0, layout.out_row0, layout.out_row1)
     return pipeline.output_8bit_stripe(dst=dst, rows=layout.out_row1 - layout.out_row0, width=layout.out_width)
+
+
+def run_stripes_8bit_batch(pipeline, rows_ptr, nframes, layout, dst):
+    """The stripes `layout` of nframes frames, stacked in one device buffer (frame k's source rows [layout.src_row0,
+    layout.src_row1) start k * (src_row1 - src_row0) rows after device address rows_ptr), in one call of
+    ipb_pipeline_output_8bit_batch; the results follow each other in dst (DevicePtr / DeviceArray)."""
+    from .pipeline import ImageSource
+    img = pipeline.globals.image
+    rows = layout.src_row1 - layout.src_row0
+    src = ImageSource(_capi.SRC_RAW_U16, img.width, rows, 1, int(rows_ptr))
+    pipeline.set_stripe_source(src, layout.src_row0, layout.out_row0, layout.out_row1)
+    return pipeline.output_8bit_batch(nframes, rows, dst, (layout.out_row1 - layout.out_row0) * layout.out_width * 3)
