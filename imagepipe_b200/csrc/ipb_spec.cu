@@ -441,7 +441,7 @@ struct TilePos { int f, tyi, txi; };
 __device__ __forceinline__ void issue_tile(const SpecParams &p, const CUtensorMap *tmap, uint32_t raw_stage, uint32_t bar,
                                            const TilePos &q) {
   const int x = q.txi * kTW - 8 + p.crop_x;
-  const int y = p.out_row0 + q.tyi * kTH - 1 + p.crop_y - p.src_row0 + q.f * p.frame_src_rows;
+  const int y = p.out_row0 + q.tyi * kTH - 1 + p.crop_y - p.src_row0 + q.f * p.frame_src_rows;   // q.f == 0 without a batch
   mbar_expect_tx(bar, kTileElems * (uint32_t)sizeof(uint16_t));
   tma_load_2d(raw_stage, tmap, x, y, bar);
 }
@@ -510,7 +510,9 @@ __device__ __forceinline__ int atoms_add(uint32_t addr, int v) {  // plain share
 // MODE 0..3: RGB Bayer, bit 1 = GF0 (even rows of the cropped frame start with green), bit 0 = AR0 (their other colour
 // is red); odd rows are the opposite on both counts (green sits on one diagonal, red and blue on the other).
 // MODE 4: any other three-colour pattern up to 12 x 12 (X-Trans): row-major tile, per-position tap masks.
-template <int NT, int MODE>
+// BATCH: the launch covers several frames (ipb_pipeline_output_8bit_batch); a single frame keeps the frame index and the
+// per-frame output pointer out of its registers.
+template <int NT, int MODE, bool BATCH>
 __global__ void __launch_bounds__(NT, NT == 512 ? 2 : 1)
 k_spec8(const __grid_constant__ SpecParams p, const __grid_constant__ CfaDev cfa, const __grid_constant__ ColorParams P,
         const __grid_constant__ CUtensorMap tmap) {
@@ -527,14 +529,15 @@ k_spec8(const __grid_constant__ SpecParams p, const __grid_constant__ CfaDev cfa
   {
     const int row = (int)blockIdx.x / p.tiles_x;
     cur.txi = (int)blockIdx.x - row * p.tiles_x;
-    cur.f = row / p.tiles_y;
+    cur.f = BATCH ? row / p.tiles_y : 0;
     cur.tyi = row - cur.f * p.tiles_y;
   }
   const int step_y = (int)gridDim.x / p.tiles_x, step_x = (int)gridDim.x - step_y * p.tiles_x;
   auto advance = [&](TilePos &q) {
     q.txi += step_x; q.tyi += step_y;
     if (q.txi >= p.tiles_x) { q.txi -= p.tiles_x; q.tyi++; }
-    while (q.tyi >= p.tiles_y) { q.tyi -= p.tiles_y; q.f++; }
+    if (BATCH)
+      while (q.tyi >= p.tiles_y) { q.tyi -= p.tiles_y; q.f++; }
   };
 
   if (tid == 0) {
@@ -663,7 +666,7 @@ k_spec8(const __grid_constant__ SpecParams p, const __grid_constant__ CfaDev cfa
     const TilePos tp = cur;
     advance(cur);
     const int ty0 = p.out_row0 + tp.tyi * kTH, tx0 = tp.txi * kTW;
-    uint8_t *const out_f = p.out + (size_t)tp.f * (size_t)p.frame_out_bytes;   // this tile's frame of the batch
+    uint8_t *const out_f = BATCH ? p.out + (size_t)tp.f * (size_t)p.frame_out_bytes : p.out;   // this tile's frame of the batch
     const uint32_t tile_base = smem_u32(&sm.plane[it & 1][0][0][0]);
     const uint32_t qaddr = smem_u32(&sm.qn[it & 1]);
     // a tile is "inner" when all its pixels exist, are wanted, and have their nine taps inside the frame
@@ -1030,16 +1033,24 @@ bool make_raw_tmap(CUtensorMap *map, const uint16_t *raw, size_t pitch_elems, si
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-template <int NT, int MODE>
-cudaError_t launch_variant(cudaStream_t s, const SpecParams &p, const CfaDev &cfa, const ColorParams &P,
-                           const CUtensorMap &tmap, int ntiles, int sm_count) {
+template <int NT, int MODE, bool BATCH>
+cudaError_t launch_variant_b(cudaStream_t s, const SpecParams &p, const CfaDev &cfa, const ColorParams &P,
+                             const CUtensorMap &tmap, int ntiles, int sm_count) {
   const size_t smem = sizeof(SmemSpec);
   const int ctas = sm_count * (NT == 512 ? 2 : 1);
   const int grid = ntiles < ctas ? ntiles : ctas;
-  cudaError_t e = cudaFuncSetAttribute(k_spec8<NT, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = cudaFuncSetAttribute(k_spec8<NT, MODE, BATCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  k_spec8<NT, MODE><<<grid, NT, smem, s>>>(p, cfa, P, tmap);
+  k_spec8<NT, MODE, BATCH><<<grid, NT, smem, s>>>(p, cfa, P, tmap);
   return cudaGetLastError();
+}
+template <int NT, int MODE>
+cudaError_t launch_variant(cudaStream_t s, const SpecParams &p, const CfaDev &cfa, const ColorParams &P,
+                           const CUtensorMap &tmap, int ntiles, int sm_count) {
+  // batches only at the default CTA size (the 1024-thread variant is a measurement aid)
+  if (p.nframes > 1 && NT == 512) return launch_variant_b<512, MODE, true>(s, p, cfa, P, tmap, ntiles, sm_count);
+  if (p.nframes > 1) return cudaErrorInvalidValue;
+  return launch_variant_b<NT, MODE, false>(s, p, cfa, P, tmap, ntiles, sm_count);
 }
 
 // RGB Bayer: 2 x 2, green on one diagonal, red and blue on the other
@@ -1119,6 +1130,7 @@ cudaError_t launch_fused_spec8(cudaStream_t s, const FusedArgs &a, const CfaDev 
   p.pw = cfa.width; p.ph = cfa.height;
   p.rcp_pw = (uint32_t)(0x100000000ull / (unsigned long long)cfa.width) + 1u;
   p.rcp_ph = (uint32_t)(0x100000000ull / (unsigned long long)cfa.height) + 1u;
+  if (p.nframes > 1) threads = 512;
   if (!is_rgb_bayer(cfa)) {
     if (threads == 1024) return launch_variant<1024, 4>(s, p, cfa, P, tmap, ntiles, sm_count);
     return launch_variant<512, 4>(s, p, cfa, P, tmap, ntiles, sm_count);
