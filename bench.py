@@ -270,9 +270,9 @@ def strong_leg(args, ip, common, torch, dist, ctx, stream, barrier, rank, world,
             own = bufs[i][me.own_row0 - me.src_row0: me.own_row1 - me.src_row0]
             ip.lib().ipb_synth_cfa_u16(ctx.handle, common.SEED + i, W5, me.own_row0, me.own_row1 - me.own_row0, own.data_ptr())
     ptrs = [b.data_ptr() for b in bufs]
-    # measured (profiles/r02e_batch.txt): behind the grouped exchange, inside a CUDA graph, one launch per stripe is as fast
-    # (2 GPUs) or faster (8 GPUs: 80 against 85 us per stripe) than one batched launch per step, so that is the default here
-    batched = args.strong_batch
+    # the stripes of a step's frames in one batched launch (profiles/r02e_batch.txt: 72.3 against 76.9 us per stripe at
+    # 8 GPUs, no difference at 2); --no-batch: one launch per stripe
+    batched = not args.no_batch
     hp = halo_plan(lays, rank, W5 * 2)
     halo_bytes = hp.send_up_bytes + hp.send_down_bytes + hp.recv_up_bytes + hp.recv_down_bytes
 
@@ -436,8 +436,6 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--frames-per-step", type=int, default=None)
     ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling (C5 stripes) leg of the default line")
-    ap.add_argument("--strong-batch", action="store_true",
-                    help="strong-scaling leg: the stripes of a step's frames in one batched launch instead of one launch each")
     ap.add_argument("--no-batch", action="store_true",
                     help="one output_8bit call (one launch) per frame instead of ipb_pipeline_output_8bit_batch over the buffer sets")
     ap.add_argument("--no-graph", action="store_true", help="c5: launch every frame from Python instead of replaying a CUDA graph")
