@@ -273,8 +273,23 @@ __device__ __forceinline__ float lab_f_exact(const float2 *__restrict__ lut, con
 __device__ __forceinline__ void exact_rgb_bayer(const SpecParams &p, uint32_t phase, int x, int y, const float t[9], float &r,
                                                 float &g, float &b) {
   const bool hn = y > 0, hs = y < p.height - 1, hw = x > 0, he = x < p.width - 1;
-  auto mean = [](float s, int n) { return n == 4 ? s * 0.25f : n == 2 ? s * 0.5f : n ? __fdiv_rn(s, (float)n) : 0.0f; };
   const float v = t[4];
+  const int c = (phase >> (2 * (2 * (y & 1) + (x & 1)))) & 3;            // this site's colour
+  const int ch = (phase >> (2 * (2 * (y & 1) + ((x & 1) ^ 1)))) & 3;     // the colour of its left / right neighbours
+  const bool gsite = c == 1;
+  const int first = gsite ? ch : c;  // colour (0 or 2) that receives `a0`
+  if (hn && hs && hw && he) {
+    // all nine taps exist (nearly every recomputed pixel): the same sums in the same order, divisions by 4 and 2 as
+    // exact scalings
+    const float mg = ((((0.0f + t[1]) + t[3]) + t[5]) + t[7]) * 0.25f, md = ((((0.0f + t[0]) + t[2]) + t[6]) + t[8]) * 0.25f;
+    const float mh = ((0.0f + t[3]) + t[5]) * 0.5f, mv = ((0.0f + t[1]) + t[7]) * 0.5f;
+    const float a0 = gsite ? mh : v, a1 = gsite ? mv : md;
+    r = first == 0 ? a0 : a1;
+    g = gsite ? v : mg;
+    b = first == 0 ? a1 : a0;
+    return;
+  }
+  auto mean = [](float s, int n) { return n == 4 ? s * 0.25f : n == 2 ? s * 0.5f : n ? __fdiv_rn(s, (float)n) : 0.0f; };
   // sums start at +0.0 and skip missing taps (x + 0.0 == x for these sums, which are never -0.0)
   float sg = 0.0f, sd = 0.0f, sh = 0.0f, sv = 0.0f;
   if (hn && hw) sd = sd + t[0];
@@ -287,12 +302,8 @@ __device__ __forceinline__ void exact_rgb_bayer(const SpecParams &p, uint32_t ph
   if (hs && he) sd = sd + t[8];
   const int nv = (int)hn + (int)hs, nh = (int)hw + (int)he;
   const float mg = mean(sg, nv + nh), md = mean(sd, nv * nh), mh = mean(sh, nh), mv = mean(sv, nv);
-  const int c = (phase >> (2 * (2 * (y & 1) + (x & 1)))) & 3;            // this site's colour
-  const int ch = (phase >> (2 * (2 * (y & 1) + ((x & 1) ^ 1)))) & 3;     // the colour of its left / right neighbours
   // green site: own sample, left/right mean for colour ch, up/down mean for the third; red / blue site: own sample,
   // edge mean for green, corner mean for the third
-  const bool gsite = c == 1;
-  const int first = gsite ? ch : c;  // colour (0 or 2) that receives `a0`
   const float a0 = gsite ? mh : v, a1 = gsite ? mv : md;
   r = first == 0 ? a0 : a1;
   g = gsite ? v : mg;
