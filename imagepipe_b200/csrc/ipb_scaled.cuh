@@ -205,6 +205,59 @@ __device__ __forceinline__ void scaled_pixel_bayer(const ScaledParams &p, const 
   for (int k = 0; k < 3; k++) px[k] = acc[k].y > 0.0f ? __fdiv_rn(acc[k].x, acc[k].y) : 0.0f;
 }
 
+// Two output pixels of one column in consecutive rows (row, row + 1): their windows share the column geometry — from_x,
+// to_x, center_x and with them 1 - delta_x^2 of every window column do not depend on the row (scaling.rs:77-98 with
+// skip_x_y == 0) — so that part is computed once.  `two` false: only (row, col) exists; pb is a copy of pa.
+template <int NX, bool UNIFORM, bool SRC>
+__device__ __forceinline__ void pair_taps_bayer(const ScaledParams &p, const CfaDev &cfa, const ScaledWindow &wa, const ScaledWindow &wb,
+                                                int nx, bool two, F2 acc_a[3], F2 acc_b[3]) {
+  float ax[NX];
+#pragma unroll
+  for (int k = 0; k < NX; k++) {
+    const float delta_x = div_skip<SRC>((float)(wa.from_x + k) - wa.center_x, p.skip_x, p.skip_x_rc);
+    ax[k] = 1.0f - (delta_x * delta_x);
+  }
+  const int pxb = wa.from_x & 1;
+  auto one = [&](const ScaledWindow &w, F2 acc[3]) {
+    const int py = w.from_y & 1;
+    const bool g00 = cfa.pat[py * 48 + pxb] == 1;
+    F2 g{0.f, 0.f}, x0{0.f, 0.f}, x1{0.f, 0.f};
+    window_rows_bayer<NX, UNIFORM, SRC>(p, ax, w.from_x, nx, w.from_y, w.to_y, w.center_y, g00, g, x0, x1);
+    const int c0 = g00 ? cfa.pat[py * 48 + (pxb ^ 1)] : cfa.pat[py * 48 + pxb];
+    acc[1] = g;
+    acc[0] = c0 == 0 ? x0 : x1;
+    acc[2] = c0 == 0 ? x1 : x0;
+  };
+  one(wa, acc_a);
+  if (two) one(wb, acc_b);
+  else { acc_b[0] = acc_a[0]; acc_b[1] = acc_a[1]; acc_b[2] = acc_a[2]; }
+}
+__device__ __forceinline__ void scaled_pair_bayer(const ScaledParams &p, const CfaDev &cfa, int row, int col, bool two, float pa[3],
+                                                  float pb[3]) {
+  const ScaledWindow wa = scaled_window(p, row, col);
+  ScaledWindow wb = wa;
+  if (two) {   // the row part of the window of (row + 1, col); the column part is wa's
+    const ScaledWindow t = scaled_window(p, row + 1, col);
+    wb.from_y = t.from_y; wb.to_y = t.to_y; wb.center_y = t.center_y;
+  }
+  const int nx = wa.to_x - wa.from_x + 1;
+  F2 acc_a[3], acc_b[3];
+  const int nx_max = __reduce_max_sync(0xffffffffu, nx), nx_min = __reduce_min_sync(0xffffffffu, nx);
+  if (nx_max == 5 && nx_min == 5) {
+    if (p.skip_rc_exact) pair_taps_bayer<5, true, true>(p, cfa, wa, wb, nx, two, acc_a, acc_b);
+    else pair_taps_bayer<5, true, false>(p, cfa, wa, wb, nx, two, acc_a, acc_b);
+  } else if (nx_max <= 6) {
+    pair_taps_bayer<6, false, false>(p, cfa, wa, wb, nx, two, acc_a, acc_b);
+  } else {
+    pair_taps_bayer<kMaxCols, false, false>(p, cfa, wa, wb, nx, two, acc_a, acc_b);
+  }
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    pa[k] = acc_a[k].y > 0.0f ? __fdiv_rn(acc_a[k].x, acc_a[k].y) : 0.0f;
+    pb[k] = acc_b[k].y > 0.0f ? __fdiv_rn(acc_b[k].x, acc_b[k].y) : 0.0f;
+  }
+}
+
 // host (ipb_fused.cu): the geometry / level-mapping part of ScaledParams from the launch arguments, including the
 // exhaustive check behind skip_rc_exact
 void fill_scaled_params(const FusedArgs &a, const CfaDev &cfa, ScaledParams *p);

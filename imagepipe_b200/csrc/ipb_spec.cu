@@ -866,17 +866,19 @@ k_spec8_scaled(const __grid_constant__ SpecParams p, const __grid_constant__ Sca
   unsigned long long nfix = 0;
   bool tables_in = false;
   const bool recompute = !(p.dbg & 1);
+  // a thread takes the two pixels of one column in rows 2k, 2k + 1 of the launch: consecutive lanes on consecutive
+  // columns (their window loads touch the fewest cache lines), and the column part of the window computed once
   const long long npix = (long long)(g.out_row1 - g.out_row0) * g.nwidth;
-  const long long npairs = (npix + 1) / 2, npairs_pad = (npairs + 31) / 32 * 32;  // whole warps stay in the loop
-  const bool out_even = (reinterpret_cast<uintptr_t>(p.out) & 1) == 0;
+  const int nrows = g.out_row1 - g.out_row0;
+  const long long npairs = (long long)((nrows + 1) / 2) * g.nwidth, npairs_pad = (npairs + 31) / 32 * 32;  // whole warps stay in the loop
   for (long long pi = (long long)blockIdx.x * kScNT + tid; pi < npairs_pad; pi += (long long)gridDim.x * kScNT) {
     const bool live = pi < npairs;
-    const long long id0 = 2 * (live ? pi : npairs - 1);
-    const bool have1 = live && id0 + 1 < npix;
-    const long long id1 = id0 + 1 < npix ? id0 + 1 : id0;
+    const long long pj = live ? pi : npairs - 1;
+    const int rp = (int)(pj / g.nwidth), col = (int)(pj - (long long)rp * g.nwidth);
+    const bool have1 = live && 2 * rp + 1 < nrows;
+    const long long id0 = (long long)(2 * rp) * g.nwidth + col, id1 = have1 ? id0 + g.nwidth : id0;
     float pa[3], pb[3];
-    scaled_pixel_bayer(g, cfa, g.out_row0 + (int)(id0 / g.nwidth), (int)(id0 % g.nwidth), pa);
-    scaled_pixel_bayer(g, cfa, g.out_row0 + (int)(id1 / g.nwidth), (int)(id1 % g.nwidth), pb);
+    scaled_pair_bayer(g, cfa, g.out_row0 + 2 * rp, col, 2 * rp + 1 < nrows, pa, pb);
     if (!tables_in) {
       mbar_wait(bar_tab, 0);
       tables_in = true;
@@ -892,14 +894,10 @@ k_spec8_scaled(const __grid_constant__ SpecParams p, const __grid_constant__ Sca
     const bool f0 = live && (d0 <= T || dark) && !(p.dbg & 2), f1 = have1 && (d1 <= T || dark) && !(p.dbg & 2);
     if (live) {
       uint8_t *o = p.out + (size_t)id0 * 3;
-      const uint32_t w01 = __byte_perm(s[0], s[2], 0x0073), w2 = s[4] >> 24;          // pixel 0: r, g | b
-      const uint32_t w34 = __byte_perm(s[3], s[5], 0x0073), w3 = s[1] >> 24;          // pixel 1: r | g, b
-      if (have1 && out_even) {
-        uint16_t *o2 = reinterpret_cast<uint16_t *>(o);
-        o2[0] = (uint16_t)w01; o2[1] = (uint16_t)(w2 | (w3 << 8)); o2[2] = (uint16_t)w34;
-      } else {
-        o[0] = (uint8_t)w01; o[1] = (uint8_t)(w01 >> 8); o[2] = (uint8_t)w2;
-        if (have1) { o[3] = (uint8_t)w3; o[4] = (uint8_t)w34; o[5] = (uint8_t)(w34 >> 8); }
+      o[0] = (uint8_t)(s[0] >> 24); o[1] = (uint8_t)(s[2] >> 24); o[2] = (uint8_t)(s[4] >> 24);
+      if (have1) {
+        uint8_t *o1 = p.out + (size_t)id1 * 3;
+        o1[0] = (uint8_t)(s[1] >> 24); o1[1] = (uint8_t)(s[3] >> 24); o1[2] = (uint8_t)(s[5] >> 24);
       }
     }
     // queue the uncertified pixels with their demosaiced values (ballot compaction: qn stays warp-uniform)
@@ -1187,7 +1185,7 @@ cudaError_t launch_scaled_spec8(cudaStream_t s, const FusedArgs &a, const CfaDev
   p.g8a = T.g8a; p.stab = T.stab; p.thr8 = T.thr8; p.stats = T.stats;
   ScaledParams g;
   fill_scaled_params(a, cfa, &g);
-  const long long npairs = ((long long)(g.out_row1 - g.out_row0) * g.nwidth + 1) / 2;
+  const long long npairs = (long long)((g.out_row1 - g.out_row0 + 1) / 2) * g.nwidth;
   const long long blocks = (npairs + kScNT - 1) / kScNT;
   const int grid = (int)(blocks < 2ll * sm_count ? blocks : 2ll * sm_count);
   const size_t smem = sizeof(SmemScaledSpec);
