@@ -508,3 +508,128 @@ impl<'c> Drop for GpuPipeline<'c> {
 pub fn run_on_gpu(ctx: &GpuContext, p: &mut Pipeline, cache: Option<&GpuCache>) -> Arc<OpBuffer> {
     GpuPipeline::from_pipeline(ctx, p).run(p, cache)
 }
+
+// ------------------------------------------------------------------------------------------------ several GPUs
+//
+// One frame too large for one GPU (BASELINE config 5) is cut into row stripes, one process per GPU.  The reference has no
+// counterpart; a host built on it would add this next to `Pipeline`.  Rank r owns the sensor rows of its stripe on its
+// device; the rows its 3x3 stencil (or the resampler's windows) needs from the neighbours travel through
+// `ipb_halo_exchange`, which resolves NCCL itself: the host only carries the 128-byte id from rank 0 to the others.
+
+/// One rank's share of a frame: which output rows it produces and which source rows it holds (halo included).
+#[derive(Clone, Copy, Debug)]
+pub struct StripeLayout {
+    pub out_row0: usize, pub out_row1: usize,   // output rows [out_row0, out_row1)
+    pub src_row0: usize, pub src_row1: usize,   // source rows needed, halo included (ipb_stripe_plan)
+    pub own_row0: usize, pub own_row1: usize,   // source rows this rank owns (the others arrive by exchange)
+    pub out_width: usize, pub out_height: usize,
+}
+
+/// Even split of the output rows over `world` ranks; every rank computes the same table (host only, no device call).
+pub fn plan_stripes(p: &Pipeline, width: usize, height: usize, world: usize) -> Vec<StripeLayout> {
+    let (ops, settings) = (pod_ops(&p.ops), pod_settings(&p.globals.settings));
+    let (mut s0, mut s1, mut ow, mut oh) = (0usize, 0usize, 0usize, 0usize);
+    // the size of the result first (rows 0..0: no stripe, only the frame's output size)
+    let rc = unsafe { ipb_stripe_plan(&ops, &settings, width, height, 0, 0, &mut s0, &mut s1, &mut ow, &mut oh) };
+    assert_eq!(rc, IPB_OK, "only the fused raw CFA path with Normal orientation is cut into stripes");
+    // balanced, interior boundaries on even rows (the Bayer period; any boundary is correct: kernels work in full-frame
+    // coordinates)
+    let bounds: Vec<usize> = (0..=world).map(|r| if r == world { oh } else { (oh * r / world + 1) / 2 * 2 }).collect();
+    let mut lays: Vec<StripeLayout> = (0..world).map(|r| {
+        let rc = unsafe { ipb_stripe_plan(&ops, &settings, width, height, bounds[r], bounds[r + 1], &mut s0, &mut s1, &mut ow, &mut oh) };
+        assert_eq!(rc, IPB_OK);
+        StripeLayout { out_row0: bounds[r], out_row1: bounds[r + 1], src_row0: s0, src_row1: s1, own_row0: s0, own_row1: s1,
+                       out_width: ow, out_height: oh }
+    }).collect();
+    // ownership: the needed ranges overlap by the halo; the midpoint of each overlap separates the owners
+    for r in 0..world.saturating_sub(1) {
+        let cut = (lays[r].src_row1 + lays[r + 1].src_row0) / 2;
+        lays[r].own_row1 = cut;
+        lays[r + 1].own_row0 = cut;
+    }
+    if world > 0 { lays[0].own_row0 = 0; lays[world - 1].own_row1 = height; }
+    lays
+}
+
+/// The byte ranges of a rank's stripe buffer that leave for / arrive from its neighbours (row_bytes = sensor width * 2).
+pub fn halo_plan(lays: &[StripeLayout], rank: usize, row_bytes: usize) -> ipb_halo {
+    let me = &lays[rank];
+    let off = |row: usize| (row - me.src_row0) * row_bytes;
+    let mut h = ipb_halo { send_up_off: 0, send_up_bytes: 0, recv_up_off: 0, recv_up_bytes: 0,
+                           send_down_off: 0, send_down_bytes: 0, recv_down_off: 0, recv_down_bytes: 0 };
+    if rank > 0 {
+        let up = &lays[rank - 1];
+        // what the upper neighbour needs of my rows, what I need of its rows
+        h.send_up_off = off(me.own_row0); h.send_up_bytes = (up.src_row1 - me.own_row0) * row_bytes;
+        h.recv_up_off = off(me.src_row0); h.recv_up_bytes = (me.own_row0 - me.src_row0) * row_bytes;
+    }
+    if rank + 1 < lays.len() {
+        let down = &lays[rank + 1];
+        h.send_down_off = off(down.src_row0); h.send_down_bytes = (me.own_row1 - down.src_row0) * row_bytes;
+        h.recv_down_off = off(me.own_row1); h.recv_down_bytes = (me.src_row1 - me.own_row1) * row_bytes;
+    }
+    h
+}
+
+/// The communicator of the stripe neighbours (one per process).  `id`: 128 bytes drawn by rank 0 with
+/// `StripeComm::unique_id()` and handed to every rank by the host program (MPI, a file, a socket).
+pub struct StripeComm { raw: *mut ipb_comm }
+impl StripeComm {
+    pub fn unique_id() -> Result<[u8; 128], String> {
+        let mut id = [0u8; 128];
+        if unsafe { ipb_comm_unique_id(id.as_mut_ptr()) } != IPB_OK { return Err(comm_error(ptr::null())); }
+        Ok(id)
+    }
+    pub fn new(device: i32, stream: *mut std::os::raw::c_void, id: &[u8; 128], rank: usize, world: usize) -> Result<Self, String> {
+        let mut raw = ptr::null_mut();
+        if unsafe { ipb_comm_create(device, stream, id.as_ptr(), rank as c_int, world as c_int, &mut raw) } != IPB_OK {
+            return Err(comm_error(ptr::null()));
+        }
+        Ok(Self { raw })
+    }
+    /// Halo rows of every buffer in `bufs` (the frames in flight; device addresses of the stripes' first source row):
+    /// one packed message per neighbour and direction, enqueued on the communicator's stream.
+    pub fn exchange(&self, bufs: &[*const std::os::raw::c_void], halo: &ipb_halo) -> Result<(), String> {
+        if unsafe { ipb_halo_exchange(self.raw, bufs.as_ptr(), bufs.len(), halo) } != IPB_OK { return Err(comm_error(self.raw)); }
+        Ok(())
+    }
+}
+impl Drop for StripeComm {
+    fn drop(&mut self) { unsafe { ipb_comm_destroy(self.raw) } }
+}
+fn comm_error(c: *const ipb_comm) -> String {
+    unsafe { std::ffi::CStr::from_ptr(ipb_comm_last_error(c)) }.to_string_lossy().into_owned()
+}
+
+impl<'c> GpuPipeline<'c> {
+    /// This rank's stripes of `nframes` frames in flight: `rows` is the device address of the first stripe's first source
+    /// row (`lay.src_row0`), the stripes follow each other (`lay.src_row1 - lay.src_row0` rows apart), their halo rows
+    /// already exchanged; `dst` (device) receives the `nframes` results one after the other.  One launch for all of them
+    /// where the speculative kernel applies (ipb_pipeline_output_8bit_batch on the stripe source).
+    pub fn output_8bit_stripes(&self, rows: *const std::os::raw::c_void, sensor_width: usize, full_height: usize, lay: &StripeLayout,
+                               nframes: usize, dst: *mut u8, dst_capacity: usize) -> Result<(usize, usize), String> {
+        let nrows = lay.src_row1 - lay.src_row0;
+        let src = ipb_source { kind: IPB_SRC_RAW_U16, width: sensor_width, height: nrows, cpp: 1, data: rows, on_device: 1 };
+        let st = ipb_stripe { full_height, src_row0: lay.src_row0, out_row0: lay.out_row0, out_row1: lay.out_row1 };
+        if unsafe { ipb_pipeline_set_stripe_source(self.raw, &src, &st) } != IPB_OK { return Err(last_error(self.ctx.raw)); }
+        let (mut w, mut h) = (0usize, 0usize);
+        let stride = (lay.out_row1 - lay.out_row0) * lay.out_width * 3;
+        let rc = unsafe { ipb_pipeline_output_8bit_batch(self.raw, nframes, nrows, dst, stride, dst_capacity, &mut w, &mut h) };
+        if rc != IPB_OK { return Err(last_error(self.ctx.raw)); }
+        Ok((w, h))
+    }
+}
+
+/// A step of the sharded pipeline on one rank, in the order the calls have to be made:
+///
+/// ```ignore
+/// let lays = plan_stripes(&pipeline, width, height, world);          // every rank, host only
+/// let me = lays[rank];
+/// let halo = halo_plan(&lays, rank, width * 2);
+/// let comm = StripeComm::new(device, stream, &id, rank, world)?;      // id: from rank 0, over the host's own channel
+/// // ... the rank's own rows of each frame in flight are on the device (bufs[k] + byte offset of me.own_row0) ...
+/// comm.exchange(&bufs, &halo)?;                                       // neighbours' rows arrive in place
+/// gpu_pipeline.output_8bit_stripes(bufs[0], width, height, &me, bufs.len(), dst, cap)?;   // stripes -> sRGB bytes
+/// ctx.synchronize();
+/// ```
+pub const SHARDED_STEP: () = ();
