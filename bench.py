@@ -658,9 +658,9 @@ def main():
             "metric": METRIC, "value": value, "unit": "MP/s", "n_gpus": world, "steps": K, "warmup": Wm,
             "ms_per_step": total_ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": dict(workload_config(world, F),
-                           launches=("ipb_pipeline_output_8bit_batch over %d frames at a time" % NSETS) if batched
-                           else "one Pipeline.output_8bit call per frame"),
+            "config": workload_config(world, F),   # the same dict on the reference arm
+            "launches": ("ipb_pipeline_output_8bit_batch over %d frames at a time" % NSETS) if batched
+            else "one Pipeline.output_8bit call per frame",
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": (measured_traffic(TRAFFIC_KEY) or 0) * frames_per_launch or None, "kernel": KERNEL_NAME,
                          "kernel_ms": kernel_ms, "peak_kind": peak_kind,
