@@ -1039,6 +1039,13 @@ static bool scaled_skip_rc_exact(int width, int height, int nwidth, int nheight,
   return true;
 }
 
+bool scaled_skip_division_exact(size_t width, size_t height, size_t nwidth, size_t nheight) {
+  if (nwidth < 2 || nheight < 2 || width < 2 || height < 2 || width >= (1u << 30) || height >= (1u << 30)) return false;
+  const float skip_x = ((float)((long)width - 1) - 0.0f) / (float)(nwidth - 1);
+  const float skip_y = ((float)((long)height - 1) - 0.0f) / (float)(nheight - 1);
+  return scaled_skip_rc_exact((int)width, (int)height, (int)nwidth, (int)nheight, skip_x, skip_y);
+}
+
 void fill_scaled_params(const FusedArgs &a, const CfaDev &cfa, ScaledParams *out) {
   ScaledParams p;
   p.raw = a.raw; p.raw_pitch = (long long)a.raw_pitch;

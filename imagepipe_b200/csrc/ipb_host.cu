@@ -20,6 +20,7 @@
 #include <vector>
 
 #include "ipb_internal.h"
+#include "ipb_scaled.cuh"
 #include "ipb_spec.h"
 
 using namespace ipb;
@@ -2380,6 +2381,10 @@ int ipb_ctx_spec_stats(ipb_ctx *ctx, unsigned long long out[4], int reset) {
   memcpy(&mb, &ctx->mufu_cbrt_err, 4);
   out[0] = h[0]; out[1] = h[4]; out[2] = db; out[3] = mb;
   return IPB_OK;
+}
+
+int ipb_scaled_division_check(size_t width, size_t height, size_t nwidth, size_t nheight) {
+  return scaled_skip_division_exact(width, height, nwidth, nheight) ? 1 : 0;
 }
 
 int ipb_spec_bound(const ipb_ops *ops, float mufu_rel_err, float *delta) {

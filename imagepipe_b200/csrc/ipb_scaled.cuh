@@ -261,5 +261,7 @@ __device__ __forceinline__ void scaled_pair_bayer(const ScaledParams &p, const C
 // host (ipb_fused.cu): the geometry / level-mapping part of ScaledParams from the launch arguments, including the
 // exhaustive check behind skip_rc_exact
 void fill_scaled_params(const FusedArgs &a, const CfaDev &cfa, ScaledParams *p);
+// host: the check behind ScaledParams::skip_rc_exact for a frame geometry (cropped frame -> output size)
+bool scaled_skip_division_exact(size_t width, size_t height, size_t nwidth, size_t nheight);
 
 }  // namespace ipb

@@ -275,6 +275,10 @@ int ipb_pipeline_spec_probe(ipb_pipeline *p, float *max_dev, double *mean_dev, f
  * parameters of `ops`, given the relative error of the XU-pipe cube root (ipb_ctx_spec_stats out[3] on a GPU box; the
  * hardware documentation's 2^-22 otherwise).  IPB_ERR_UNSUPPORTED when these parameters would run on the exact kernel. */
 int ipb_spec_bound(const ipb_ops *ops, float mufu_rel_err, float delta[4]);
+/* Diagnostic, host only: 1 when the scaled kernels may divide window coordinates by the skip (scaling.rs:94-98) in the
+ * three-instruction reciprocal form for this geometry (cropped frame width x height -> nwidth x nheight) — decided by
+ * walking every tap of every window and comparing with IEEE division — else 0 (they then divide the IEEE way). */
+int ipb_scaled_division_check(size_t width, size_t height, size_t nwidth, size_t nheight);
 /* Host-resident source and/or destination: output_8bit / output_16bit cut the frame into bands of about `megabytes`
  * of PCIe traffic and overlap the H2D copy, the kernel and the D2H copy of neighbouring bands on three streams
  * (default 16: lowest latency of a single call).  0 = one band: whole-frame copies, which use the PCIe link better

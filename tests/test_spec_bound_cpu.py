@@ -49,3 +49,19 @@ def test_parameters_outside_the_measured_range_are_refused(ip):
     (IPB_ERR_UNSUPPORTED) and the pipeline takes the exact kernel."""
     rc, _ = bound(ip, matrix=common.CAM_TO_XYZ * np.float32(8.0))
     assert rc != 0
+
+
+def test_scaled_division_check(ip):
+    """ipb_scaled_division_check walks every tap of every window of a geometry: the reciprocal form of delta / skip
+    (scaling.rs:94-98) equals IEEE division for BASELINE config 4 and for every geometry of a random sample (the form
+    only fails for pathological divisors; the kernels divide the IEEE way when the check says 0); degenerate sizes: 0."""
+    import random
+    L = ip.lib()
+    assert L.ipb_scaled_division_check(6000, 4000, 1500, 1000) == 1
+    assert L.ipb_scaled_division_check(6000, 4000, 1, 1000) == 0
+    rnd = random.Random(7)
+    for _ in range(200):
+        w = rnd.randint(64, 9000)
+        nw = rnd.randint(max(2, w // 7 + 1), max(3, w // 2))
+        h = rnd.randint(64, 6000)
+        assert L.ipb_scaled_division_check(w, h, nw, max(2, h * nw // w)) == 1, (w, h, nw)
