@@ -1,4 +1,5 @@
-// ipb_spec.cu — the speculative 8-bit raw -> sRGB kernel (the roofline kernel of BASELINE config 2 / 5).
+// ipb_spec.cu — the speculative 8-bit raw -> sRGB kernels: k_spec8 (full resolution: the roofline kernel of BASELINE
+// configs 2, 3 and 5) and k_spec8_scaled (behind scaled_demosaic: config 4, further down).
 //
 // output_8bit of a full-resolution RGB Bayer frame is a function  u16 CFA samples -> 3 bytes per pixel.  The bytes
 // are decided by which of the 255 thresholds of  v -> output8bit(apply_srgb_gamma(clamp(v)))  (gamma.rs:21,
@@ -11,8 +12,8 @@
 //                to_lab -> basecurve -> from_lab collapsed to   t = f(v) + (S(f(Y)) - f(Y)),  v' = t^3   with S the
 //                basecurve in f-space read from a slope/intercept table, and the 8-bit gamma through a 32-bit
 //                {byte, threshold} table in fixed point.  Its linear value differs from the reference's by at most
-//                delta (derivation: DESIGN.md "speculative pass"; bound computed per launch on the host from the
-//                actual matrices and curve, ipb_host.cu spec_error_bound; measured by ipb_spec_probe).
+//                delta (derivation: DESIGN.md 3.1 "The bound"; computed per parameter set on the host from the actual
+//                matrices and curve, ipb_spec_host.cu spec_build; measured by ipb_pipeline_spec_probe).
 //   certificate  a channel whose cheap value is farther than delta from every threshold has, by monotonicity, exactly
 //                the reference's byte.  One add and one mask per channel produce byte and distance together.
 //   fix-up       pixels with a channel inside +-delta of a threshold (about 2 %), and the frame's border pixels, are
@@ -25,7 +26,9 @@
 // Tile pipeline as in k_fused_full: persistent CTAs, raw u16 boxes by TMA (cp.async.bulk.tensor.2d + mbarrier) one
 // tile ahead, conversion into a double-buffered f32 tile whose even and odd columns live in separate planes (so that
 // the two same-kind pixels of a four-pixel task sit in one aligned register pair and no window load has a bank
-// conflict), one __syncthreads per tile.
+// conflict), one __syncthreads per tile plus an immediate second one that frees the queue.  Three-colour patterns other
+// than RGB Bayer (X-Trans ...) take MODE 4: row-major tile, per-position tap masks, exact means, the same chain.  A
+// batch of frames of one geometry (BATCH) is one launch whose tile sequence runs through the frames.
 #include <cuda.h>
 
 #include "ipb_internal.h"
