@@ -181,6 +181,7 @@ def lib():
         "ipb_ctx_set_spec": (i, [vp, C.c_float, i]),
         "ipb_spec_bound": (i, [vp, C.c_float, C.POINTER(C.c_float)]),
         "ipb_scaled_division_check": (i, [sz, sz, sz, sz]),
+        "ipb_spec_tables": (i, [vp, C.c_float, C.c_float, vp, vp, vp, vp, vp, vp]),
         "ipb_ctx_spec_stats": (i, [vp, C.POINTER(C.c_ulonglong), i]),
         "ipb_pipeline_spec_probe": (i, [vp, C.POINTER(C.c_float), C.POINTER(C.c_double), C.POINTER(C.c_float)]),
         "ipb_selftest_gamma8": (i, [vp, C.POINTER(C.c_ulonglong)]),

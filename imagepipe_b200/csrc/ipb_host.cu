@@ -2383,6 +2383,33 @@ int ipb_ctx_spec_stats(ipb_ctx *ctx, unsigned long long out[4], int reset) {
   return IPB_OK;
 }
 
+int ipb_spec_tables(const ipb_ops *ops, float mufu_rel_err, float delta_override, uint32_t *g8a, float *thresholds, float one[3],
+                    uint32_t wmul[3], uint32_t *amb_t, float delta[4]) {
+  if (!ops || !g8a || !thresholds || !one || !wmul || !amb_t || !delta) return IPB_ERR_INVALID;
+  static std::once_flag once;
+  std::call_once(once, [] { if (!g_gamma8_ok && g_gamma8.empty()) g_gamma8_ok = build_gamma8(tables().fwd, &g_gamma8); });
+  if (!g_gamma8_ok) return IPB_ERR_UNSUPPORTED;
+  ColorParams P;
+  memset(&P, 0, sizeof(P));
+  fill_tolab(&P, &ops->tolab, 0);
+  P.use_e = 0;
+  if (!build_spline(&ops->basecurve, &P.sp)) return IPB_ERR_INVALID;
+  std::vector<float> thr;
+  for (const Gamma8Entry &g : g_gamma8)
+    if (g.thr <= 1.0f) thr.push_back(g.thr);
+  std::vector<uint32_t> tab;
+  std::vector<float2> stab;
+  SpecParams c;
+  const float black = ops->gofloat.blacklevels[0], range = ops->gofloat.whitelevels[0] - black;
+  if (!spec_build(P, black, range, mufu_rel_err, delta_override, thr, &tab, &stab, &c, delta)) return IPB_ERR_UNSUPPORTED;
+  if (thr.size() != 255 || tab.size() != (size_t)kSpecG8Entries) return IPB_ERR_UNSUPPORTED;
+  memcpy(g8a, tab.data(), tab.size() * sizeof(uint32_t));
+  memcpy(thresholds, thr.data(), 255 * sizeof(float));
+  for (int k = 0; k < 3; k++) { one[k] = c.one[k]; wmul[k] = c.wmul[k]; }
+  *amb_t = c.amb_t;
+  return IPB_OK;
+}
+
 int ipb_scaled_division_check(size_t width, size_t height, size_t nwidth, size_t nheight) {
   return scaled_skip_division_exact(width, height, nwidth, nheight) ? 1 : 0;
 }

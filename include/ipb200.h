@@ -275,6 +275,12 @@ int ipb_pipeline_spec_probe(ipb_pipeline *p, float *max_dev, double *mean_dev, f
  * parameters of `ops`, given the relative error of the XU-pipe cube root (ipb_ctx_spec_stats out[3] on a GPU box; the
  * hardware documentation's 2^-22 otherwise).  IPB_ERR_UNSUPPORTED when these parameters would run on the exact kernel. */
 int ipb_spec_bound(const ipb_ops *ops, float mufu_rel_err, float delta[4]);
+/* Diagnostic, host only: what the speculative kernels' 8-bit stage is built from for a parameter set — the fixed-point
+ * gamma table (8192 words), the 255 thresholds of output8bit(apply_srgb_gamma(v)) it encodes, and the constants of the
+ * certificate (ipb_spec.h SpecParams: one[], wmul[], amb_t) — so that table and certificate can be checked against the
+ * thresholds without a GPU (tests/test_spec_bound_cpu.py).  delta_override > 0 forces the bound. */
+int ipb_spec_tables(const ipb_ops *ops, float mufu_rel_err, float delta_override, uint32_t *g8a, float *thresholds,
+                    float one[3], uint32_t wmul[3], uint32_t *amb_t, float delta[4]);
 /* Diagnostic, host only: 1 when the scaled kernels may divide window coordinates by the skip (scaling.rs:94-98) in the
  * three-instruction reciprocal form for this geometry (cropped frame width x height -> nwidth x nheight) — decided by
  * walking every tap of every window and comparing with IEEE division — else 0 (they then divide the IEEE way). */

@@ -203,6 +203,7 @@ extern "C" {
     pub fn ipb_ctx_spec_stats(ctx: *mut ipb_ctx, out: *mut c_ulonglong, reset: c_int) -> c_int;
     pub fn ipb_pipeline_spec_probe(p: *mut ipb_pipeline, max_dev: *mut f32, mean_dev: *mut f64, delta: *mut f32) -> c_int;
     pub fn ipb_spec_bound(ops: *const ipb_ops, mufu_rel_err: f32, delta: *mut f32) -> c_int;
+    pub fn ipb_spec_tables(ops: *const ipb_ops, mufu_rel_err: f32, delta_override: f32, g8a: *mut u32, thresholds: *mut f32, one: *mut f32, wmul: *mut u32, amb_t: *mut u32, delta: *mut f32) -> c_int;
     pub fn ipb_scaled_division_check(width: usize, height: usize, nwidth: usize, nheight: usize) -> c_int;
     pub fn ipb_pipeline_set_band_mb(p: *mut ipb_pipeline, megabytes: c_int) -> c_int;
     pub fn ipb_pipeline_output_size(p: *mut ipb_pipeline, width: *mut usize, height: *mut usize) -> c_int;
